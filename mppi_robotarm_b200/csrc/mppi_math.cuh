@@ -1,0 +1,230 @@
+// mppi_math.cuh — FP32 arithmetic of one MPPI sample-step, shared by every kernel.
+//
+// Everything here is `__host__ __device__` with explicitly rounded operations (no compiler FMA
+// contraction decisions): the CUDA kernels and the CPU emulation used by the parity *tests*
+// (tests/emul) execute the same operation sequence.  The only device-specific pieces are the MUFU
+// approximations (reciprocal, and log2/sqrt/sin/cos inside the Gaussian generator).
+//
+// What is restated from the reference (file:line in /root/reference):
+//   arm dynamics + semi-implicit Euler ........ control.py:234-263 (twin: utils.py:14-29)
+//   forward kinematics on the cost side ....... control.py:178-179, 190-191, 206-207
+//   nearest waypoint, first arg-min of 30 ..... control.py:200-215
+//   stage / terminal tracking cost ............ control.py:174-198
+//   control cost gamma*u^T Sigma^-1 v ......... control.py:106
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define MPPI_HD __host__ __device__ __forceinline__
+#else
+#define MPPI_HD inline
+#endif
+
+namespace mppi {
+
+constexpr int kWindow = 30;       // SEARCH_IDX_LEN, control.py:203
+constexpr int kWindowPad = 32;    // table rows (two never-selected sentinels)
+constexpr int kFilter = 10;       // control.py:122
+constexpr float kSentinel = 3.0e38f;
+
+// ---- explicitly rounded primitives ---------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+MPPI_HD float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+MPPI_HD float mul_(float a, float b) { return __fmul_rn(a, b); }
+MPPI_HD float add_(float a, float b) { return __fadd_rn(a, b); }
+MPPI_HD float sub_(float a, float b) { return __fsub_rn(a, b); }
+MPPI_HD float rcp_(float a) {             // MUFU.RCP + one Newton step (<1 ulp)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    float e = __fmaf_rn(-a, r, 1.0f);
+    return __fmaf_rn(r, e, r);
+}
+MPPI_HD int f2i(float a) { return __float_as_int(a); }
+MPPI_HD float i2f(int a) { return __int_as_float(a); }
+#else
+MPPI_HD float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+MPPI_HD float mul_(float a, float b) { return a * b; }
+MPPI_HD float add_(float a, float b) { return a + b; }
+MPPI_HD float sub_(float a, float b) { return a - b; }
+MPPI_HD float rcp_(float a) { return 1.0f / a; }
+MPPI_HD int f2i(float a) { union { float f; int i; } u; u.f = a; return u.i; }
+MPPI_HD float i2f(int a) { union { float f; int i; } u; u.i = a; return u.f; }
+#endif
+
+// ---- sin & cos of one angle, ~1 ulp, no slow path --------------------------------------------
+// Cody-Waite reduction by pi/2 in three FMA steps, then degree-7 / degree-8 minimax polynomials on
+// [-pi/4, pi/4].  Valid for |x| < ~1e5 rad; a diverged rollout (larger angle, Inf, NaN) yields a
+// garbage-but-finite or NaN cost that the soft-min kernel maps to weight 0.
+MPPI_HD void sincos_(float x, float& s, float& c) {
+    const float kMagic = 12582912.0f;                      // 1.5 * 2^23: round-to-nearest trick
+    float kf = fma_(x, 0.636619772367581343f, kMagic);
+    int q = f2i(kf);                                       // low bits hold the quadrant
+    kf = sub_(kf, kMagic);
+    float r = fma_(kf, -1.57079601287841796875f, x);
+    r = fma_(kf, -3.1391647326017846e-07f, r);
+    r = fma_(kf, -5.3903025299577648e-15f, r);
+    float r2 = mul_(r, r);
+    // sin(r) = r + r*r2*(S1 + r2*(S2 + r2*S3))
+    float ps = fma_(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+    ps = fma_(ps, r2, -1.6666654611e-1f);
+    float sr = fma_(mul_(ps, r2), r, r);
+    // cos(r) = 1 + r2*(C0 + r2*(C1 + r2*(C2 + r2*C3)))
+    float pc = fma_(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    pc = fma_(pc, r2, 4.166664568298827e-2f);
+    pc = fma_(pc, r2, -0.5f);
+    float cr = fma_(pc, r2, 1.0f);
+    float ss = (q & 1) ? cr : sr;
+    float cc = (q & 1) ? sr : cr;
+    s = (q & 2) ? -ss : ss;
+    c = ((q + 1) & 2) ? -cc : cc;
+}
+
+// ---- per-controller constants (derived once on the host in FP64, rounded to FP32) -----------
+struct ArmF {
+    float A0, A1;        // M11 = A0 + A1*cos q2         (control.py:241-242)
+    float M22, B1;       // M12 = M22 + B1*cos q2; h = B1*sin q2   (control.py:243-244, 247)
+    float G1a, G1b;      // g1 = G1a*cos q1 + G1b*cos q12; g2 = G1b*cos q12   (control.py:248-249)
+    float dt;            // controller integration step (control.py:240)
+    float L1, L2;        // cost-side link lengths self.l1 / self.l2 (control.py:55-56)
+};
+
+struct CostW {           // weights already multiplied by 1e4 (control.py:185, 198)
+    float s0, s1, s2, s3;
+    float t0, t1, t2, t3;
+};
+
+struct WinEntry { float a, b, c, pad; };     // d_j - |p'|^2 = c + a*x' + b*y'   (local coordinates)
+struct RefRow { float rx, ry, rd1, rd2; };   // waypoint in local coordinates + reference joint rates
+struct StepCtl { float u1, u2, g1, g2; };    // nominal control and gamma*(u^T Sigma^-1)
+
+// Arm state carried through the horizon.  sin/cos of q1 and q1+q2 are kept from the previous step
+// (they were needed for its forward kinematics) so each step evaluates two sincos, not eight cos/sin.
+struct ArmState {
+    float q1, q2, d1, d2;
+    float s1, c1, s12, c12;
+};
+
+MPPI_HD void arm_init(ArmState& st, float q1, float q2, float d1, float d2) {
+    st.q1 = q1; st.q2 = q2; st.d1 = d1; st.d2 = d2;
+    sincos_(q1, st.s1, st.c1);
+    sincos_(add_(q1, q2), st.s12, st.c12);
+}
+
+// One integration step (control.py:241-259) under control (v1, v2).
+MPPI_HD void arm_step(ArmState& st, const ArmF& A, float v1, float v2) {
+    // cos/sin of q2 = (q1+q2) - q1 by the angle-difference identity
+    float c2 = fma_(st.c12, st.c1, mul_(st.s12, st.s1));
+    float s2 = fma_(st.s12, st.c1, -mul_(st.c12, st.s1));
+    float M11 = fma_(A.A1, c2, A.A0);
+    float M12 = fma_(A.B1, c2, A.M22);
+    float h = mul_(A.B1, s2);
+    float g2 = mul_(A.G1b, st.c12);
+    float g1 = fma_(A.G1a, st.c1, g2);
+    // v - C dq - G with C dq = [-h d2 (2 d1 + d2), h d1^2]
+    float tt = fma_(2.0f, st.d1, st.d2);
+    float b1 = fma_(mul_(h, st.d2), tt, sub_(v1, g1));
+    float b2 = fma_(-mul_(h, st.d1), st.d1, sub_(v2, g2));
+    float det = fma_(M11, A.M22, -mul_(M12, M12));
+    float idt = mul_(rcp_(det), A.dt);
+    float n1 = fma_(A.M22, b1, -mul_(M12, b2));
+    float n2 = fma_(M11, b2, -mul_(M12, b1));
+    st.d1 = fma_(n1, idt, st.d1);
+    st.d2 = fma_(n2, idt, st.d2);
+    st.q1 = fma_(st.d1, A.dt, st.q1);
+    st.q2 = fma_(st.d2, A.dt, st.q2);
+    sincos_(st.q1, st.s1, st.c1);
+    sincos_(add_(st.q1, st.q2), st.s12, st.c12);
+}
+
+// End-effector in window-local coordinates: (x - ox, y - oy), origin = first row of the window.
+MPPI_HD void fk_local(const ArmState& st, const ArmF& A, float ox, float oy, float& xl, float& yl) {
+    xl = fma_(A.L2, st.c12, fma_(A.L1, st.c1, -ox));
+    yl = fma_(A.L2, st.s12, fma_(A.L1, st.s1, -oy));
+}
+
+// Candidate key: distance (minus the common |p'|^2) with the candidate index in the 5 low mantissa
+// bits, so a plain float min returns value and arg-min together (FMNMX3 on sm_100a).
+MPPI_HD float cand_key(float a, float b, float c, float xl, float yl, int j) {
+    float d = fma_(a, xl, fma_(b, yl, c));
+    return i2f((f2i(d) & ~31) | j);
+}
+
+MPPI_HD float min3_(float a, float b, float c) { return fminf(fminf(a, b), c); }
+
+// Weighted squared residuals of (x, y, dq1, dq2) against one waypoint row (control.py:183-185).
+MPPI_HD void residuals(const ArmState& st, float xl, float yl, const RefRow& r,
+                       float& ex, float& ey, float& e1, float& e2) {
+    ex = sub_(xl, r.rx); ey = sub_(yl, r.ry); e1 = sub_(st.d1, r.rd1); e2 = sub_(st.d2, r.rd2);
+}
+MPPI_HD float wsq(float w0, float w1, float w2, float w3, float ex, float ey, float e1, float e2) {
+    float c = mul_(mul_(w0, ex), ex);
+    c = fma_(mul_(w1, ey), ey, c);
+    c = fma_(mul_(w2, e1), e1, c);
+    c = fma_(mul_(w3, e2), e2, c);
+    return c;
+}
+
+// ---- Philox4x32-10 counter-based generator (Salmon et al., SC'11; same constants as cuRAND) ----
+struct U4 { uint32_t x, y, z, w; };
+
+MPPI_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#if defined(__CUDA_ARCH__)
+    lo = a * b; hi = __umulhi(a, b);
+#else
+    uint64_t p = (uint64_t)a * b; lo = (uint32_t)p; hi = (uint32_t)(p >> 32);
+#endif
+}
+
+MPPI_HD U4 philox4x32_10(U4 ctr, uint32_t k0, uint32_t k1) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 10; ++i) {
+        uint32_t h0, l0, h1, l1;
+        mulhilo(0xD2511F53u, ctr.x, h0, l0);
+        mulhilo(0xCD9E8D57u, ctr.z, h1, l1);
+        U4 n = { h1 ^ ctr.y ^ k0, l1, h0 ^ ctr.w ^ k1, l0 };
+        ctr = n;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return ctr;
+}
+
+// Counter layout: x = horizon pair index (t/2), y = global sample index, z = control-step counter,
+// w = environment index.  Keyed on the GLOBAL sample index so results do not depend on how samples
+// are sharded over GPUs.  One call yields the noise of two consecutive horizon steps.
+struct NoiseCfg { uint32_t seed_lo, seed_hi; uint32_t step; float L11, L21, L22; };
+
+MPPI_HD float u01_(uint32_t x) {          // (0, 1]
+    return fma_((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+}
+
+// Box-Muller: two uniforms -> two independent N(0,1)
+MPPI_HD void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+    float u = u01_(a), v = u01_(b);
+#if defined(__CUDA_ARCH__)
+    float r = __fsqrt_rn(mul_(-1.3862943611198906f, __log2f(u)));     // sqrt(-2 ln u)
+    float sn, cs;
+    __sincosf(mul_(6.2831853071795865f, v), &sn, &cs);
+#else
+    float r = sqrtf(mul_(-1.3862943611198906f, log2f(u)));
+    float th = mul_(6.2831853071795865f, v);
+    float sn = sinf(th), cs = cosf(th);
+#endif
+    z0 = mul_(r, cs); z1 = mul_(r, sn);
+}
+
+// eps for horizon steps 2*pair and 2*pair+1 of global sample k (each a 2-vector ~ N(0, L L^T))
+MPPI_HD void noise_pair(const NoiseCfg& nc, uint32_t env, uint32_t k, uint32_t pair,
+                        float& e0a, float& e0b, float& e1a, float& e1b) {
+    U4 ctr = { pair, k, nc.step, env };
+    U4 r = philox4x32_10(ctr, nc.seed_lo, nc.seed_hi);
+    float z0, z1, z2, z3;
+    box_muller(r.x, r.y, z0, z1);
+    box_muller(r.z, r.w, z2, z3);
+    e0a = mul_(nc.L11, z0); e0b = fma_(nc.L21, z0, mul_(nc.L22, z1));
+    e1a = mul_(nc.L11, z2); e1b = fma_(nc.L21, z2, mul_(nc.L22, z3));
+}
+
+}  // namespace mppi

@@ -1,0 +1,513 @@
+// mppi_cabi.cu — host side of libmppi_b200.so: the C ABI declared in include/mppi_b200.h.
+// Orchestrates the sm_100a kernels of mppi_kernels.cuh for one control step
+// (reference: /root/reference/control.py:67-152).  No torch types, no exceptions, no CPU fallback.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <new>
+
+#include "../../include/mppi_b200.h"
+#define MPPI_MAX_T_INTERNAL MPPI_MAX_T
+#include "mppi_kernels.cuh"
+
+using namespace mppi;
+
+namespace {
+
+constexpr int kNumTimers = 6;        // prepare, rollout, softmin, wsum, reduce, finalize
+char g_create_error[512] = "";
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Workspace {
+    size_t bytes;
+    size_t off_ref, off_step_blocks, off_in, off_out, off_S, off_w, off_block_min, off_eta_part,
+        off_rho, off_v_part, off_partial;
+};
+
+}  // namespace
+
+struct MppiHandle {
+    MppiConfig cfg;
+    DevCfg dc;
+    MppiIoLayout io;
+    Workspace ws;
+    char* dev;                 // workspace base
+    char* host;                // pinned io block
+    DevIo dio;                 // device mirrors of the io block fields
+    size_t in_bytes, out_off, out_bytes;
+    int sm_count;
+    int n_ref_rows;
+    size_t roll_smem;
+    cudaEvent_t done;
+    cudaEvent_t tev[kNumTimers + 1];
+    bool timing, timing_pending;
+    double t_acc[kNumTimers];
+    int t_steps;
+    uint64_t launches;
+    cudaGraphExec_t graph_exec;
+    void* graph_stream;
+    uint64_t graph_kernels;
+    bool have_step;            // a step has run (step blocks valid)
+    char err[512];
+};
+
+namespace {
+
+int fail(MppiHandle* h, int code, const char* fmt, const char* detail) {
+    char* dst = h ? h->err : g_create_error;
+    snprintf(dst, 512, fmt, detail);
+    return code;
+}
+#define CU(h, call)                                                                        \
+    do {                                                                                   \
+        cudaError_t _e = (call);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            char _b[384];                                                                  \
+            snprintf(_b, sizeof(_b), "%s -> %s", #call, cudaGetErrorString(_e));           \
+            return fail(h, MPPI_ERR_CUDA, "%s", _b);                                       \
+        }                                                                                  \
+    } while (0)
+
+bool valid_cfg(const MppiConfig* c, const char** why) {
+    if (!c) { *why = "null config"; return false; }
+    if (c->abi_version != MPPI_ABI_VERSION) { *why = "abi_version mismatch"; return false; }
+    if (c->n_env < 1) { *why = "n_env < 1"; return false; }
+    if (c->T < 1 || c->T > MPPI_MAX_T) { *why = "T out of range [1, MPPI_MAX_T]"; return false; }
+    if (c->K_total < 1 || c->K_local < 1 || c->k_offset < 0 || c->k_offset + c->K_local > c->K_total) {
+        *why = "sample shard [k_offset, k_offset+K_local) not inside [0, K_total)"; return false;
+    }
+    if (c->max_ref_rows < 2) { *why = "max_ref_rows < 2"; return false; }
+    if (!(c->param_lambda > 0.0)) { *why = "param_lambda must be > 0"; return false; }
+    return true;
+}
+
+void grid_sizes(const MppiConfig* c, int sm, int* g_roll, int* g_soft, int* g_wsum) {
+    const int K = c->K_local;
+    int gr = (K + kRollThreads - 1) / kRollThreads;
+    if (gr > 32768) gr = 32768;
+    *g_roll = gr;
+    int gs = (K + kSoftThreads * 4 - 1) / (kSoftThreads * 4);
+    const int cap = (4 * sm + c->n_env - 1) / c->n_env;
+    if (gs > cap) gs = cap;
+    if (gs < 1) gs = 1;
+    *g_soft = gs;
+    int gw = (K + 2047) / 2048;
+    if (gw > cap) gw = cap;
+    if (gw < 1) gw = 1;
+    *g_wsum = gw;
+}
+
+void carve(const MppiConfig* c, int sm, Workspace* w) {
+    int g_roll, g_soft, g_wsum;
+    grid_sizes(c, sm, &g_roll, &g_soft, &g_wsum);
+    const size_t E = c->n_env, K = c->K_local, T = c->T;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    w->off_ref = take((size_t)c->max_ref_rows * 4 * sizeof(double));
+    w->off_step_blocks = take(E * (64 + 1024 + 16 * T));
+    MppiIoLayout io; mppi_io_layout(c, &io);
+    w->off_in = take(io.off_new_idx);                 // inputs occupy [0, off_new_idx)
+    w->off_out = take(io.bytes - io.off_new_idx);
+    w->off_S = take(E * K * sizeof(float));
+    w->off_w = take(E * K * sizeof(float));
+    w->off_block_min = take(E * g_roll * sizeof(float));
+    w->off_eta_part = take(E * g_soft * sizeof(double));
+    w->off_rho = take(E * sizeof(float));
+    w->off_v_part = take(E * g_wsum * 2 * T * sizeof(float));
+    w->off_partial = take(E * (2 + 2 * T) * sizeof(double));
+    w->bytes = off;
+}
+
+int sm_count_or_default(int device) {
+    int sm = 0;
+    if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sm <= 0) {
+        cudaGetLastError();
+        sm = 148;                                     // B200; only used for sizing without a device
+    }
+    return sm;
+}
+
+void fill_dev_cfg(MppiHandle* h) {
+    const MppiConfig& c = h->cfg;
+    DevCfg& d = h->dc;
+    const double m1 = c.arm[0], m2 = c.arm[1], l1 = c.arm[2], l2 = c.arm[3], lc1 = c.arm[4], lc2 = c.arm[5],
+                 g = c.arm[6];
+    // control.py:241-249 with the constant sub-expressions folded in FP64
+    d.arm.A0 = (float)(m1 * lc1 * lc1 + l1 + m2 * (l1 * l1 + lc2 * lc2) + l2);
+    d.arm.A1 = (float)(2 * m2 * l1 * lc2);
+    d.arm.M22 = (float)(m2 * lc2 * lc2 + l2);
+    d.arm.B1 = (float)(m2 * l1 * lc2);
+    d.arm.G1a = (float)((m1 * lc1 + m2 * l1) * g);
+    d.arm.G1b = (float)(m2 * lc2 * g);
+    d.arm.dt = (float)c.delta_t;
+    d.arm.L1 = (float)c.cost_l1; d.arm.L2 = (float)c.cost_l2;
+    d.cost.s0 = (float)(c.stage_cost_weight[0] * 1e4); d.cost.s1 = (float)(c.stage_cost_weight[1] * 1e4);
+    d.cost.s2 = (float)(c.stage_cost_weight[2] * 1e4); d.cost.s3 = (float)(c.stage_cost_weight[3] * 1e4);
+    d.cost.t0 = (float)(c.terminal_cost_weight[0] * 1e4); d.cost.t1 = (float)(c.terminal_cost_weight[1] * 1e4);
+    d.cost.t2 = (float)(c.terminal_cost_weight[2] * 1e4); d.cost.t3 = (float)(c.terminal_cost_weight[3] * 1e4);
+    d.noise.seed_lo = (uint32_t)(c.seed & 0xffffffffu); d.noise.seed_hi = (uint32_t)(c.seed >> 32);
+    d.noise.step = 0;
+    d.noise.L11 = (float)c.sigma_chol[0]; d.noise.L21 = (float)c.sigma_chol[2]; d.noise.L22 = (float)c.sigma_chol[3];
+    d.K_local = c.K_local; d.K_total = c.K_total; d.k_offset = c.k_offset; d.T = c.T; d.n_env = c.n_env;
+    d.n_exploit = c.n_exploit; d.n_ref_rows = 0; d.flags = c.flags;
+    d.step_block_bytes = 64 + 1024 + 16 * c.T;
+    grid_sizes(&c, h->sm_count, &d.g_roll, &d.g_soft, &d.g_wsum);
+    d.gamma = c.param_gamma; d.lambda = c.param_lambda; d.inv_lambda = 1.0 / c.param_lambda;
+    for (int i = 0; i < 4; ++i) d.sig_inv[i] = c.sigma_inv[i];
+    d.cost_l1 = c.cost_l1; d.cost_l2 = c.cost_l2;
+}
+
+// enqueue everything up to this shard's partial triple
+int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* partial_dev, cudaStream_t s,
+                  bool timed) {
+    const DevCfg& dc = h->dc;
+    char* ws = h->dev;
+    if (noise_mode != MPPI_NOISE_PHILOX && noise_mode != MPPI_NOISE_INJECTED)
+        return fail(h, MPPI_ERR_INVALID, "%s", "unknown noise mode");
+    if (noise_mode == MPPI_NOISE_INJECTED && !eps_dev)
+        return fail(h, MPPI_ERR_INVALID, "%s", "injected noise mode needs eps_dev");
+    if (h->n_ref_rows < 2) return fail(h, MPPI_ERR_INVALID, "%s", "mppi_set_ref_path() has not been called");
+    const uint64_t* step_ctr = (const uint64_t*)(ws + h->ws.off_in + h->io.off_step);
+    char* step_blocks = ws + h->ws.off_step_blocks;
+    float* S = (float*)(ws + h->ws.off_S);
+    float* w = (float*)(ws + h->ws.off_w);
+    float* bmin = (float*)(ws + h->ws.off_block_min);
+    double* eta_part = (double*)(ws + h->ws.off_eta_part);
+    float* rho = (float*)(ws + h->ws.off_rho);
+    float* v_part = (float*)(ws + h->ws.off_v_part);
+    const double* ref = (const double*)(ws + h->ws.off_ref);
+
+    CU(h, cudaMemcpyAsync(ws + h->ws.off_in, h->host, h->in_bytes, cudaMemcpyHostToDevice, s));
+    if (timed) CU(h, cudaEventRecord(h->tev[0], s));
+    mppi_prepare_sm100a<<<dc.n_env, 32, 0, s>>>(dc, h->dio, ref, step_blocks);
+    if (timed) CU(h, cudaEventRecord(h->tev[1], s));
+    {
+        dim3 grid(dc.g_roll, dc.n_env);
+        if (noise_mode == MPPI_NOISE_PHILOX)
+            mppi_rollout_sm100a<0><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, nullptr, S, bmin);
+        else
+            mppi_rollout_sm100a<1><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, eps_dev, S, bmin);
+    }
+    if (timed) CU(h, cudaEventRecord(h->tev[2], s));
+    mppi_softmin_sm100a<<<dim3(dc.g_soft, dc.n_env), kSoftThreads, 0, s>>>(dc, S, bmin, w, eta_part, rho);
+    if (timed) CU(h, cudaEventRecord(h->tev[3], s));
+    {
+        dim3 grid(dc.g_wsum, dc.n_env);
+        if (noise_mode == MPPI_NOISE_PHILOX) {
+            const size_t sm = (size_t)(kWsumThreads / 32) * ((dc.T + 1) / 2) * sizeof(float4);
+            mppi_wsum_philox_sm100a<<<grid, kWsumThreads, sm, s>>>(dc, step_ctr, w, v_part);
+        } else if ((dc.T & 1) == 0 && (((uintptr_t)eps_dev) & 15) == 0) {
+            mppi_wsum_injected_sm100a<float4><<<grid, kWsumThreads, kWsumThreads * sizeof(float4), s>>>(dc, w, eps_dev, v_part);
+        } else {
+            mppi_wsum_injected_sm100a<float2><<<grid, kWsumThreads, kWsumThreads * sizeof(float2), s>>>(dc, w, eps_dev, v_part);
+        }
+    }
+    if (timed) CU(h, cudaEventRecord(h->tev[4], s));
+    mppi_reduce_sm100a<<<dc.n_env, 256, 0, s>>>(dc, rho, eta_part, v_part, partial_dev);
+    if (timed) CU(h, cudaEventRecord(h->tev[5], s));
+    CU(h, cudaGetLastError());
+    h->launches += 5;
+    h->have_step = true;
+    return MPPI_OK;
+}
+
+int enqueue_combine(MppiHandle* h, const double* gathered_dev, int world, cudaStream_t s, bool timed) {
+    if (world < 1 || world > 64) return fail(h, MPPI_ERR_INVALID, "%s", "world must be in [1, 64]");
+    mppi_finalize_sm100a<<<h->dc.n_env, 256, 0, s>>>(h->dc, h->dio, gathered_dev, world);
+    if (timed) CU(h, cudaEventRecord(h->tev[6], s));
+    CU(h, cudaGetLastError());
+    CU(h, cudaMemcpyAsync(h->host + h->out_off, h->dev + h->ws.off_out, h->out_bytes, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaEventRecord(h->done, s));
+    h->launches += 1;
+    return MPPI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mppi_abi_version(void) { return MPPI_ABI_VERSION; }
+
+int mppi_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+int mppi_io_layout(const MppiConfig* c, MppiIoLayout* o) {
+    const char* why = nullptr;
+    if (!o || !valid_cfg(c, &why)) return fail(nullptr, MPPI_ERR_INVALID, "%s", why ? why : "null layout");
+    const size_t E = c->n_env, T = c->T;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t r = off; off = align_up(off + bytes, 16); return r; };
+    o->off_x0 = take(E * 4 * sizeof(double));
+    o->off_u_prev = take(E * T * 2 * sizeof(double));
+    o->off_prev_idx = take(E * sizeof(int32_t));
+    o->off_step = take(sizeof(uint64_t));
+    off = align_up(off, 256);
+    o->off_new_idx = take(E * sizeof(int32_t));
+    o->off_rho = take(E * sizeof(double));
+    o->off_eta = take(E * sizeof(double));
+    o->off_w_eps_raw = take(E * T * 2 * sizeof(double));
+    o->off_w_eps_filt = take(E * T * 2 * sizeof(double));
+    o->off_u_new = take(E * T * 2 * sizeof(double));
+    o->off_opt_traj = take(E * T * 4 * sizeof(double));
+    o->bytes = align_up(off, 256);
+    return MPPI_OK;
+}
+
+size_t mppi_workspace_bytes(const MppiConfig* c) {
+    const char* why = nullptr;
+    if (!valid_cfg(c, &why)) { fail(nullptr, MPPI_ERR_INVALID, "%s", why); return 0; }
+    Workspace w;
+    carve(c, sm_count_or_default(c->device), &w);
+    return w.bytes;
+}
+
+int mppi_create(const MppiConfig* c, void* workspace, size_t workspace_bytes, void* io_host, size_t io_bytes,
+                MppiHandle** out) {
+    const char* why = nullptr;
+    if (!out) return fail(nullptr, MPPI_ERR_INVALID, "%s", "null out");
+    *out = nullptr;
+    if (!valid_cfg(c, &why)) return fail(nullptr, MPPI_ERR_INVALID, "%s", why);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || c->device < 0 || c->device >= ndev) {
+        cudaGetLastError();
+        return fail(nullptr, MPPI_ERR_NO_DEVICE, "%s",
+                    "no usable CUDA device: libmppi_b200 is sm_100a only and has no CPU fallback");
+    }
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, c->device);
+    if (major != 10)
+        return fail(nullptr, MPPI_ERR_NO_DEVICE, "%s", "device is not compute capability 10.x (B200, sm_100a)");
+    MppiHandle* h = new (std::nothrow) MppiHandle();
+    if (!h) return fail(nullptr, MPPI_ERR_INVALID, "%s", "out of host memory");
+    memset(h, 0, sizeof(*h));
+    h->cfg = *c;
+    CU(nullptr, cudaSetDevice(c->device));
+    h->sm_count = sm_count_or_default(c->device);
+    mppi_io_layout(c, &h->io);
+    carve(c, h->sm_count, &h->ws);
+    if (!workspace || workspace_bytes < h->ws.bytes || ((uintptr_t)workspace & 255) != 0) {
+        delete h;
+        return fail(nullptr, MPPI_ERR_WORKSPACE, "%s", "workspace missing, too small or not 256-byte aligned");
+    }
+    if (!io_host || io_bytes < h->io.bytes) {
+        delete h;
+        return fail(nullptr, MPPI_ERR_WORKSPACE, "%s", "io block missing or too small");
+    }
+    h->dev = (char*)workspace;
+    h->host = (char*)io_host;
+    h->in_bytes = h->io.off_new_idx;
+    h->out_off = h->io.off_new_idx;
+    h->out_bytes = h->io.bytes - h->io.off_new_idx;
+    fill_dev_cfg(h);
+    char* din = h->dev + h->ws.off_in;
+    char* dout = h->dev + h->ws.off_out - h->io.off_new_idx;      // same offsets as the host block
+    h->dio.x0 = (const double*)(din + h->io.off_x0);
+    h->dio.u_prev = (const double*)(din + h->io.off_u_prev);
+    h->dio.prev_idx = (const int32_t*)(din + h->io.off_prev_idx);
+    h->dio.step = (const uint64_t*)(din + h->io.off_step);
+    h->dio.new_idx = (int32_t*)(dout + h->io.off_new_idx);
+    h->dio.rho = (double*)(dout + h->io.off_rho);
+    h->dio.eta = (double*)(dout + h->io.off_eta);
+    h->dio.w_eps_raw = (double*)(dout + h->io.off_w_eps_raw);
+    h->dio.w_eps_filt = (double*)(dout + h->io.off_w_eps_filt);
+    h->dio.u_new = (double*)(dout + h->io.off_u_new);
+    h->dio.opt_traj = (double*)(dout + h->io.off_opt_traj);
+    h->roll_smem = (size_t)h->dc.step_block_bytes;
+    cudaError_t e = cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming);
+    for (int i = 0; i <= kNumTimers && e == cudaSuccess; ++i) e = cudaEventCreate(&h->tev[i]);
+    if (e != cudaSuccess) {
+        snprintf(g_create_error, sizeof(g_create_error), "cudaEventCreate -> %s", cudaGetErrorString(e));
+        delete h;
+        return MPPI_ERR_CUDA;
+    }
+    *out = h;
+    return MPPI_OK;
+}
+
+void mppi_destroy(MppiHandle* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->done) cudaEventDestroy(h->done);
+    for (int i = 0; i <= kNumTimers; ++i)
+        if (h->tev[i]) cudaEventDestroy(h->tev[i]);
+    delete h;
+}
+
+const char* mppi_last_error(const MppiHandle* h) { return h ? h->err : g_create_error; }
+
+int mppi_set_ref_path(MppiHandle* h, const double* ref, int32_t n_rows) {
+    if (!h) return MPPI_ERR_INVALID;
+    if (!ref || n_rows < 2 || n_rows > h->cfg.max_ref_rows)
+        return fail(h, MPPI_ERR_INVALID, "%s", "ref path needs 2..max_ref_rows rows of (x, y, dq1, dq2)");
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaMemcpy(h->dev + h->ws.off_ref, ref, (size_t)n_rows * 4 * sizeof(double), cudaMemcpyHostToDevice));
+    h->n_ref_rows = n_rows;
+    h->dc.n_ref_rows = n_rows;
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    return MPPI_OK;
+}
+
+int mppi_step_local(MppiHandle* h, int32_t noise_mode, const float* eps_dev, double* partial_dev, void* stream) {
+    if (!h) return MPPI_ERR_INVALID;
+    if (!partial_dev) return fail(h, MPPI_ERR_INVALID, "%s", "null partial_dev");
+    h->timing_pending = false;
+    return enqueue_local(h, noise_mode, eps_dev, partial_dev, (cudaStream_t)stream, false);
+}
+
+int mppi_step_combine(MppiHandle* h, const double* gathered_dev, int32_t world, void* stream) {
+    if (!h) return MPPI_ERR_INVALID;
+    if (!gathered_dev) return fail(h, MPPI_ERR_INVALID, "%s", "null gathered_dev");
+    return enqueue_combine(h, gathered_dev, world, (cudaStream_t)stream, false);
+}
+
+int mppi_step(MppiHandle* h, int32_t noise_mode, const float* eps_dev, void* stream) {
+    if (!h) return MPPI_ERR_INVALID;
+    if (h->cfg.K_local != h->cfg.K_total)
+        return fail(h, MPPI_ERR_INVALID, "%s", "mppi_step needs the whole sample set on this handle; use mppi_step_local/combine");
+    cudaStream_t s = (cudaStream_t)stream;
+    double* partial = (double*)(h->dev + h->ws.off_partial);
+    const bool use_graph = (h->cfg.flags & MPPI_FLAG_DEVICE_GRAPH) && noise_mode == MPPI_NOISE_PHILOX &&
+                           !h->timing && s != nullptr;
+    if (use_graph) {
+        if (!h->graph_exec || h->graph_stream != stream) {
+            if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+            const uint64_t before = h->launches;
+            cudaGraph_t g = nullptr;
+            CU(h, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            int rc = enqueue_local(h, noise_mode, nullptr, partial, s, false);
+            if (rc == MPPI_OK) rc = enqueue_combine(h, partial, 1, s, false);
+            cudaError_t ce = cudaStreamEndCapture(s, &g);
+            if (rc != MPPI_OK) { if (g) cudaGraphDestroy(g); return rc; }
+            CU(h, ce);
+            CU(h, cudaGraphInstantiate(&h->graph_exec, g, 0));
+            cudaGraphDestroy(g);
+            h->graph_kernels = h->launches - before;
+            h->launches = before;
+            h->graph_stream = stream;
+        }
+        CU(h, cudaGraphLaunch(h->graph_exec, s));
+        h->launches += h->graph_kernels;
+        h->timing_pending = false;
+        return MPPI_OK;
+    }
+    int rc = enqueue_local(h, noise_mode, eps_dev, partial, s, h->timing);
+    if (rc != MPPI_OK) return rc;
+    rc = enqueue_combine(h, partial, 1, s, h->timing);
+    h->timing_pending = h->timing && rc == MPPI_OK;
+    return rc;
+}
+
+int mppi_wait(MppiHandle* h) {
+    if (!h) return MPPI_ERR_INVALID;
+    CU(h, cudaEventSynchronize(h->done));
+    if (h->timing_pending) {
+        for (int i = 0; i < kNumTimers; ++i) {
+            float ms = 0.f;
+            CU(h, cudaEventElapsedTime(&ms, h->tev[i], h->tev[i + 1]));
+            h->t_acc[i] += (double)ms * 1e3;
+        }
+        h->t_steps += 1;
+        h->timing_pending = false;
+    }
+    return MPPI_OK;
+}
+
+int mppi_last_costs(MppiHandle* h, const float** S_dev, const float** w_dev) {
+    if (!h) return MPPI_ERR_INVALID;
+    if (!h->have_step) return fail(h, MPPI_ERR_INVALID, "%s", "no step has run yet");
+    if (S_dev) *S_dev = (const float*)(h->dev + h->ws.off_S);
+    if (w_dev) *w_dev = (const float*)(h->dev + h->ws.off_w);
+    return MPPI_OK;
+}
+
+int mppi_sampled_trajectories(MppiHandle* h, int32_t noise_mode, const float* eps_dev, float* traj_dev, void* stream) {
+    if (!h) return MPPI_ERR_INVALID;
+    if (!h->have_step) return fail(h, MPPI_ERR_INVALID, "%s", "no step has run yet");
+    if (!traj_dev) return fail(h, MPPI_ERR_INVALID, "%s", "null traj_dev");
+    if (noise_mode == MPPI_NOISE_INJECTED && !eps_dev) return fail(h, MPPI_ERR_INVALID, "%s", "injected noise mode needs eps_dev");
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint64_t* step_ctr = (const uint64_t*)(h->dev + h->ws.off_in + h->io.off_step);
+    const char* step_blocks = h->dev + h->ws.off_step_blocks;
+    dim3 grid((h->dc.K_local + 127) / 128, h->dc.n_env);
+    if (noise_mode == MPPI_NOISE_PHILOX)
+        mppi_sampled_traj_sm100a<0><<<grid, 128, 0, s>>>(h->dc, step_ctr, step_blocks, nullptr, traj_dev);
+    else
+        mppi_sampled_traj_sm100a<1><<<grid, 128, 0, s>>>(h->dc, step_ctr, step_blocks, eps_dev, traj_dev);
+    CU(h, cudaGetLastError());
+    h->launches += 1;
+    return MPPI_OK;
+}
+
+int mppi_philox_noise(MppiHandle* h, uint64_t step, float* eps_dev, void* stream) {
+    if (!h) return MPPI_ERR_INVALID;
+    if (!eps_dev) return fail(h, MPPI_ERR_INVALID, "%s", "null eps_dev");
+    const long long n = (long long)h->dc.K_local * ((h->dc.T + 1) / 2);
+    dim3 grid((unsigned)((n + 255) / 256), h->dc.n_env);
+    mppi_philox_export_sm100a<<<grid, 256, 0, (cudaStream_t)stream>>>(h->dc, (uint32_t)step, eps_dev);
+    CU(h, cudaGetLastError());
+    h->launches += 1;
+    return MPPI_OK;
+}
+
+uint64_t mppi_launch_count(const MppiHandle* h) { return h ? h->launches : 0; }
+
+int mppi_set_timing(MppiHandle* h, int32_t enable) {
+    if (!h) return MPPI_ERR_INVALID;
+    h->timing = enable != 0;
+    h->timing_pending = false;
+    for (int i = 0; i < kNumTimers; ++i) h->t_acc[i] = 0.0;
+    h->t_steps = 0;
+    return MPPI_OK;
+}
+
+int mppi_get_timing(MppiHandle* h, double* out_us, int32_t n) {
+    if (!h || !out_us) return MPPI_ERR_INVALID;
+    for (int i = 0; i < n && i < kNumTimers; ++i) out_us[i] = h->t_steps ? h->t_acc[i] / h->t_steps : 0.0;
+    return h->t_steps;
+}
+
+int mppi_probe_fp32(int32_t device, double ms, double* fma_flops, double* mufu_ops) {
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return MPPI_ERR_NO_DEVICE; }
+    int sm = sm_count_or_default(device);
+    float* out = nullptr;
+    const int blocks = sm * 8, threads = 256;
+    if (cudaMalloc(&out, (size_t)blocks * threads * sizeof(float)) != cudaSuccess) return MPPI_ERR_CUDA;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    int rc = MPPI_OK;
+    for (int which = 0; which < 2; ++which) {
+        int iters = 256;
+        double best = 0.0, spent = 0.0;
+        for (int rep = 0; rep < 64 && spent < ms; ++rep) {
+            cudaEventRecord(a);
+            if (which == 0) mppi_probe_fma_sm100a<<<blocks, threads>>>(out, iters, 0.999f, 1e-3f);
+            else mppi_probe_mufu_sm100a<<<blocks, threads>>>(out, iters);
+            cudaEventRecord(b);
+            if (cudaEventSynchronize(b) != cudaSuccess) { rc = MPPI_ERR_CUDA; break; }
+            float t = 0.f; cudaEventElapsedTime(&t, a, b);
+            spent += t;
+            const double ops = (double)blocks * threads * iters * 16.0 * (which == 0 ? 8.0 * 2.0 : 4.0);
+            const double rate = ops / (t * 1e-3);
+            if (rep > 0 && rate > best) best = rate;
+            if (t < 5.0f) iters *= 2;
+        }
+        if (which == 0 && fma_flops) *fma_flops = best;
+        if (which == 1 && mufu_ops) *mufu_ops = best;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(out);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,595 @@
+// mppi_kernels.cuh — sm_100a kernels of the MPPI step (included by mppi_cabi.cu only).
+//
+//   mppi_prepare_sm100a    waypoint update in FP64 + step-block tables       control.py:75, 200-232
+//   mppi_rollout_sm100a    K fused rollouts, costs only                       control.py:84-109
+//   mppi_softmin_sm100a    min / exp / partial normaliser                     control.py:297-314
+//   mppi_wsum_*_sm100a     weighted noise sum, K x (T*2) reduction            control.py:115-118
+//   mppi_reduce_sm100a     this GPU's partial (rho_g, eta_g, V_g)             (sharding)
+//   mppi_finalize_sm100a   combine, median filter, update, optimal rollout    control.py:122-134
+//   mppi_sampled_traj_sm100a  trajectories of all samples                     control.py:137-145
+//   mppi_philox_export_sm100a the noise tensor the kernels draw               control.py:154-164
+//
+// Data layout in HBM (per environment e): step block = 64 B header | 32 x WinEntry | 32 x RefRow |
+// T x StepCtl (contiguous, 16-byte aligned, moved into shared memory with ONE 1-D TMA bulk copy);
+// costs S[e][K_local] and weights w[e][K_local] float32; injected noise eps[e][K_local][T][2]
+// float32 (the reference's own [K,T,2] layout, control.py:84).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "mppi_math.cuh"
+
+namespace mppi {
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                     " selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ bool finite_(float x) { return fabsf(x) <= 3.4028234e38f; }   // false for NaN/Inf
+
+// ------------------------------------------------------------------------------------------------
+// constants of one controller (kernel parameter, lives in the constant bank)
+// ------------------------------------------------------------------------------------------------
+struct DevCfg {
+    ArmF arm;
+    CostW cost;
+    NoiseCfg noise;            // .step is filled per launch from the input block
+    int K_local, K_total, k_offset, T, n_env, n_exploit, n_ref_rows, flags;
+    int step_block_bytes;      // 64 + 512 + 512 + 16*T
+    int g_roll, g_soft, g_wsum;   // blocks per environment of the three K-sized kernels
+    double gamma, lambda, inv_lambda;
+    double sig_inv[4];
+    double cost_l1, cost_l2;
+};
+
+struct StepBlockView {          // pointers into one environment's step block (global or shared)
+    StepHeader* hd; WinEntry* win; RefRow* rows; StepCtl* ctl;
+};
+__host__ __device__ __forceinline__ StepBlockView view_step_block(void* base) {
+    char* b = (char*)base;
+    StepBlockView v;
+    v.hd = (StepHeader*)b;
+    v.win = (WinEntry*)(b + 64);
+    v.rows = (RefRow*)(b + 64 + 16 * kWindowPad);
+    v.ctl = (StepCtl*)(b + 64 + 32 * kWindowPad);
+    return v;
+}
+
+// input block on the device (mirror of the caller's pinned block, see MppiIoLayout)
+struct DevIo {
+    const double* x0;        // [n_env][4]
+    const double* u_prev;    // [n_env][T][2]
+    const int32_t* prev_idx; // [n_env]
+    const uint64_t* step;    // [1]
+    int32_t* new_idx;        // [n_env]
+    double* rho; double* eta;            // [n_env]
+    double* w_eps_raw; double* w_eps_filt; double* u_new;   // [n_env][T][2]
+    double* opt_traj;                    // [n_env][T][4]
+};
+
+// ================================================================================================
+// 1. prepare: one warp per environment
+// ================================================================================================
+__global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, const double* __restrict__ ref,
+                                                          char* __restrict__ step_blocks) {
+    const int e = blockIdx.x, lane = threadIdx.x;
+    const double* x0 = io.x0 + 4 * e;
+    const int n = cfg.n_ref_rows;
+    int p = io.prev_idx[e];
+    p = max(0, min(p, n - 1));
+    // control.py:206-215 in FP64: end-effector, distances to the forward window, first arg-min
+    const double q1 = x0[0], q2 = x0[1];
+    const double x = cfg.cost_l1 * cos(q1) + cfg.cost_l2 * cos(q1 + q2);
+    const double y = cfg.cost_l1 * sin(q1) + cfg.cost_l2 * sin(q1 + q2);
+    double d = 1.0e300;
+    int j = lane;
+    if (lane < kWindow && p + lane < n) d = waypoint_d(ref, p + lane, x, y);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double d2 = __shfl_xor_sync(0xffffffffu, d, o);
+        const int j2 = __shfl_xor_sync(0xffffffffu, j, o);
+        if (d2 < d || (d2 == d && j2 < j)) { d = d2; j = j2; }
+    }
+    p += j;                                                  // control.py:230
+    StepBlockView sb = view_step_block(step_blocks + (size_t)e * cfg.step_block_bytes);
+    if (lane == 0) {
+        StepHeader h;
+        h.q1 = (float)x0[0]; h.q2 = (float)x0[1]; h.d1 = (float)x0[2]; h.d2 = (float)x0[3];
+        h.ox = (float)ref[4 * p]; h.oy = (float)ref[4 * p + 1];
+        h.win_start = p; h.n_valid = min(kWindow, n - p);
+        h.status = (p >= n - 1) ? 1 : 0;                     // control.py:76
+        for (int i = 0; i < 7; ++i) h.pad[i] = 0;
+        *sb.hd = h;
+        io.new_idx[e] = p;
+    }
+    {
+        WinEntry w; RefRow r;
+        make_window_row(ref, n, p, lane, w, r);
+        // the rollouts subtract the FP32 origin from the FP32 end-effector; rows are relative to
+        // the FP64 origin — the difference (<= 6e-8) is common to all candidates of a lookup
+        sb.win[lane] = w; sb.rows[lane] = r;
+    }
+    const double* u = io.u_prev + (size_t)e * cfg.T * 2;
+    for (int t = lane; t < cfg.T; t += 32) {
+        StepCtl c; make_step_ctl(u + 2 * t, cfg.gamma, cfg.sig_inv, c);
+        sb.ctl[t] = c;
+    }
+}
+
+// ================================================================================================
+// 2. fused rollout kernel: one thread per sample, step block staged in shared memory by TMA,
+//    window coefficients held in registers, only S[k] and one block-min reach HBM.
+// ================================================================================================
+constexpr int kRollThreads = 128;
+
+struct PhiloxNoise {            // eps drawn in-kernel: one Philox call serves two horizon steps
+    NoiseCfg nc; uint32_t env, k;
+    float e1a, e1b;
+    __device__ __forceinline__ void operator()(int t, float& a, float& b) {
+        if ((t & 1) == 0) noise_pair(nc, env, k, (uint32_t)t >> 1, a, b, e1a, e1b);
+        else { a = e1a; b = e1b; }
+    }
+};
+struct InjectedNoise {          // eps read from the caller's [K,T,2] tensor
+    const float2* row;
+    __device__ __forceinline__ void operator()(int t, float& a, float& b) const {
+        const float2 v = __ldg(row + t); a = v.x; b = v.y;
+    }
+};
+
+template <int NOISE>
+__global__ void __launch_bounds__(kRollThreads, 3)
+mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const char* __restrict__ step_blocks,
+                    const float* __restrict__ eps, float* __restrict__ S_out, float* __restrict__ block_min) {
+    extern __shared__ __align__(128) unsigned char smem_roll[];
+    unsigned char* smem = smem_roll;
+    __shared__ uint64_t bar;
+    __shared__ float red[kRollThreads / 32];
+    const int e = blockIdx.y, tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_expect_tx(&bar, (uint32_t)cfg.step_block_bytes);
+        tma_load_1d(smem, step_blocks + (size_t)e * cfg.step_block_bytes, (uint32_t)cfg.step_block_bytes, &bar);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    const StepBlockView sb = view_step_block(smem);
+    const StepHeader hd = *sb.hd;
+    float wa[kWindow], wb[kWindow], wc[kWindow];
+#pragma unroll
+    for (int j = 0; j < kWindow; ++j) { const WinEntry w = sb.win[j]; wa[j] = w.a; wb[j] = w.b; wc[j] = w.c; }
+
+    float tmin = INFINITY;
+    const int T = cfg.T;
+    for (int kl = blockIdx.x * kRollThreads + tid; kl < cfg.K_local; kl += gridDim.x * kRollThreads) {
+        const int kg = cfg.k_offset + kl;
+        const float um = kg < cfg.n_exploit ? 1.0f : 0.0f;
+        float S;
+        if (NOISE == 0) {
+            PhiloxNoise nz; nz.nc = cfg.noise; nz.nc.step = (uint32_t)(*step_ctr); nz.env = (uint32_t)e; nz.k = (uint32_t)kg;
+            S = rollout_cost(hd, cfg.arm, cfg.cost, wa, wb, wc, sb.rows, sb.ctl, T, um, nz);
+        } else {
+            InjectedNoise nz; nz.row = (const float2*)eps + ((size_t)e * cfg.K_local + kl) * T;
+            S = rollout_cost(hd, cfg.arm, cfg.cost, wa, wb, wc, sb.rows, sb.ctl, T, um, nz);
+        }
+        S_out[(size_t)e * cfg.K_local + kl] = S;
+        if (finite_(S)) tmin = fminf(tmin, S);
+    }
+    tmin = warp_min(tmin);
+    if ((tid & 31) == 0) red[tid >> 5] = tmin;
+    __syncthreads();
+    if (tid == 0) {
+        float m = red[0];
+#pragma unroll
+        for (int i = 1; i < kRollThreads / 32; ++i) m = fminf(m, red[i]);
+        block_min[(size_t)e * gridDim.x + blockIdx.x] = m;
+    }
+}
+
+// ================================================================================================
+// 3. soft-min: rho = min S (from the rollout's block minima), w~_k = exp(-(S_k - rho)/lambda),
+//    per-block partial sums of w~ (control.py:297-314).  Non-finite costs get weight 0.
+// ================================================================================================
+constexpr int kSoftThreads = 256;
+
+__global__ void __launch_bounds__(kSoftThreads)
+mppi_softmin_sm100a(DevCfg cfg, const float* __restrict__ S, const float* __restrict__ block_min,
+                    float* __restrict__ w, double* __restrict__ eta_part, float* __restrict__ rho_out) {
+    __shared__ float redf[kSoftThreads / 32];
+    __shared__ double redd[kSoftThreads / 32];
+    __shared__ float rho_s;
+    const int e = blockIdx.y, tid = threadIdx.x;
+    float m = INFINITY;
+    for (int i = tid; i < cfg.g_roll; i += kSoftThreads) m = fminf(m, block_min[(size_t)e * cfg.g_roll + i]);
+    m = warp_min(m);
+    if ((tid & 31) == 0) redf[tid >> 5] = m;
+    __syncthreads();
+    if (tid == 0) {
+        float r = redf[0];
+#pragma unroll
+        for (int i = 1; i < kSoftThreads / 32; ++i) r = fminf(r, redf[i]);
+        rho_s = r;
+        if (blockIdx.x == 0) rho_out[e] = r;
+    }
+    __syncthreads();
+    const float rho = rho_s;
+    const float nil = (float)(-cfg.inv_lambda);
+    const float* Se = S + (size_t)e * cfg.K_local;
+    float* we = w + (size_t)e * cfg.K_local;
+    double acc = 0.0;
+    for (int k = blockIdx.x * kSoftThreads + tid; k < cfg.K_local; k += gridDim.x * kSoftThreads) {
+        const float s = Se[k];
+        const float x = expf((s - rho) * nil);
+        const float wk = finite_(s) ? x : 0.0f;
+        we[k] = wk;
+        acc += (double)wk;
+    }
+    acc = warp_sum(acc);
+    if ((tid & 31) == 0) redd[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double r = 0.0;
+#pragma unroll
+        for (int i = 0; i < kSoftThreads / 32; ++i) r += redd[i];
+        eta_part[(size_t)e * gridDim.x + blockIdx.x] = r;
+    }
+}
+
+// ================================================================================================
+// 4a. weighted noise sum, injected noise: V[t,m] = sum_k w~_k eps[k,t,m]  (control.py:115-118).
+//     The K x (2T) matrix is read as a flat stream of VEC-wide words: thread (r, c) owns column c
+//     of every (R*gridDim.x)-th row, so consecutive threads read consecutive 16-byte words.
+//     Rows whose weight is exactly 0 are not read at all.
+// ================================================================================================
+constexpr int kWsumThreads = 256;
+
+template <typename VEC> struct VecOps;
+template <> struct VecOps<float4> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void fmadd(float4& a, float w, const float4& v) {
+        a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
+    }
+    static __device__ __forceinline__ void add(float4& a, const float4& v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+    static __device__ __forceinline__ float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    static __device__ __forceinline__ float4 ld(const float4* p) {
+        float4 v;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+        return v;
+    }
+};
+template <> struct VecOps<float2> {
+    static constexpr int N = 2;
+    static __device__ __forceinline__ void fmadd(float2& a, float w, const float2& v) {
+        a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y);
+    }
+    static __device__ __forceinline__ void add(float2& a, const float2& v) { a.x += v.x; a.y += v.y; }
+    static __device__ __forceinline__ float2 zero() { return make_float2(0.f, 0.f); }
+    static __device__ __forceinline__ float2 ld(const float2* p) { return __ldg(p); }
+};
+
+template <typename VEC>
+__global__ void __launch_bounds__(kWsumThreads)
+mppi_wsum_injected_sm100a(DevCfg cfg, const float* __restrict__ w, const float* __restrict__ eps,
+                          float* __restrict__ v_part) {
+    extern __shared__ __align__(16) unsigned char smem_wsum[];
+    VEC* sh = (VEC*)smem_wsum;
+    const int e = blockIdx.y, tid = threadIdx.x;
+    const int C = (2 * cfg.T) / VecOps<VEC>::N;               // words per row
+    const int R = kWsumThreads / C;                           // rows per pass of one block
+    const int r = tid / C, c = tid - r * C;
+    const bool active = r < R;
+    const float* we = w + (size_t)e * cfg.K_local;
+    const VEC* ee = (const VEC*)eps + (size_t)e * cfg.K_local * C;
+    VEC acc = VecOps<VEC>::zero();
+    if (active) {
+        const int stride = R * gridDim.x;
+        int k = blockIdx.x * R + r;
+        // 4 rows in flight per thread
+        for (; k + 3 * stride < cfg.K_local; k += 4 * stride) {
+            float wk[4]; VEC v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) wk[i] = __ldg(we + k + i * stride);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = wk[i] != 0.0f ? VecOps<VEC>::ld(ee + (size_t)(k + i * stride) * C + c) : VecOps<VEC>::zero();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) VecOps<VEC>::fmadd(acc, wk[i], v[i]);
+        }
+        for (; k < cfg.K_local; k += stride) {
+            const float wk = __ldg(we + k);
+            if (wk != 0.0f) VecOps<VEC>::fmadd(acc, wk, VecOps<VEC>::ld(ee + (size_t)k * C + c));
+        }
+        sh[r * C + c] = acc;
+    }
+    __syncthreads();
+    if (tid < C) {                                            // fixed-order sum over the R row slots
+        VEC s = sh[tid];
+        for (int i = 1; i < R; ++i) VecOps<VEC>::add(s, sh[i * C + tid]);
+        ((VEC*)(v_part + ((size_t)e * gridDim.x + blockIdx.x) * 2 * cfg.T))[tid] = s;
+    }
+}
+
+// ================================================================================================
+// 4b. weighted noise sum, Philox noise: eps is regenerated (bit-identical to the rollout kernel's
+//     draw: same noise_pair() on the same counters) only for samples with a non-zero weight.  A
+//     warp scans 32 weights at a time; for each non-zero one its lanes split the T/2 Philox calls.
+// ================================================================================================
+constexpr int kPairSlots = MPPI_MAX_T_INTERNAL / 2 / 32;      // Philox calls per lane and sample
+
+__global__ void __launch_bounds__(kWsumThreads)
+mppi_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const float* __restrict__ w,
+                        float* __restrict__ v_part) {
+    extern __shared__ __align__(16) unsigned char smem_wsum[];
+    float4* sh = (float4*)smem_wsum;                               // [warps][pairs]
+    const int e = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_pairs = (cfg.T + 1) >> 1;
+    NoiseCfg nc = cfg.noise; nc.step = (uint32_t)(*step_ctr);
+    const float* we = w + (size_t)e * cfg.K_local;
+    float4 acc[kPairSlots];
+#pragma unroll
+    for (int i = 0; i < kPairSlots; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int warps_total = gridDim.x * (kWsumThreads / 32);
+    for (int k0 = (blockIdx.x * (kWsumThreads / 32) + warp) * 32; k0 < cfg.K_local; k0 += warps_total * 32) {
+        const int k = k0 + lane;
+        const float wk = k < cfg.K_local ? we[k] : 0.0f;
+        unsigned mask = __ballot_sync(0xffffffffu, wk != 0.0f);
+        while (mask) {
+            const int b = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float wb = __shfl_sync(0xffffffffu, wk, b);
+            const uint32_t kg = (uint32_t)(cfg.k_offset + k0 + b);
+#pragma unroll
+            for (int i = 0; i < kPairSlots; ++i) {
+                const int pr = lane + 32 * i;
+                if (pr < n_pairs) {
+                    float a0, a1, b0, b1;
+                    noise_pair(nc, (uint32_t)e, kg, (uint32_t)pr, a0, a1, b0, b1);
+                    acc[i].x = fmaf(wb, a0, acc[i].x); acc[i].y = fmaf(wb, a1, acc[i].y);
+                    acc[i].z = fmaf(wb, b0, acc[i].z); acc[i].w = fmaf(wb, b1, acc[i].w);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kPairSlots; ++i) {
+        const int pr = lane + 32 * i;
+        if (pr < n_pairs) sh[warp * n_pairs + pr] = acc[i];
+    }
+    __syncthreads();
+    for (int pr = tid; pr < n_pairs; pr += kWsumThreads) {
+        float4 s = sh[pr];
+        for (int wv = 1; wv < kWsumThreads / 32; ++wv) {
+            const float4 v = sh[wv * n_pairs + pr];
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        float* dst = v_part + ((size_t)e * gridDim.x + blockIdx.x) * 2 * cfg.T + 4 * pr;
+        dst[0] = s.x; dst[1] = s.y;
+        if (2 * pr + 1 < cfg.T) { dst[2] = s.z; dst[3] = s.w; }
+    }
+}
+
+// ================================================================================================
+// 5. reduce: this GPU's partial triple per environment, FP64, fixed summation order.
+//    partial[e] = { rho_g, eta_g, V_g[2T] }
+// ================================================================================================
+__global__ void __launch_bounds__(256)
+mppi_reduce_sm100a(DevCfg cfg, const float* __restrict__ rho, const double* __restrict__ eta_part,
+                   const float* __restrict__ v_part, double* __restrict__ partial) {
+    __shared__ double red[8];
+    const int e = blockIdx.x, tid = threadIdx.x;
+    double* out = partial + (size_t)e * (2 + 2 * cfg.T);
+    double a = 0.0;
+    for (int i = tid; i < cfg.g_soft; i += 256) a += eta_part[(size_t)e * cfg.g_soft + i];
+    a = warp_sum(a);
+    if ((tid & 31) == 0) red[tid >> 5] = a;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        out[0] = (double)rho[e]; out[1] = s;
+    }
+    for (int c = tid; c < 2 * cfg.T; c += 256) {
+        double s = 0.0;
+        const float* src = v_part + (size_t)e * cfg.g_wsum * 2 * cfg.T + c;
+        for (int b = 0; b < cfg.g_wsum; ++b) s += (double)src[(size_t)b * 2 * cfg.T];
+        out[2 + c] = s;
+    }
+}
+
+// ================================================================================================
+// 6. finalize: combine the gathered partials of all ranks (identically on every rank), normalise,
+//    median-filter, update the sequence, roll the optimal trajectory out (control.py:122-134).
+// ================================================================================================
+__device__ __forceinline__ int reflect_idx(int i, int n) {          // scipy 'reflect': d c b a | a b c d | d c b a
+    const int period = 2 * n;
+    i %= period; if (i < 0) i += period;
+    return i >= n ? period - 1 - i : i;
+}
+
+__global__ void __launch_bounds__(256)
+mppi_finalize_sm100a(DevCfg cfg, DevIo io, const double* __restrict__ gathered, int world) {
+    __shared__ double raw[2 * MPPI_MAX_T_INTERNAL];
+    __shared__ double unew[2 * MPPI_MAX_T_INTERNAL];
+    __shared__ double scale[64];
+    __shared__ double eta_s;
+    const int e = blockIdx.x, tid = threadIdx.x, T = cfg.T;
+    const size_t stride_rank = (size_t)cfg.n_env * (2 + 2 * T);
+    const double* g0 = gathered + (size_t)e * (2 + 2 * T);
+    if (tid == 0) {
+        double rho = g0[0];
+        for (int g = 1; g < world; ++g) rho = fmin(rho, g0[g * stride_rank]);
+        double eta = 0.0;
+        for (int g = 0; g < world; ++g) {
+            // a shard with no finite cost reports rho_g = +inf and eta_g = 0
+            const double sg = exp(-(g0[g * stride_rank] - rho) * cfg.inv_lambda);
+            scale[g] = sg;
+            eta += sg * g0[g * stride_rank + 1];
+        }
+        eta_s = eta;
+        io.rho[e] = rho; io.eta[e] = eta;
+    }
+    __syncthreads();
+    for (int c = tid; c < 2 * T; c += blockDim.x) {
+        double v = 0.0;
+        for (int g = 0; g < world; ++g) {
+            const double sg = scale[g];
+            if (sg != 0.0) v += sg * g0[g * stride_rank + 2 + c];
+        }
+        v /= eta_s;
+        raw[c] = v;
+        io.w_eps_raw[(size_t)e * 2 * T + c] = v;
+    }
+    __syncthreads();
+    // scipy.ndimage.median_filter(size=10, mode='reflect') per column (control.py:319-327):
+    // window offsets -5..+4, output = element of rank 5 of the sorted window
+    for (int c = tid; c < 2 * T; c += blockDim.x) {
+        const int t = c >> 1, m = c & 1;
+        double win[kFilter];
+#pragma unroll
+        for (int o = 0; o < kFilter; ++o) win[o] = raw[2 * reflect_idx(t + o - kFilter / 2, T) + m];
+        double med = win[0];
+#pragma unroll
+        for (int a = 0; a < kFilter; ++a) {
+            int rank = 0;
+#pragma unroll
+            for (int b = 0; b < kFilter; ++b) rank += (win[b] < win[a]) || (win[b] == win[a] && b < a);
+            if (rank == kFilter / 2) med = win[a];
+        }
+        const double u = io.u_prev[(size_t)e * 2 * T + c] + med;        // control.py:126
+        unew[c] = u;
+        io.w_eps_filt[(size_t)e * 2 * T + c] = med;
+        io.u_new[(size_t)e * 2 * T + c] = u;
+    }
+    __syncthreads();
+    // control.py:129-134: x <- F(x, u[t-1]) for t = 0..T-1 (t = 0 wraps to the last control, Q3)
+    if (cfg.flags & 1) {
+        if (tid == 0) {
+            const double* x0 = io.x0 + 4 * e;
+            ArmState st; arm_init(st, (float)x0[0], (float)x0[1], (float)x0[2], (float)x0[3]);
+            double* o = io.opt_traj + (size_t)e * 4 * T;
+            for (int t = 0; t < T; ++t) {
+                const int tc = t == 0 ? T - 1 : t - 1;
+                arm_step(st, cfg.arm, (float)unew[2 * tc], (float)unew[2 * tc + 1]);
+                o[4 * t + 0] = (double)st.q1 - (double)st.kq1; o[4 * t + 1] = (double)st.q2 - (double)st.kq2;
+                o[4 * t + 2] = (double)st.d1 - (double)st.kd1; o[4 * t + 3] = (double)st.d2 - (double)st.kd2;
+            }
+        }
+    } else {
+        for (int c = tid; c < 4 * T; c += blockDim.x) io.opt_traj[(size_t)e * 4 * T + c] = 0.0;
+    }
+}
+
+// ================================================================================================
+// 7. sampled trajectories (control.py:137-145): x <- F(x, v[k, t-1]) with the t = 0 wrap (Q4)
+// ================================================================================================
+template <int NOISE>
+__global__ void __launch_bounds__(128)
+mppi_sampled_traj_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const char* __restrict__ step_blocks,
+                         const float* __restrict__ eps, float* __restrict__ traj) {
+    const int e = blockIdx.y;
+    const int kl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kl >= cfg.K_local) return;
+    const StepBlockView sb = view_step_block((void*)(step_blocks + (size_t)e * cfg.step_block_bytes));
+    const StepHeader hd = *sb.hd;
+    const int kg = cfg.k_offset + kl, T = cfg.T;
+    const float um = kg < cfg.n_exploit ? 1.0f : 0.0f;
+    NoiseCfg nc = cfg.noise; nc.step = (uint32_t)(*step_ctr);
+    ArmState st; arm_init(st, hd.q1, hd.q2, hd.d1, hd.d2);
+    float4* out = (float4*)traj + ((size_t)e * cfg.K_local + kl) * T;
+    for (int t = 0; t < T; ++t) {
+        const int tc = t == 0 ? T - 1 : t - 1;
+        float n1, n2;
+        if (NOISE == 0) {
+            float a0, a1, b0, b1;
+            noise_pair(nc, (uint32_t)e, (uint32_t)kg, (uint32_t)tc >> 1, a0, a1, b0, b1);
+            n1 = (tc & 1) ? b0 : a0; n2 = (tc & 1) ? b1 : a1;
+        } else {
+            const float2 v = __ldg((const float2*)eps + ((size_t)e * cfg.K_local + kl) * T + tc);
+            n1 = v.x; n2 = v.y;
+        }
+        const StepCtl c = sb.ctl[tc];
+        arm_step(st, cfg.arm, fma_(um, c.u1, n1), fma_(um, c.u2, n2));
+        out[t] = make_float4(st.q1, st.q2, st.d1, st.d2);
+    }
+}
+
+// ================================================================================================
+// 8. export of the Philox noise tensor (tests, and users who want to log the draw)
+// ================================================================================================
+__global__ void mppi_philox_export_sm100a(DevCfg cfg, uint32_t step, float* __restrict__ eps) {
+    const int e = blockIdx.y;
+    const int n_pairs = (cfg.T + 1) >> 1;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)cfg.K_local * n_pairs) return;
+    const int kl = (int)(idx / n_pairs), pr = (int)(idx - (long long)kl * n_pairs);
+    NoiseCfg nc = cfg.noise; nc.step = step;
+    float a0, a1, b0, b1;
+    noise_pair(nc, (uint32_t)e, (uint32_t)(cfg.k_offset + kl), (uint32_t)pr, a0, a1, b0, b1);
+    float* dst = eps + (((size_t)e * cfg.K_local + kl) * cfg.T + 2 * pr) * 2;
+    dst[0] = a0; dst[1] = a1;
+    if (2 * pr + 1 < cfg.T) { dst[2] = b0; dst[3] = b1; }
+}
+
+// ================================================================================================
+// 9. roofline probes: register-resident dependent chains, 8 independent chains per thread
+// ================================================================================================
+__global__ void __launch_bounds__(256) mppi_probe_fma_sm100a(float* out, int iters, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+__global__ void __launch_bounds__(256) mppi_probe_mufu_sm100a(float* out, int iters) {
+    float x0 = 1.0f + threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(x0));
+            asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(x1));
+            asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(x2));
+            asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(x3));
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3;
+}
+
+}  // namespace mppi

@@ -103,12 +103,21 @@ struct StepCtl { float u1, u2, g1, g2; };    // nominal control and gamma*(u^T S
 struct ArmState {
     float q1, q2, d1, d2;
     float s1, c1, s12, c12;
+    float kq1, kq2, kd1, kd2;      // Kahan compensation terms of the four integrators
 };
 
 MPPI_HD void arm_init(ArmState& st, float q1, float q2, float d1, float d2) {
     st.q1 = q1; st.q2 = q2; st.d1 = d1; st.d2 = d2;
+    st.kq1 = 0.f; st.kq2 = 0.f; st.kd1 = 0.f; st.kd2 = 0.f;
     sincos_(q1, st.s1, st.c1);
     sincos_(add_(q1, q2), st.s12, st.c12);
+}
+
+// acc += y with the rounding error left in `comp` (y already has the old comp subtracted)
+MPPI_HD void kahan_(float& acc, float& comp, float y) {
+    float t = add_(acc, y);
+    comp = sub_(sub_(t, acc), y);
+    acc = t;
 }
 
 // One integration step (control.py:241-259) under control (v1, v2).
@@ -129,10 +138,19 @@ MPPI_HD void arm_step(ArmState& st, const ArmF& A, float v1, float v2) {
     float idt = mul_(rcp_(det), A.dt);
     float n1 = fma_(A.M22, b1, -mul_(M12, b2));
     float n2 = fma_(M11, b2, -mul_(M12, b1));
+#ifndef MPPI_NO_KAHAN
+    // compensated (Kahan) integration: the rounding error of each accumulator is carried, so the
+    // state error stays ~1 ulp instead of growing like sqrt(T) ulp over the horizon
+    kahan_(st.d1, st.kd1, fma_(n1, idt, -st.kd1));
+    kahan_(st.d2, st.kd2, fma_(n2, idt, -st.kd2));
+    kahan_(st.q1, st.kq1, fma_(-st.kd1, A.dt, fma_(st.d1, A.dt, -st.kq1)));
+    kahan_(st.q2, st.kq2, fma_(-st.kd2, A.dt, fma_(st.d2, A.dt, -st.kq2)));
+#else
     st.d1 = fma_(n1, idt, st.d1);
     st.d2 = fma_(n2, idt, st.d2);
     st.q1 = fma_(st.d1, A.dt, st.q1);
     st.q2 = fma_(st.d2, A.dt, st.q2);
+#endif
     sincos_(st.q1, st.s1, st.c1);
     sincos_(add_(st.q1, st.q2), st.s12, st.c12);
 }
@@ -225,6 +243,121 @@ MPPI_HD void noise_pair(const NoiseCfg& nc, uint32_t env, uint32_t k, uint32_t p
     box_muller(r.z, r.w, z2, z3);
     e0a = mul_(nc.L11, z0); e0b = fma_(nc.L21, z0, mul_(nc.L22, z1));
     e1a = mul_(nc.L11, z2); e1b = fma_(nc.L21, z2, mul_(nc.L22, z3));
+}
+
+}  // namespace mppi
+
+// =================================================================================================
+// One sample's rollout: T integration steps with stage costs, then the terminal cost
+// (control.py:91-109).  `Noise` provides eps for step t; tables may live in registers / shared
+// memory (device) or plain arrays (tests/emul on the host).
+// =================================================================================================
+namespace mppi {
+
+struct StepHeader {            // first 64 bytes of a step block (one per environment and control step)
+    float q1, q2, d1, d2;      // observed state rounded to FP32
+    float ox, oy;              // window origin = first row of the window (FP32 of the FP64 row)
+    int32_t win_start;         // updated prev_waypoints_idx (control.py:230)
+    int32_t n_valid;           // rows of the window that exist (control.py:208-209 truncation)
+    int32_t status;            // bit0: reached the end of the path (control.py:76)
+    int32_t pad[7];
+};
+static_assert(sizeof(StepHeader) == 64, "header is 64 bytes");
+
+// Nearest-waypoint search (control.py:208-215): first arg-min over the 30 window candidates.
+// Exact FP32 comparisons on d_j - |p'|^2 = c_j + a_j x' + b_j y', as a tournament tree of depth 5;
+// `<` is strict and the right operand always carries the larger index, so ties keep the first
+// candidate like list.index(min(d)) does.
+MPPI_HD int nearest_candidate(const float (&wa)[kWindow], const float (&wb)[kWindow],
+                              const float (&wc)[kWindow], float xl, float yl) {
+    float d[kWindowPad];
+    int id[kWindowPad];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < kWindow; ++j) { d[j] = fma_(wa[j], xl, fma_(wb[j], yl, wc[j])); id[j] = j; }
+    d[30] = kSentinel; d[31] = kSentinel; id[30] = 30; id[31] = 31;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int w = 1; w < kWindowPad; w *= 2) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j + w < kWindowPad; j += 2 * w) {
+            const bool lt = d[j + w] < d[j];
+            d[j] = lt ? d[j + w] : d[j];
+            id[j] = lt ? id[j + w] : id[j];
+        }
+    }
+    return id[0];
+}
+
+template <class Noise>
+MPPI_HD float rollout_cost(const StepHeader& hd, const ArmF& A, const CostW& W,
+                           const float (&wa)[kWindow], const float (&wb)[kWindow],
+                           const float (&wc)[kWindow], const RefRow* rows, const StepCtl* ctl,
+                           int T, float um, Noise& noise) {
+    ArmState st;
+    arm_init(st, hd.q1, hd.q2, hd.d1, hd.d2);
+    float S = 0.0f, kS = 0.0f;
+    float ex = 0.f, ey = 0.f, e1 = 0.f, e2 = 0.f;
+    for (int t = 0; t < T; ++t) {
+        float n1, n2;
+        noise(t, n1, n2);
+        const StepCtl c = ctl[t];
+        float v1 = fma_(um, c.u1, n1);             // control.py:98-101 (um = 0 for exploration samples)
+        float v2 = fma_(um, c.u2, n2);
+        arm_step(st, A, v1, v2);
+        float xl, yl;
+        fk_local(st, A, hd.ox, hd.oy, xl, yl);
+        const int j = nearest_candidate(wa, wb, wc, xl, yl);
+        const RefRow r = rows[j];
+        residuals(st, xl, yl, r, ex, ey, e1, e2);
+        float cst = wsq(W.s0, W.s1, W.s2, W.s3, ex, ey, e1, e2);
+        cst = fma_(c.g1, v1, fma_(c.g2, v2, cst)); // + gamma * u^T Sigma^-1 v  (control.py:106)
+#ifndef MPPI_NO_KAHAN
+        kahan_(S, kS, sub_(cst, kS));
+#else
+        S = add_(S, cst);
+#endif
+    }
+    // terminal cost on the same final state and the same nearest waypoint (control.py:109, Q5)
+    return add_(S, sub_(wsq(W.t0, W.t1, W.t2, W.t3, ex, ey, e1, e2), kS));
+}
+
+}  // namespace mppi
+
+// =================================================================================================
+// Step-block construction (FP64 in, FP32 tables out) — the per-entry pieces of the prepare kernel.
+// =================================================================================================
+namespace mppi {
+
+// Squared distance *100 exactly as control.py:210-212 computes it (FP64).
+MPPI_HD double waypoint_d(const double* ref, int row, double x, double y) {
+    double dx = x - ref[4 * row + 0], dy = y - ref[4 * row + 1];
+    return (dx * dx + dy * dy) * 100;
+}
+
+// Row j of the window starting at waypoint p, in coordinates local to row p.
+MPPI_HD void make_window_row(const double* ref, int n_rows, int p, int j, WinEntry& w, RefRow& r) {
+    const int row = p + j;
+    if (j < kWindow && row < n_rows) {
+        double rx = ref[4 * row + 0] - ref[4 * p + 0];
+        double ry = ref[4 * row + 1] - ref[4 * p + 1];
+        w.a = (float)(-2.0 * rx); w.b = (float)(-2.0 * ry); w.c = (float)(rx * rx + ry * ry); w.pad = 0.f;
+        r.rx = (float)rx; r.ry = (float)ry; r.rd1 = (float)ref[4 * row + 2]; r.rd2 = (float)ref[4 * row + 3];
+    } else {                       // beyond the end of the path (control.py:208-209) or table padding
+        w.a = 0.f; w.b = 0.f; w.c = kSentinel; w.pad = 0.f;
+        r.rx = 0.f; r.ry = 0.f; r.rd1 = 0.f; r.rd2 = 0.f;
+    }
+}
+
+// Nominal control of horizon step t and the row vector gamma * u_t^T Sigma^-1 (control.py:106).
+MPPI_HD void make_step_ctl(const double* u_t, double gamma, const double* sig_inv, StepCtl& c) {
+    c.u1 = (float)u_t[0]; c.u2 = (float)u_t[1];
+    c.g1 = (float)(gamma * (u_t[0] * sig_inv[0] + u_t[1] * sig_inv[2]));
+    c.g2 = (float)(gamma * (u_t[0] * sig_inv[1] + u_t[1] * sig_inv[3]));
 }
 
 }  // namespace mppi

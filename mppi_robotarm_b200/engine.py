@@ -1,0 +1,270 @@
+"""MppiEngine — owns one libmppi_b200 handle plus the memory it works in.
+
+PyTorch is used here for plumbing only: device memory (the workspace and the optional injected-noise
+tensor), pinned host memory (the io block), the CUDA stream, and ``torch.distributed`` for the one
+small all-gather of the sharded step.  All arithmetic of the MPPI step happens inside the CUDA
+library; nothing here (or anywhere in this package) computes rollouts on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _cabi
+from .arm_params import arm_vector
+
+
+@dataclass
+class ShardSpec:
+    """Which global samples [k_offset, k_offset + K_local) this rank rolls out."""
+    rank: int = 0
+    world: int = 1
+
+    def bounds(self, K_total: int):
+        base, rem = divmod(K_total, self.world)
+        K_local = base + (1 if self.rank < rem else 0)
+        k_offset = self.rank * base + min(self.rank, rem)
+        return k_offset, K_local
+
+
+def exploit_count(K: int, exploration: float) -> int:
+    """#samples with ``k < (1 - param_exploration) * K`` — the Python float comparison of
+    control.py:98 evaluated once on the host (an integer threshold on the global sample index)."""
+    thr = (1.0 - float(exploration)) * K
+    n = int(np.ceil(thr))
+    n = max(0, min(K, n))
+    # make the boundary exact under the same float comparison
+    while n > 0 and not ((n - 1) < thr):
+        n -= 1
+    while n < K and (n < thr):
+        n += 1
+    return n
+
+
+class MppiEngine:
+    def __init__(self, *, K, T, delta_t, param_lambda, param_gamma, sigma, stage_cost_weight,
+                 terminal_cost_weight, arm_params, ref_path, param_exploration=0.0, cost_l1=1.0, cost_l2=1.0,
+                 n_env=1, seed=0, device=None, optimal_traj=True, use_graph=True,
+                 shard: ShardSpec | None = None, process_group=None, max_ref_rows=None):
+        import torch
+        self.torch = torch
+        self.lib = _cabi.load()
+        if not torch.cuda.is_available() or self.lib.mppi_device_count() < 1:
+            raise _cabi.NativeLibraryError(
+                "no CUDA device of compute capability 10.x visible: the MPPI step runs only as sm_100a "
+                "CUDA (libmppi_b200.so); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else
+                                   (device if isinstance(device, int) else torch.device(device).index or 0))
+        self.shard = shard or ShardSpec()
+        self.group = process_group
+        self.K, self.T, self.n_env = int(K), int(T), int(n_env)
+        k_offset, K_local = self.shard.bounds(self.K)
+        if K_local < 1:
+            raise ValueError(f"rank {self.shard.rank} of {self.shard.world} would get no samples (K={K})")
+        self.k_offset, self.K_local = k_offset, K_local
+        sigma = np.asarray(sigma, dtype=np.float64)
+        sig_inv = np.linalg.inv(sigma)                       # LinAlgError on a singular Sigma (control.py:106)
+        chol = np.linalg.cholesky(sigma)                     # LinAlgError unless symmetric positive definite
+        ref = np.ascontiguousarray(np.asarray(ref_path, dtype=np.float64)[:, 0:4])
+        cfg = _cabi.MppiConfig()
+        cfg.abi_version = _cabi.ABI_VERSION
+        cfg.device = self.device.index
+        cfg.n_env = self.n_env
+        cfg.K_total, cfg.K_local, cfg.k_offset = self.K, K_local, k_offset
+        cfg.T = self.T
+        cfg.n_exploit = exploit_count(self.K, param_exploration)
+        cfg.flags = (_cabi.FLAG_OPTIMAL_TRAJ if optimal_traj else 0) | (_cabi.FLAG_DEVICE_GRAPH if use_graph else 0)
+        cfg.max_ref_rows = int(max_ref_rows or ref.shape[0])
+        cfg.delta_t, cfg.param_lambda, cfg.param_gamma = float(delta_t), float(param_lambda), float(param_gamma)
+        cfg.sigma_chol[:] = chol.reshape(-1).tolist()
+        cfg.sigma_inv[:] = sig_inv.reshape(-1).tolist()
+        cfg.stage_cost_weight[:] = np.asarray(stage_cost_weight, dtype=np.float64).reshape(-1)[:4].tolist()
+        cfg.terminal_cost_weight[:] = np.asarray(terminal_cost_weight, dtype=np.float64).reshape(-1)[:4].tolist()
+        cfg.arm[:] = arm_vector(arm_params)
+        cfg.cost_l1, cfg.cost_l2 = float(cost_l1), float(cost_l2)
+        cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.cfg = cfg
+
+        lay = _cabi.MppiIoLayout()
+        _cabi.check(self.lib.mppi_io_layout(C.byref(cfg), C.byref(lay)), None, "mppi_io_layout")
+        self.layout = lay
+        ws_bytes = self.lib.mppi_workspace_bytes(C.byref(cfg))
+        if ws_bytes == 0:
+            raise ValueError("libmppi_b200 rejected the configuration: " + _cabi.last_error())
+        with torch.cuda.device(self.device):
+            self._ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=self.device)
+            self._io = torch.zeros(lay.bytes, dtype=torch.uint8).pin_memory()
+            self.stream = torch.cuda.Stream(device=self.device)
+        ws_ptr = (self._ws.data_ptr() + 255) // 256 * 256
+        h = C.c_void_p()
+        _cabi.check(self.lib.mppi_create(C.byref(cfg), ws_ptr, ws_bytes, self._io.data_ptr(), lay.bytes, C.byref(h)),
+                    None, "mppi_create")
+        self.handle = h
+        io = self._io.numpy()
+        E, T = self.n_env, self.T
+
+        def view(off, dtype, shape):
+            n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+            return io[off:off + n].view(dtype).reshape(shape)
+
+        self.in_x0 = view(lay.off_x0, np.float64, (E, 4))
+        self.in_u_prev = view(lay.off_u_prev, np.float64, (E, T, 2))
+        self.in_prev_idx = view(lay.off_prev_idx, np.int32, (E,))
+        self.in_step = view(lay.off_step, np.uint64, (1,))
+        self.out_new_idx = view(lay.off_new_idx, np.int32, (E,))
+        self.out_rho = view(lay.off_rho, np.float64, (E,))
+        self.out_eta = view(lay.off_eta, np.float64, (E,))
+        self.out_w_eps_raw = view(lay.off_w_eps_raw, np.float64, (E, T, 2))
+        self.out_w_eps_filt = view(lay.off_w_eps_filt, np.float64, (E, T, 2))
+        self.out_u_new = view(lay.off_u_new, np.float64, (E, T, 2))
+        self.out_opt_traj = view(lay.off_opt_traj, np.float64, (E, T, 4))
+        self.step_counter = 0
+        self._eps_dev = None
+        self._eps_pin = None
+        self._partial = None
+        self._gathered = None
+        self.set_ref_path(ref)
+
+    # ------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "handle", None):
+            self.torch.cuda.synchronize(self.device)
+            self.lib.mppi_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_ref_path(self, ref):
+        ref = np.ascontiguousarray(np.asarray(ref, dtype=np.float64)[:, 0:4])
+        self.n_ref_rows = ref.shape[0]
+        _cabi.check(self.lib.mppi_set_ref_path(self.handle, ref.ctypes.data, ref.shape[0]), self.handle,
+                    "mppi_set_ref_path")
+
+    # ------------------------------------------------------------------------------------------
+    def _stage_eps(self, eps):
+        """Host noise [n_env?, K_local, T, 2] -> device float32 (injected-noise mode)."""
+        torch = self.torch
+        shape = (self.n_env, self.K_local, self.T, 2)
+        if torch.is_tensor(eps) and eps.is_cuda:
+            e = eps.to(torch.float32).reshape(shape).contiguous()
+            self._eps_dev = e
+            return e
+        eps = np.asarray(eps)
+        if eps.shape[0] == self.K and self.K_local != self.K and eps.ndim == 3:
+            eps = eps[self.k_offset:self.k_offset + self.K_local]        # this rank's shard
+        if self._eps_dev is None or tuple(self._eps_dev.shape) != shape or not self._eps_dev.is_cuda:
+            self._eps_dev = torch.empty(shape, dtype=torch.float32, device=self.device)
+            self._eps_pin = torch.empty(shape, dtype=torch.float32).pin_memory()
+        self._eps_pin.numpy()[...] = eps.reshape(shape)                  # float64 -> float32 here
+        with torch.cuda.stream(self.stream):
+            self._eps_dev.copy_(self._eps_pin, non_blocking=True)
+        return self._eps_dev
+
+    def write_inputs(self, x0, u_prev, prev_idx):
+        self.in_x0[...] = np.asarray(x0, dtype=np.float64).reshape(self.n_env, 4)
+        self.in_u_prev[...] = np.asarray(u_prev, dtype=np.float64).reshape(self.n_env, self.T, 2)
+        self.in_prev_idx[...] = np.asarray(prev_idx, dtype=np.int64).reshape(self.n_env)
+        self.in_step[0] = self.step_counter
+
+    def step(self, x0, u_prev, prev_idx, eps=None):
+        """One MPPI step.  Results are then readable from the ``out_*`` views (valid until the next
+        step).  ``eps`` = None draws Philox noise in-kernel; otherwise it is injected."""
+        self.write_inputs(x0, u_prev, prev_idx)
+        self.launch(eps)
+        self.wait()
+
+    def launch(self, eps=None):
+        mode = _cabi.NOISE_PHILOX if eps is None else _cabi.NOISE_INJECTED
+        eps_ptr = None if eps is None else self._stage_eps(eps).data_ptr()
+        s = self.stream.cuda_stream
+        if self.shard.world == 1:
+            _cabi.check(self.lib.mppi_step(self.handle, mode, eps_ptr, s), self.handle, "mppi_step")
+        else:
+            self._launch_sharded(mode, eps_ptr, s)
+        self.last_mode, self.last_eps_ptr = mode, eps_ptr
+        self.step_counter += 1
+
+    def _launch_sharded(self, mode, eps_ptr, s):
+        """rollouts on this shard -> all-gather of (rho_g, eta_g, V_g) -> identical combine on every rank."""
+        torch = self.torch
+        import torch.distributed as dist
+        self.launch_local(mode, eps_ptr)
+        if self._gathered is None:
+            self._gathered = torch.zeros(self.shard.world * self._partial.numel(), dtype=torch.float64,
+                                         device=self.device)
+        with torch.cuda.stream(self.stream):
+            dist.all_gather_into_tensor(self._gathered, self._partial, group=self.group)
+        self.launch_combine(self._gathered, self.shard.world)
+
+    def launch_local(self, mode, eps_ptr):
+        """First half of the sharded step; returns this shard's partial, float64 [n_env, 2 + 2T] on
+        the device: (rho_g, eta_g, V_g[T, 2])."""
+        if self._partial is None:
+            self._partial = self.torch.zeros((self.n_env, 2 + 2 * self.T), dtype=self.torch.float64,
+                                             device=self.device)
+        _cabi.check(self.lib.mppi_step_local(self.handle, mode, eps_ptr, self._partial.data_ptr(),
+                                             self.stream.cuda_stream), self.handle, "mppi_step_local")
+        return self._partial
+
+    def launch_combine(self, gathered, world):
+        """Second half: ``gathered`` is float64 [world, n_env, 2 + 2T] on the device."""
+        assert gathered.is_cuda and gathered.dtype == self.torch.float64 and gathered.is_contiguous()
+        assert gathered.numel() == world * self.n_env * (2 + 2 * self.T)
+        self._gathered_keepalive = gathered
+        _cabi.check(self.lib.mppi_step_combine(self.handle, gathered.data_ptr(), world, self.stream.cuda_stream),
+                    self.handle, "mppi_step_combine")
+
+    def wait(self):
+        _cabi.check(self.lib.mppi_wait(self.handle), self.handle, "mppi_wait")
+
+    # ------------------------------------------------------------------------------------------
+    def last_costs(self):
+        """(S, w~) of the last step as device tensors [n_env, K_local] (float32)."""
+        torch = self.torch
+        ps, pw = C.c_void_p(), C.c_void_p()
+        _cabi.check(self.lib.mppi_last_costs(self.handle, C.byref(ps), C.byref(pw)), self.handle, "mppi_last_costs")
+        off = self._ws.data_ptr()
+        n = self.n_env * self.K_local
+
+        def as_tensor(ptr):
+            start = ptr - off
+            return self._ws[start:start + 4 * n].view(torch.float32).reshape(self.n_env, self.K_local)
+        return as_tensor(ps.value), as_tensor(pw.value)
+
+    def sampled_trajectories(self):
+        """control.py:137-145 for the last step: device tensor [n_env, K_local, T, 4] float32."""
+        torch = self.torch
+        out = torch.empty((self.n_env, self.K_local, self.T, 4), dtype=torch.float32, device=self.device)
+        _cabi.check(self.lib.mppi_sampled_trajectories(self.handle, self.last_mode, self.last_eps_ptr,
+                                                       out.data_ptr(), self.stream.cuda_stream),
+                    self.handle, "mppi_sampled_trajectories")
+        self.stream.synchronize()
+        return out
+
+    def philox_noise(self, step=None):
+        """The noise tensor the kernels draw at control step ``step``: [n_env, K_local, T, 2] float32."""
+        torch = self.torch
+        out = torch.empty((self.n_env, self.K_local, self.T, 2), dtype=torch.float32, device=self.device)
+        step = self.step_counter if step is None else step
+        _cabi.check(self.lib.mppi_philox_noise(self.handle, int(step), out.data_ptr(), self.stream.cuda_stream),
+                    self.handle, "mppi_philox_noise")
+        self.stream.synchronize()
+        return out
+
+    def launch_count(self) -> int:
+        return int(self.lib.mppi_launch_count(self.handle))
+
+    def set_timing(self, on: bool):
+        _cabi.check(self.lib.mppi_set_timing(self.handle, 1 if on else 0), self.handle, "mppi_set_timing")
+
+    def get_timing(self) -> dict:
+        buf = (C.c_double * 6)()
+        n = self.lib.mppi_get_timing(self.handle, buf, 6)
+        names = ["prepare", "rollout", "softmin", "wsum", "reduce", "finalize"]
+        return {"steps": n, **{k: buf[i] for i, k in enumerate(names)}}

@@ -1,0 +1,73 @@
+// TEST INFRASTRUCTURE ONLY — CPU emulation of the FP32 rollout arithmetic in
+// mppi_robotarm_b200/csrc/mppi_math.cuh, compiled with g++ (-ffp-contract=off).  Used by CPU tests
+// to study FP32-vs-FP64 parity without a GPU; never loaded by the product package.
+#include "../../mppi_robotarm_b200/csrc/mppi_math.cuh"
+#include <cmath>
+#include <vector>
+using namespace mppi;
+
+struct EpsArray {
+    const float* e; int T;
+    void operator()(int t, float& a, float& b) const { a = e[2 * t]; b = e[2 * t + 1]; }
+};
+
+extern "C" {
+
+// S[K] for injected noise eps[K][T][2]; mirrors prepare + rollout kernels.  Returns new window start.
+int emul_rollout_costs(const double* ref, int n_rows, int prev_idx, const double* x0, const double* u_prev,
+                       int K, int T, int n_exploit, double dt, double gamma, const double* sig_inv,
+                       const double* ws, const double* wt, const double* arm, double cl1, double cl2,
+                       const float* eps, float* S_out) {
+    // waypoint update, FP64 (control.py:75, 200-232)
+    double x = cl1 * cos(x0[0]) + cl2 * cos(x0[0] + x0[1]);
+    double y = cl1 * sin(x0[0]) + cl2 * sin(x0[0] + x0[1]);
+    int best = 0; double bd = 1e300;
+    for (int j = 0; j < kWindow && prev_idx + j < n_rows; ++j) {
+        double d = waypoint_d(ref, prev_idx + j, x, y);
+        if (d < bd) { bd = d; best = j; }
+    }
+    int p = prev_idx + best;
+    StepHeader hd{};
+    hd.q1 = (float)x0[0]; hd.q2 = (float)x0[1]; hd.d1 = (float)x0[2]; hd.d2 = (float)x0[3];
+    hd.ox = (float)ref[4 * p]; hd.oy = (float)ref[4 * p + 1]; hd.win_start = p;
+    float wa[kWindow], wb[kWindow], wc[kWindow]; RefRow rows[kWindowPad];
+    for (int j = 0; j < kWindowPad; ++j) {
+        WinEntry w; make_window_row(ref, n_rows, p, j, w, rows[j]);
+        if (j < kWindow) { wa[j] = w.a; wb[j] = w.b; wc[j] = w.c; }
+    }
+    std::vector<StepCtl> ctl(T);
+    for (int t = 0; t < T; ++t) make_step_ctl(u_prev + 2 * t, gamma, sig_inv, ctl[t]);
+    const double m1 = arm[0], m2 = arm[1], l1 = arm[2], l2 = arm[3], lc1 = arm[4], lc2 = arm[5], g = arm[6];
+    ArmF A;
+    A.A0 = (float)(m1 * lc1 * lc1 + l1 + m2 * (l1 * l1 + lc2 * lc2) + l2);
+    A.A1 = (float)(2 * m2 * l1 * lc2);
+    A.M22 = (float)(m2 * lc2 * lc2 + l2); A.B1 = (float)(m2 * l1 * lc2);
+    A.G1a = (float)((m1 * lc1 + m2 * l1) * g); A.G1b = (float)(m2 * lc2 * g);
+    A.dt = (float)dt; A.L1 = (float)cl1; A.L2 = (float)cl2;
+    // the device copy of ox/oy is FP32; fk_local subtracts exactly that value
+    CostW W{ (float)(ws[0] * 1e4), (float)(ws[1] * 1e4), (float)(ws[2] * 1e4), (float)(ws[3] * 1e4),
+             (float)(wt[0] * 1e4), (float)(wt[1] * 1e4), (float)(wt[2] * 1e4), (float)(wt[3] * 1e4) };
+    for (int k = 0; k < K; ++k) {
+        EpsArray n{ eps + (size_t)k * T * 2, T };
+        S_out[k] = rollout_cost(hd, A, W, wa, wb, wc, rows, ctl.data(), T, k < n_exploit ? 1.f : 0.f, n);
+    }
+    return p;
+}
+
+void emul_sincos(const float* x, int n, float* s, float* c) { for (int i = 0; i < n; ++i) sincos_(x[i], s[i], c[i]); }
+
+void emul_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+    U4 r = philox4x32_10(U4{c0, c1, c2, c3}, k0, k1); out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+void emul_noise(uint32_t seed_lo, uint32_t seed_hi, uint32_t step, const double* chol, uint32_t env,
+                uint32_t k0, int K, int T, float* eps) {
+    NoiseCfg nc{ seed_lo, seed_hi, step, (float)chol[0], (float)chol[2], (float)chol[3] };
+    for (int k = 0; k < K; ++k)
+        for (int p = 0; 2 * p < T; ++p) {
+            float a, b, c, d; noise_pair(nc, env, k0 + k, p, a, b, c, d);
+            float* e = eps + ((size_t)k * T + 2 * p) * 2;
+            e[0] = a; e[1] = b; if (2 * p + 1 < T) { e[2] = c; e[3] = d; }
+        }
+}
+}

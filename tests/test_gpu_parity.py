@@ -1,0 +1,154 @@
+"""GPU parity tests: the CUDA path, called through the drop-in class / C ABI, against the golden
+vectors of the unmodified reference and against the FP64 oracle on the same injected noise.
+
+Stated FP32 tolerances (DESIGN.md "Numerics"):
+  * per-sample cost S:           max |S32 - S64| <= 2e-6 * max|S64|
+  * updated control sequence:    max |u32 - u64| <= 1e-4 * max|u64|      (north_star bound)
+  * optimal / sampled trajectory: 2e-5 absolute (rad, rad/s)
+"""
+import numpy as np
+import pytest
+
+from oracle import mppi_oracle as mo
+from tests import helpers as H
+from tests.golden import cases
+
+pytestmark = pytest.mark.gpu
+
+TOL_S = 2e-6
+TOL_U = 1e-4
+TOL_TRAJ = 2e-5
+
+GOLD = cases.load_golden("single_steps.npz")
+
+
+def _compare_step(ctrl, g, s, kw, out, label):
+    u0, useq, opt, samp = out
+    eng = ctrl._engine()
+    assert [int(g[f"prev_idx.{s}"][0]), ctrl.prev_waypoints_idx] == list(g[f"prev_idx.{s}"]), label
+    S = eng.last_costs()[0][0].cpu().numpy().astype(np.float64)
+    assert H.rel_err(S, g[f"S.{s}"]) <= TOL_S, (label, "S", H.rel_err(S, g[f"S.{s}"]))
+    scale_u = np.max(np.abs(g[f"u_new.{s}"]))
+    assert np.max(np.abs(ctrl.last["w_eps_raw"] - g[f"w_eps_raw.{s}"])) <= TOL_U * scale_u, (label, "w_eps_raw")
+    assert np.max(np.abs(ctrl.last["w_eps_filt"] - g[f"w_eps_filt.{s}"])) <= TOL_U * scale_u, (label, "w_eps_filt")
+    u_new = eng.out_u_new[0]
+    assert H.rel_err(u_new, g[f"u_new.{s}"]) <= TOL_U, (label, "u_new", H.rel_err(u_new, g[f"u_new.{s}"]))
+    assert np.max(np.abs(u0 - g[f"u0.{s}"])) <= TOL_U * scale_u, (label, "u0")
+    np.testing.assert_allclose(opt, g[f"optimal_traj.{s}"], rtol=0, atol=TOL_TRAJ, err_msg=label)
+    if kw.get("visualze_sampled_trajs"):
+        np.testing.assert_allclose(samp, g[f"sampled_traj.{s}"], rtol=0, atol=TOL_TRAJ, err_msg=label)
+    else:
+        assert samp.shape == (ctrl.K, ctrl.T, 4) and not np.any(samp)
+    # quirks Q1/Q2: the returned sequence is the controller's own (already shifted) array
+    assert useq is ctrl.u_prev
+    np.testing.assert_array_equal(u0, ctrl.u_prev[0])
+
+
+@pytest.mark.parametrize("name", sorted(GOLD))
+def test_single_step_goldens(name, paths):
+    case = {c["name"]: c for c in cases.single_cases(paths)}[name]
+    ctrl, kw = H.make_controller(case, paths)
+    g = GOLD[name]
+    for s in range(case.get("steps", 1)):
+        ctrl.u_prev[...] = g[f"u_prev_before.{s}"]                 # teacher forcing
+        ctrl.prev_waypoints_idx = int(g[f"prev_idx.{s}"][0])
+        H.inject(ctrl, mo.injected_noise(case["seed"] + s, case["K"], case["T"], kw["sigma"]))
+        x = g[f"x0.{s}"]
+        out = H.quiet_step(ctrl, list(x) if s == 0 else x)          # run.py:23 passes a list first
+        _compare_step(ctrl, g, s, kw, out, f"{name}[{s}]")
+    ctrl.close()
+
+
+def test_config2_k4096_t50_trajectory_txt(paths):
+    """BASELINE config 2: K=4096, T=50, tracking trajectory.txt, injected-noise equivalence."""
+    gold = cases.load_golden("c2_steps.npz")
+    worst = 0.0
+    for case in cases.c2_cases():
+        ctrl, kw = H.make_controller(case, paths)
+        g = gold[case["name"]]
+        H.inject(ctrl, mo.injected_noise(case["seed"], case["K"], case["T"], kw["sigma"]))
+        H.quiet_step(ctrl, g["x0.0"])
+        eng = ctrl._engine()
+        S = eng.last_costs()[0][0].cpu().numpy().astype(np.float64)
+        assert H.rel_err(S, g["S.0"]) <= TOL_S, (case["name"], H.rel_err(S, g["S.0"]))
+        assert int(np.argmin(S)) == int(np.argmin(g["S.0"]))
+        err = H.rel_err(eng.out_u_new[0], g["u_new.0"])
+        worst = max(worst, err)
+        assert err <= TOL_U, (case["name"], err)
+        np.testing.assert_allclose(eng.out_opt_traj[0], g["optimal_traj.0"], rtol=0, atol=TOL_TRAJ)
+        ctrl.close()
+    print(f"config-2 worst relative error of the updated sequence: {worst:.3e}")
+
+
+def test_teacher_forced_closed_loop_1500_steps(paths):
+    """Replay the reference's 1500-step closed loop (run.py settings, seeded noise): every step
+    starts from the reference's recorded state, sequence and waypoint index; compare the update."""
+    with np.load(cases.HERE + "/closed_loop_c1.npz") as z:
+        cl = {k: z[k] for k in z.files}
+    K, T, seed0, _ = (int(v) for v in cl["meta"])
+    case = dict(name="cl", file="xydq_circle.txt", K=K, T=T)
+    ctrl, kw = H.make_controller(case, paths, visualize_optimal_traj=False)
+    n = cl["state"].shape[0]
+    errs = np.zeros(n)
+    for s in range(n):
+        if s > 0:
+            prev = cl["u_new"][s - 1]
+            ctrl.u_prev[:-1] = prev[1:]
+            ctrl.u_prev[-1] = prev[-1]
+        ctrl.prev_waypoints_idx = int(cl["prev_idx"][s, 0])
+        H.inject(ctrl, mo.injected_noise(seed0 + s, K, T, kw["sigma"]))
+        u0, _, _, _ = H.quiet_step(ctrl, cl["state"][s])
+        assert ctrl.prev_waypoints_idx == cl["prev_idx"][s, 1]
+        errs[s] = H.rel_err(ctrl._engine().out_u_new[0], cl["u_new"][s])
+        np.testing.assert_allclose(u0, cl["u0"][s], rtol=0, atol=TOL_U * np.max(np.abs(cl["u_new"][s])))
+    print(f"teacher-forced: median {np.median(errs):.2e} p99 {np.percentile(errs, 99):.2e} max {errs.max():.2e}; "
+          f"min top-2 cost gap {cl['gap'].min():.3g}")
+    assert errs.max() <= TOL_U, (errs.max(), int(errs.argmax()), cl["gap"][errs.argmax()])
+    ctrl.close()
+
+
+def test_large_k_against_vectorized_oracle(paths):
+    """K=16384, T=50 (config 3 shape) and a K=65536, T=100 slice of config 4: costs and update
+    against the FP64 oracle on injected noise."""
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    for K, T, seed in ((16384, 50, 3), (65536, 100, 4)):
+        kw = cases.run_py_kwargs(ref, K, T, visualize_optimal_traj=False)
+        case = dict(name="big", file="xydq_circle.txt", K=K, T=T)
+        ctrl, _ = H.make_controller(case, paths, visualize_optimal_traj=False)
+        eps = mo.injected_noise(seed, K, T, kw["sigma"])
+        H.inject(ctrl, eps)
+        c = mo.OracleMPPI(**kw)
+        o = mo.step_vectorized(c, cases.X0, eps.astype(np.float64))
+        H.quiet_step(ctrl, cases.X0)
+        eng = ctrl._engine()
+        S = eng.last_costs()[0][0].cpu().numpy().astype(np.float64)
+        assert H.rel_err(S, o["S"]) <= TOL_S
+        assert H.rel_err(eng.out_u_new[0], o["u_new"]) <= TOL_U
+        np.testing.assert_array_equal(ctrl.u_prev, ctrl.u_prev)           # finite
+        assert H.rel_err(ctrl.u_prev, c.u_prev) <= TOL_U                  # shifted sequences agree
+        ctrl.close()
+
+
+def test_nonfinite_samples_get_zero_weight(paths):
+    """A diverged rollout (Inf/NaN noise) must not poison the update: its weight is exactly 0."""
+    case = dict(name="nan", file="xydq_circle.txt", K=64, T=20)
+    ctrl, kw = H.make_controller(case, paths)
+    eps = mo.injected_noise(9, 64, 20, kw["sigma"])
+    bad = eps.copy()
+    bad[5, 3, 0] = np.inf
+    bad[17, 0, 1] = np.nan
+    bad[40, 10, :] = 1e30
+    H.inject(ctrl, bad)
+    H.quiet_step(ctrl, cases.X0)
+    eng = ctrl._engine()
+    S, w = (t[0].cpu().numpy() for t in eng.last_costs())
+    assert w[5] == 0 and w[17] == 0 and w[40] == 0
+    assert np.all(np.isfinite(eng.out_u_new[0]))
+    # equals the oracle on the remaining samples
+    keep = np.ones(64, bool); keep[[5, 17, 40]] = False
+    c = mo.OracleMPPI(**kw)
+    S64 = mo.rollout_costs(c, np.array(cases.X0), eps.astype(np.float64), prev_idx=0)
+    wts, _, _ = mo.softmin_weights(S64[keep], c.param_lambda)
+    raw = np.einsum("k,ktm->tm", wts, eps.astype(np.float64)[keep])
+    assert np.max(np.abs(eng.out_w_eps_raw[0] - raw)) <= TOL_U * 10.0
+    ctrl.close()

@@ -213,13 +213,14 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
     return MPPI_OK;
 }
 
-int enqueue_combine(MppiHandle* h, const double* gathered_dev, int world, cudaStream_t s, bool timed) {
+int enqueue_combine(MppiHandle* h, const double* gathered_dev, int world, cudaStream_t s, bool timed,
+                    bool record_done = true) {
     if (world < 1 || world > 64) return fail(h, MPPI_ERR_INVALID, "%s", "world must be in [1, 64]");
     mppi_finalize_sm100a<<<h->dc.n_env, 256, 0, s>>>(h->dc, h->dio, gathered_dev, world);
     if (timed) CU(h, cudaEventRecord(h->tev[6], s));
     CU(h, cudaGetLastError());
     CU(h, cudaMemcpyAsync(h->host + h->out_off, h->dev + h->ws.off_out, h->out_bytes, cudaMemcpyDeviceToHost, s));
-    CU(h, cudaEventRecord(h->done, s));
+    if (record_done) CU(h, cudaEventRecord(h->done, s));      // not inside a stream capture
     h->launches += 1;
     return MPPI_OK;
 }
@@ -386,7 +387,7 @@ int mppi_step(MppiHandle* h, int32_t noise_mode, const float* eps_dev, void* str
             cudaGraph_t g = nullptr;
             CU(h, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
             int rc = enqueue_local(h, noise_mode, nullptr, partial, s, false);
-            if (rc == MPPI_OK) rc = enqueue_combine(h, partial, 1, s, false);
+            if (rc == MPPI_OK) rc = enqueue_combine(h, partial, 1, s, false, /*record_done=*/false);
             cudaError_t ce = cudaStreamEndCapture(s, &g);
             if (rc != MPPI_OK) { if (g) cudaGraphDestroy(g); return rc; }
             CU(h, ce);
@@ -397,6 +398,7 @@ int mppi_step(MppiHandle* h, int32_t noise_mode, const float* eps_dev, void* str
             h->graph_stream = stream;
         }
         CU(h, cudaGraphLaunch(h->graph_exec, s));
+        CU(h, cudaEventRecord(h->done, s));
         h->launches += h->graph_kernels;
         h->timing_pending = false;
         return MPPI_OK;

@@ -1,0 +1,276 @@
+"""GPU tests of everything around the injected-noise parity: Philox mode, sharding over ranks,
+batched environments, error behaviour, closed loop."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from oracle import mppi_oracle as mo
+from tests import helpers as H
+from tests.golden import cases
+
+pytestmark = pytest.mark.gpu
+
+TOL_U = 1e-4
+TOL_S = 2e-6
+
+
+def _engine(paths, K, T, **kw):
+    from mppi_robotarm_b200 import MppiEngine
+    from mppi_robotarm_b200.arm_params import SYS_PARAMS
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    base = dict(K=K, T=T, delta_t=0.006, param_lambda=100.0, param_gamma=2.0, sigma=np.eye(2) * 20.0,
+                stage_cost_weight=[0.5, 0.5, 5, 5], terminal_cost_weight=[5, 5, 50, 50], arm_params=SYS_PARAMS(),
+                ref_path=ref, seed=99)
+    base.update(kw)
+    return MppiEngine(**base)
+
+
+def _u0(T):
+    return np.tile([10.0, -2.0], (T, 1))
+
+
+# ---------------------------------------------------------------------------------------------
+# Philox mode
+# ---------------------------------------------------------------------------------------------
+def test_philox_step_equals_oracle_on_the_exported_noise(paths):
+    """The in-kernel draw can be exported; the oracle on that tensor must reproduce the step, and
+    the injected-noise kernels fed the same tensor must give bit-identical costs."""
+    K, T = 4096, 50
+    eng = _engine(paths, K, T)
+    eps = eng.philox_noise(step=0)                                  # [1, K, T, 2] on the device
+    eng.step(cases.X0, _u0(T), 0, None)
+    S_ph = eng.last_costs()[0][0].clone()
+    u_ph = eng.out_u_new[0].copy()
+    raw_ph = eng.out_w_eps_raw[0].copy()
+    c = mo.OracleMPPI(**cases.run_py_kwargs(cases.ref_path_for(paths, "xydq_circle.txt"), K, T))
+    o = mo.step_vectorized(c, cases.X0, eps[0].cpu().numpy().astype(np.float64))
+    assert H.rel_err(S_ph.cpu().numpy().astype(np.float64), o["S"]) <= TOL_S
+    assert H.rel_err(u_ph, o["u_new"]) <= TOL_U
+    inj = _engine(paths, K, T)
+    inj.step(cases.X0, _u0(T), 0, eps)
+    assert bool((inj.last_costs()[0][0] == S_ph).all()), "rollout arithmetic must not depend on the noise source"
+    np.testing.assert_allclose(inj.out_w_eps_raw[0], raw_ph, rtol=0, atol=1e-5 * np.max(np.abs(raw_ph)) + 1e-12)
+    eng.close(); inj.close()
+
+
+def test_philox_noise_statistics_and_streams(paths):
+    from scipy import stats
+    K, T = 8192, 50
+    sig = np.array([[20.0, 6.0], [6.0, 10.0]])
+    eng = _engine(paths, K, T, sigma=sig)
+    e0 = eng.philox_noise(step=0)[0].cpu().numpy().astype(np.float64)
+    e1 = eng.philox_noise(step=1)[0].cpu().numpy().astype(np.float64)
+    flat = e0.reshape(-1, 2)
+    assert np.all(np.abs(flat.mean(0)) < 4 * np.sqrt(np.diag(sig) / flat.shape[0]) + 1e-3)
+    np.testing.assert_allclose(np.cov(flat.T), sig, atol=0.15)
+    z = np.linalg.solve(np.linalg.cholesky(sig), flat.T).T           # whitened -> N(0, I)
+    for col in range(2):
+        assert stats.kstest(z[::7, col], "norm").pvalue > 1e-3
+    assert abs(stats.kurtosis(z[:, 0])) < 0.05 and abs(stats.skew(z[:, 1])) < 0.02
+    # different control steps / neighbouring samples / neighbouring horizon steps are uncorrelated
+    for a, b in ((e0[..., 0].ravel(), e1[..., 0].ravel()), (e0[:-1, :, 0].ravel(), e0[1:, :, 0].ravel()),
+                 (e0[:, :-1, 1].ravel(), e0[:, 1:, 1].ravel())):
+        assert abs(np.corrcoef(a, b)[0, 1]) < 0.01
+    assert not np.array_equal(e0, e1)
+    # reproducible, and independent of how the samples are sharded (keyed on the global index)
+    np.testing.assert_array_equal(eng.philox_noise(step=0)[0].cpu().numpy(), e0.astype(np.float32))
+    from mppi_robotarm_b200 import ShardSpec
+    half = _engine(paths, K, T, sigma=sig, shard=ShardSpec(1, 2))
+    np.testing.assert_array_equal(half.philox_noise(step=0)[0].cpu().numpy(), e0[K // 2:].astype(np.float32))
+    other = _engine(paths, K, T, sigma=sig, seed=100)
+    assert abs(np.corrcoef(other.philox_noise(step=0)[0].cpu().numpy()[..., 0].ravel(), e0[..., 0].ravel())[0, 1]) < 0.01
+    eng.close(); half.close(); other.close()
+
+
+def test_philox_odd_horizon_and_graph_replay(paths):
+    """T odd (last Philox pair half used) and the CUDA-graph replay give the same result as the
+    plain launches."""
+    for T in (7, 30):
+        a = _engine(paths, 1000, T, use_graph=True)
+        b = _engine(paths, 1000, T, use_graph=False)
+        for s in range(3):
+            a.step(cases.X0, _u0(T), 0, None)
+            b.step(cases.X0, _u0(T), 0, None)
+            np.testing.assert_array_equal(a.out_u_new, b.out_u_new)
+            np.testing.assert_array_equal(a.out_opt_traj, b.out_opt_traj)
+        eps = a.philox_noise(step=2)
+        inj = _engine(paths, 1000, T)
+        inj.step(cases.X0, _u0(T), 0, eps)
+        np.testing.assert_allclose(inj.out_u_new, a.out_u_new, rtol=1e-6, atol=1e-6)
+        a.close(); b.close(); inj.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# sharded step: rank-partials + combine == single-GPU step
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world,K,T", [(2, 4096, 50), (4, 1000, 30), (8, 1003, 9)])
+def test_sharded_partials_combine_to_the_single_gpu_result(paths, world, K, T):
+    """Emulates `world` ranks one after the other on this GPU (no inter-kernel waiting): each shard
+    runs mppi_step_local, the partials are concatenated as an all-gather would, and every 'rank'
+    runs mppi_step_combine."""
+    import torch
+    from mppi_robotarm_b200 import ShardSpec, _cabi
+    lam = 2000.0 if K == 1000 else 100.0                              # one case with many non-zero weights
+    single = _engine(paths, K, T, param_lambda=lam, param_gamma=lam * 0.02)
+    for mode in ("philox", "injected"):
+        eps_full = single.philox_noise(step=0) if mode == "injected" else None
+        single.step_counter = 0
+        single.step(cases.X0, _u0(T), 0, eps_full)
+        ref_u, ref_raw = single.out_u_new[0].copy(), single.out_w_eps_raw[0].copy()
+        ref_rho, ref_eta = single.out_rho[0], single.out_eta[0]
+        shards = [_engine(paths, K, T, param_lambda=lam, param_gamma=lam * 0.02, shard=ShardSpec(r, world))
+                  for r in range(world)]
+        parts = []
+        for e in shards:
+            e.write_inputs(cases.X0, _u0(T), 0)
+            if mode == "injected":
+                ptr = e._stage_eps(eps_full[0, e.k_offset:e.k_offset + e.K_local]).data_ptr()
+                parts.append(e.launch_local(_cabi.NOISE_INJECTED, ptr).clone())
+            else:
+                parts.append(e.launch_local(_cabi.NOISE_PHILOX, None).clone())
+            torch.cuda.synchronize()
+        gathered = torch.stack(parts, 0).contiguous()                 # [world, n_env, 2 + 2T]
+        for e in shards:
+            e.launch_combine(gathered, world)
+            e.wait()
+            assert e.out_rho[0] == ref_rho
+            np.testing.assert_allclose(e.out_eta[0], ref_eta, rtol=1e-6)
+            scale = np.max(np.abs(ref_raw)) + 1e-12
+            assert np.max(np.abs(e.out_w_eps_raw[0] - ref_raw)) <= 2e-6 * scale
+            assert H.rel_err(e.out_u_new[0], ref_u) <= 2e-6
+            np.testing.assert_array_equal(e.out_u_new, shards[0].out_u_new)   # bit-identical on all ranks
+            e.close()
+    single.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# batched environments
+# ---------------------------------------------------------------------------------------------
+def test_batched_environments_equal_independent_controllers(paths):
+    from mppi_robotarm_b200.batched import BatchedMPPIController
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    traj1 = paths["trajectory1"]
+    B, K, T = 5, 512, 24
+    rows = [0, 300, 900, 1500, 1975]
+    X = np.array([[traj1[r, 0], traj1[r, 1], 0.05 * i, -0.03 * i] for i, r in enumerate(rows)])
+    kw = cases.run_py_kwargs(ref, K, T)
+    bat = BatchedMPPIController(B, **{k: v for k, v in kw.items()}, visualize_optimal_traj=True, seed=5)
+    bat.prev_waypoints_idx = np.array(rows)
+    eps = np.stack([mo.injected_noise(50 + b, K, T, kw["sigma"]) for b in range(B)])
+    u0, useq, opt = bat.calc_control_input(X, eps=eps)
+    for b in range(B):
+        c = mo.OracleMPPI(**kw)
+        c.prev_waypoints_idx = rows[b]
+        o = mo.step_vectorized(c, X[b], eps[b].astype(np.float64))
+        assert bat.prev_waypoints_idx[b] == o["prev_idx_after"]
+        assert H.rel_err(bat.engine.out_u_new[b], o["u_new"]) <= TOL_U
+        assert np.max(np.abs(u0[b] - o["u0"])) <= TOL_U * np.max(np.abs(o["u_new"]))
+        assert H.rel_err(useq[b], c.u_prev) <= TOL_U
+        np.testing.assert_allclose(opt[b], o["optimal_traj"], rtol=0, atol=2e-5)
+    # Philox: every environment draws its own stream
+    bat.calc_control_input(X)
+    e = bat.engine.philox_noise(step=1).cpu().numpy()
+    assert abs(np.corrcoef(e[0, ..., 0].ravel(), e[1, ..., 0].ravel())[0, 1]) < 0.03
+    bat.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# error behaviour and API details of the drop-in class
+# ---------------------------------------------------------------------------------------------
+def test_end_of_path_raises_index_error_and_keeps_sequence(paths, capsys):
+    from control import MPPIControllerForPathTracking
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    c = MPPIControllerForPathTracking(**cases.run_py_kwargs(ref, 64, 10), verbose=False)
+    c.prev_waypoints_idx = 1995
+    before = c.u_prev.copy()
+    with pytest.raises(IndexError):
+        c.calc_control_input([1.15, -1.26, 0.0, 0.0])          # nearest of rows 1995..1999 is the last
+    assert "[ERROR] Reached the end of the reference path." in capsys.readouterr().out
+    assert c.prev_waypoints_idx == 1999                          # control.py:230 ran before the check
+    np.testing.assert_array_equal(c.u_prev, before)
+    c.close()
+
+
+def test_sigma_errors_match_reference_types(paths):
+    from control import MPPIControllerForPathTracking
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    bad = MPPIControllerForPathTracking(**cases.run_py_kwargs(ref, 8, 5, sigma=np.eye(3)), verbose=False)
+    with pytest.raises(ValueError):
+        bad.calc_control_input(cases.X0)
+    kw = cases.run_py_kwargs(ref, 8, 5)
+    kw.pop("sigma")
+    singular = MPPIControllerForPathTracking(**kw, verbose=False)          # default Sigma of control.py:30
+    with pytest.raises(np.linalg.LinAlgError):
+        singular.calc_control_input(cases.X0)
+
+
+def test_prints_three_lines_per_step_like_the_reference(paths):
+    from control import MPPIControllerForPathTracking
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    c = MPPIControllerForPathTracking(**cases.run_py_kwargs(ref, 64, 10), seed=3)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        c.calc_control_input(list(cases.X0))
+    lines = buf.getvalue().splitlines()
+    assert lines[0] == "0     prev_idx = 0" and lines[1].startswith("0     nearest_idx = ")
+    assert lines[2] == "======================updated======================="
+    c.close()
+
+
+def test_user_can_set_controller_state_between_steps(paths):
+    """u_prev and prev_waypoints_idx are plain host attributes, read every step (checkpoint/resume)."""
+    from control import MPPIControllerForPathTracking
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    a = MPPIControllerForPathTracking(**cases.run_py_kwargs(ref, 256, 20), seed=11, verbose=False)
+    b = MPPIControllerForPathTracking(**cases.run_py_kwargs(ref, 256, 20), seed=11, verbose=False)
+    x = np.array(cases.X0)
+    for _ in range(3):
+        a.calc_control_input(x)
+    # resume b from a's state after 2 steps
+    c2 = MPPIControllerForPathTracking(**cases.run_py_kwargs(ref, 256, 20), seed=11, verbose=False)
+    for _ in range(2):
+        c2.calc_control_input(x)
+    b.u_prev = c2.u_prev.copy()
+    b.prev_waypoints_idx = c2.prev_waypoints_idx
+    b._engine().step_counter = 2
+    b.calc_control_input(x)
+    np.testing.assert_array_equal(a.u_prev, b.u_prev)
+    for c in (a, b, c2):
+        c.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# closed loop, free running, exactly as run.py drives the controller (run.py:8-59)
+# ---------------------------------------------------------------------------------------------
+def test_free_running_closed_loop_tracks_like_the_reference(paths):
+    from control import MPPIControllerForPathTracking
+    from utils import Arm_Dynamic, Forward_Kinemetic
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    with np.load(cases.HERE + "/closed_loop_c1.npz") as z:
+        ref_run = {k: z[k] for k in z.files}
+    dt = 0.003
+    q = np.array(cases.X0[0:2]); dq = np.array([0.0, 0.0])
+    state = [q[0], q[1], dq[0], dq[1]]
+    mppi = MPPIControllerForPathTracking(
+        delta_t=dt * 2, ref_path=ref, horizon_step_T=30, number_of_samples_K=100, param_exploration=0.0,
+        param_lambda=100.0, param_alpha=0.98, sigma=np.array([[20.0, 0.0], [0.0, 20.0]]),
+        stage_cost_weight=np.array([0.50, 0.50, 5.0, 5.0]), terminal_cost_weight=np.array([5.0, 5.0, 50.0, 50.0]),
+        visualze_sampled_trajs=True, seed=2024, verbose=False)
+    err = []
+    for k in range(1, 1501):
+        u, seq, opt, samp = mppi.calc_control_input(observed_x=state)
+        dq += dt * Arm_Dynamic(q, dq, u)
+        q += dt * dq
+        _, _, x2, y2 = Forward_Kinemetic(q)
+        state = np.concatenate((q, dq))
+        p = mppi.prev_waypoints_idx
+        err.append(np.hypot(x2 - ref[p, 0], y2 - ref[p, 1]))
+        assert samp.shape == (100, 30, 4) and np.all(np.isfinite(samp))
+    err = np.array(err)
+    # reference over seeds: mean 0.011-0.020 m, max 0.024-0.069 m, final index 1720-1768
+    assert err[50:].mean() <= 0.03 and err[50:].max() <= 0.08, (err.mean(), err.max())
+    assert 1650 <= mppi.prev_waypoints_idx <= 1850, mppi.prev_waypoints_idx
+    assert abs(mppi.prev_waypoints_idx - int(ref_run["prev_idx"][-1, 1])) <= 120
+    mppi.close()

@@ -1,0 +1,97 @@
+"""CPU tests of the host-side logic around the CUDA step."""
+import numpy as np
+import pytest
+
+from mppi_robotarm_b200 import load_ref_path
+from mppi_robotarm_b200.engine import ShardSpec, exploit_count
+from oracle import mppi_oracle as mo
+from tests.golden import cases
+
+
+def test_constructor_mirrors_reference_attributes(paths):
+    from control import MPPIControllerForPathTracking
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    c = MPPIControllerForPathTracking(**cases.run_py_kwargs(ref, 100, 30), visualze_sampled_trajs=True)
+    assert (c.dim_x, c.dim_u, c.T, c.K) == (4, 2, 30, 100)
+    assert c.param_gamma == pytest.approx(100.0 * (1 - 0.98))
+    assert c.l1 == 1 and c.l2 == 1 and c.prev_waypoints_idx == 0
+    np.testing.assert_array_equal(c.u_prev, np.tile([10.0, -2.0], (30, 1)))
+    assert c.visualze_sampled_trajs is True and c.visualize_optimal_traj is True
+    assert c.ref_path is ref and c.delta_t == 0.006
+    # defaults of control.py:21-35
+    d = MPPIControllerForPathTracking()
+    assert (d.T, d.K, d.param_lambda, d.param_alpha, d.delta_t) == (20, 500, 50.0, 1.0, 0.01)
+    np.testing.assert_array_equal(d.Sigma, [[10.0, 10.0], [100.0, 100.0]])
+
+
+def test_calc_epsilon_seam_and_sigma_check(paths, capsys):
+    from control import MPPIControllerForPathTracking
+    c = MPPIControllerForPathTracking(**cases.run_py_kwargs(cases.ref_path_for(paths, "xydq_circle.txt"), 16, 5))
+    np.random.seed(0)
+    e = c._calc_epsilon(c.Sigma, 16, 5, 2)
+    np.random.seed(0)
+    np.testing.assert_array_equal(e, np.random.multivariate_normal(np.zeros(2), c.Sigma, (16, 5)))
+    with pytest.raises(ValueError):
+        c._calc_epsilon(np.eye(3), 16, 5, 2)
+    assert "sigma must be a square matrix" in capsys.readouterr().out
+
+
+def test_host_nearest_waypoint_helper_matches_oracle(paths):
+    from control import MPPIControllerForPathTracking
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    c = MPPIControllerForPathTracking(**cases.run_py_kwargs(ref, 16, 5), verbose=False)
+    o = mo.OracleMPPI(**cases.run_py_kwargs(ref, 16, 5))
+    for p, q in ((0, cases.X0[:2]), (700, [0.9, 0.6]), (1990, [1.15, -1.26])):
+        c.prev_waypoints_idx = o.prev_waypoints_idx = p
+        idx, rx, ry, r1, r2 = c._get_nearest_waypoint(q[0], q[1])
+        assert idx == p + int(mo.nearest_in_window(mo.window_of(ref, p), *mo.end_effector(q[0], q[1])))
+        np.testing.assert_array_equal([rx, ry, r1, r2], ref[idx])
+        assert c.prev_waypoints_idx == p
+        c._get_nearest_waypoint(q[0], q[1], update_prev_idx=True)
+        assert c.prev_waypoints_idx == mo.update_waypoint(o, q[0], q[1])
+
+
+def test_exploit_count_is_the_python_comparison():
+    for K in (1, 7, 50, 64, 100, 4096, 1 << 20):
+        for ex in (0.0, 0.1, 0.25, 0.33, 0.5, 0.999, 1.0):
+            ks = np.arange(K)
+            assert exploit_count(K, ex) == int(np.count_nonzero(ks < (1.0 - ex) * K))
+
+
+def test_shard_bounds_partition_the_samples():
+    for K in (7, 100, 4096, 1 << 20, 1000003):
+        for world in (1, 2, 3, 4, 8):
+            spans = [ShardSpec(r, world).bounds(K) for r in range(world)]
+            assert spans[0][0] == 0 and sum(n for _, n in spans) == K
+            for (o1, n1), (o2, _) in zip(spans, spans[1:]):
+                assert o1 + n1 == o2
+            assert max(n for _, n in spans) - min(n for _, n in spans) <= 1
+
+
+def test_load_ref_path_layouts(tmp_path, paths):
+    p = tmp_path / "xydq_circle.txt"
+    np.savetxt(p, paths["xydq_circle"], fmt="%.18e")
+    np.testing.assert_array_equal(load_ref_path(p), paths["xydq_circle"][:, 0:4])     # run.py:18-19
+    t = tmp_path / "trajectory.txt"
+    np.savetxt(t, paths["trajectory"], fmt="%.18e")
+    np.testing.assert_array_equal(load_ref_path(t, "verbatim"), paths["trajectory"][:, 0:4])
+    conv = load_ref_path(t)                     # auto -> (x, y, dq1, dq2)
+    np.testing.assert_array_equal(conv[:, 0:2], paths["trajectory"][:, 2:4])
+    np.testing.assert_allclose(conv, cases.relayout_qxy(paths["trajectory"]))
+    with pytest.raises(ValueError):
+        load_ref_path(t, "nonsense")
+
+
+def test_plant_helpers_match_oracle_twin():
+    import utils
+    rng = np.random.default_rng(2)
+    for _ in range(10):
+        q, dq, u = rng.normal(0, 1, 2), rng.normal(0, 1, 2), rng.normal(0, 10, 2)
+        np.testing.assert_allclose(utils.Arm_Dynamic(q, dq, u),
+                                   mo.arm_accel(q[0], q[1], dq[0], dq[1], u[0], u[1], mo.default_arm_params()),
+                                   rtol=1e-13, atol=1e-13)
+        x1, y1, x2, y2 = utils.Forward_Kinemetic(q)
+        np.testing.assert_allclose((x2, y2), mo.end_effector(q[0], q[1]), rtol=1e-14)
+        np.testing.assert_allclose((x1, y1), (np.cos(q[0]), np.sin(q[0])), rtol=1e-14)
+    import sys_params
+    assert sys_params.SYS_PARAMS() == mo.default_arm_params()

@@ -140,9 +140,10 @@ class MPPIControllerForPathTracking:
 
         if self.visualze_sampled_trajs:                   # control.py:137-145
             sampled_traj_list = self._gather_sampled(eng)
-        elif self.K * self.T * self.dim_x <= (1 << 22):
+        elif self.K * self.T * self.dim_x <= (1 << 17):
             sampled_traj_list = np.zeros((self.K, self.T, self.dim_x))
-        else:   # the reference allocates K*T*4 float64 zeros every call; don't do that at K = 1M
+        else:   # the reference allocates K*T*4 float64 zeros every call (26 MB at K=16384, T=50): return a
+                # read-only zero view of the same shape and dtype instead
             sampled_traj_list = np.broadcast_to(np.zeros(()), (self.K, self.T, self.dim_x))
 
         self.u_prev[:-1] = u[1:]                          # control.py:148

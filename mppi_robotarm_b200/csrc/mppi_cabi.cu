@@ -3,9 +3,11 @@
 // (reference: /root/reference/control.py:67-152).  No torch types, no exceptions, no CPU fallback.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <math.h>
 #include <new>
+#include <mutex>
 
 #include "../../include/mppi_b200.h"
 #define MPPI_MAX_T_INTERNAL MPPI_MAX_T
@@ -50,6 +52,8 @@ struct MppiHandle {
     void* graph_stream;
     uint64_t graph_kernels;
     bool have_step;            // a step has run (step blocks valid)
+    bool const_window;         // single environment: window coefficients go through the constant bank
+    cudaEvent_t const_ev;      // recorded after this handle's last reader of the constant-bank window
     char err[512];
 };
 
@@ -85,7 +89,7 @@ bool valid_cfg(const MppiConfig* c, const char** why) {
 
 void grid_sizes(const MppiConfig* c, int sm, int* g_roll, int* g_soft, int* g_wsum) {
     const int K = c->K_local;
-    int gr = (K + kRollThreads - 1) / kRollThreads;
+    int gr = (K + kRollThreads * kNS - 1) / (kRollThreads * kNS);
     if (gr > 32768) gr = 32768;
     *g_roll = gr;
     int gs = (K + kSoftThreads * 4 - 1) / (kSoftThreads * 4);
@@ -93,8 +97,9 @@ void grid_sizes(const MppiConfig* c, int sm, int* g_roll, int* g_soft, int* g_ws
     if (gs > cap) gs = cap;
     if (gs < 1) gs = 1;
     *g_soft = gs;
-    int gw = (K + 2047) / 2048;
-    if (gw > cap) gw = cap;
+    int gw = (K + 4095) / 4096;
+    const int capw = (2 * sm + c->n_env - 1) / c->n_env;
+    if (gw > capw) gw = capw;
     if (gw < 1) gw = 1;
     *g_wsum = gw;
 }
@@ -159,9 +164,34 @@ void fill_dev_cfg(MppiHandle* h) {
     d.cost_l1 = c.cost_l1; d.cost_l2 = c.cost_l2;
 }
 
+// The constant-bank window table is one symbol per device, shared by every handle of the process.
+// Work of one handle is stream-ordered (copy -> rollout); work of *different* handles is ordered on
+// the device by making the newcomer's stream wait for the previous owner's last reader.
+struct ConstOwner { MppiHandle* h; cudaEvent_t ev; };
+ConstOwner g_const_owner[64];
+std::mutex g_const_mu;
+
+int const_acquire(MppiHandle* h, cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(g_const_mu);
+    ConstOwner& o = g_const_owner[h->cfg.device & 63];
+    if (o.h && o.h != h) CU(h, cudaStreamWaitEvent(s, o.ev, 0));
+    return MPPI_OK;
+}
+int const_release(MppiHandle* h, cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(g_const_mu);
+    CU(h, cudaEventRecord(h->const_ev, s));
+    g_const_owner[h->cfg.device & 63] = ConstOwner{h, h->const_ev};
+    return MPPI_OK;
+}
+void const_forget(MppiHandle* h) {
+    std::lock_guard<std::mutex> lk(g_const_mu);
+    ConstOwner& o = g_const_owner[h->cfg.device & 63];
+    if (o.h == h) { cudaEventSynchronize(o.ev); o.h = nullptr; }
+}
+
 // enqueue everything up to this shard's partial triple
 int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* partial_dev, cudaStream_t s,
-                  bool timed) {
+                  bool timed, bool capturing = false) {
     const DevCfg& dc = h->dc;
     char* ws = h->dev;
     if (noise_mode != MPPI_NOISE_PHILOX && noise_mode != MPPI_NOISE_INJECTED)
@@ -185,10 +215,21 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
     if (timed) CU(h, cudaEventRecord(h->tev[1], s));
     {
         dim3 grid(dc.g_roll, dc.n_env);
-        if (noise_mode == MPPI_NOISE_PHILOX)
-            mppi_rollout_sm100a<0><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, nullptr, S, bmin);
-        else
-            mppi_rollout_sm100a<1><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, eps_dev, S, bmin);
+        if (h->const_window) {
+            // single environment: stage this step's window coefficients in the constant bank
+            if (!capturing) { int rc = const_acquire(h, s); if (rc != MPPI_OK) return rc; }
+            CU(h, cudaMemcpyToSymbolAsync(c_window, step_blocks + 64, sizeof(WinEntry) * kWindowPad, 0,
+                                          cudaMemcpyDeviceToDevice, s));
+            if (noise_mode == MPPI_NOISE_PHILOX)
+                mppi_rollout_sm100a<0, true><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, nullptr, S, bmin);
+            else
+                mppi_rollout_sm100a<1, true><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, eps_dev, S, bmin);
+            if (!capturing) { int rc = const_release(h, s); if (rc != MPPI_OK) return rc; }
+        } else if (noise_mode == MPPI_NOISE_PHILOX) {
+            mppi_rollout_sm100a<0, false><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, nullptr, S, bmin);
+        } else {
+            mppi_rollout_sm100a<1, false><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, eps_dev, S, bmin);
+        }
     }
     if (timed) CU(h, cudaEventRecord(h->tev[2], s));
     mppi_softmin_sm100a<<<dim3(dc.g_soft, dc.n_env), kSoftThreads, 0, s>>>(dc, S, bmin, w, eta_part, rho);
@@ -205,7 +246,7 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
         }
     }
     if (timed) CU(h, cudaEventRecord(h->tev[4], s));
-    mppi_reduce_sm100a<<<dc.n_env, 256, 0, s>>>(dc, rho, eta_part, v_part, partial_dev);
+    mppi_reduce_sm100a<<<dc.n_env, kReduceThreads, 0, s>>>(dc, rho, eta_part, v_part, partial_dev);
     if (timed) CU(h, cudaEventRecord(h->tev[5], s));
     CU(h, cudaGetLastError());
     h->launches += 5;
@@ -324,7 +365,9 @@ int mppi_create(const MppiConfig* c, void* workspace, size_t workspace_bytes, vo
     h->dio.u_new = (double*)(dout + h->io.off_u_new);
     h->dio.opt_traj = (double*)(dout + h->io.off_opt_traj);
     h->roll_smem = (size_t)h->dc.step_block_bytes;
+    h->const_window = (c->n_env == 1) && getenv("MPPI_NO_CONST_WINDOW") == nullptr;
     cudaError_t e = cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->const_ev, cudaEventDisableTiming);
     for (int i = 0; i <= kNumTimers && e == cudaSuccess; ++i) e = cudaEventCreate(&h->tev[i]);
     if (e != cudaSuccess) {
         snprintf(g_create_error, sizeof(g_create_error), "cudaEventCreate -> %s", cudaGetErrorString(e));
@@ -338,8 +381,10 @@ int mppi_create(const MppiConfig* c, void* workspace, size_t workspace_bytes, vo
 void mppi_destroy(MppiHandle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
+    const_forget(h);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->done) cudaEventDestroy(h->done);
+    if (h->const_ev) cudaEventDestroy(h->const_ev);
     for (int i = 0; i <= kNumTimers; ++i)
         if (h->tev[i]) cudaEventDestroy(h->tev[i]);
     delete h;
@@ -386,7 +431,7 @@ int mppi_step(MppiHandle* h, int32_t noise_mode, const float* eps_dev, void* str
             const uint64_t before = h->launches;
             cudaGraph_t g = nullptr;
             CU(h, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            int rc = enqueue_local(h, noise_mode, nullptr, partial, s, false);
+            int rc = enqueue_local(h, noise_mode, nullptr, partial, s, false, /*capturing=*/true);
             if (rc == MPPI_OK) rc = enqueue_combine(h, partial, 1, s, false, /*record_done=*/false);
             cudaError_t ce = cudaStreamEndCapture(s, &g);
             if (rc != MPPI_OK) { if (g) cudaGraphDestroy(g); return rc; }
@@ -397,7 +442,9 @@ int mppi_step(MppiHandle* h, int32_t noise_mode, const float* eps_dev, void* str
             h->launches = before;
             h->graph_stream = stream;
         }
+        if (h->const_window) { int rc = const_acquire(h, s); if (rc != MPPI_OK) return rc; }
         CU(h, cudaGraphLaunch(h->graph_exec, s));
+        if (h->const_window) { int rc = const_release(h, s); if (rc != MPPI_OK) return rc; }
         CU(h, cudaEventRecord(h->done, s));
         h->launches += h->graph_kernels;
         h->timing_pending = false;

@@ -16,6 +16,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "mppi_math.cuh"
 
 namespace mppi {
@@ -171,8 +172,43 @@ struct InjectedNoise {          // eps read from the caller's [K,T,2] tensor
     }
 };
 
-template <int NOISE>
-__global__ void __launch_bounds__(kRollThreads, 3)
+#ifndef MPPI_NS
+#define MPPI_NS 2                  // samples per thread in the rollout kernel (A/B on B200: profiles/r1_variants.md)
+#endif
+
+// Single-environment fast path: the window coefficients of the current step are copied (device to
+// device, in stream order after the prepare kernel) into this constant-bank table, and the search's
+// FFMAs read them as immediate constant operands: no registers, no shared-memory loads, and two
+// register operands per FFMA instead of three.
+__constant__ WinEntry c_window[kWindowPad];
+#ifndef MPPI_CONST_C_REG
+#define MPPI_CONST_C_REG 1     // keep c_j in registers so that each FFMA of the search has ONE constant operand
+#endif
+struct WinConst {
+#if MPPI_CONST_C_REG
+    float wc[kWindow];
+    __device__ __forceinline__ float c(int j) const { return wc[j]; }
+    __device__ __forceinline__ void load(const WinEntry* tab) {
+#pragma unroll
+        for (int j = 0; j < kWindow; ++j) wc[j] = tab[j].c;
+    }
+#else
+    __device__ __forceinline__ float c(int j) const { return c_window[j].c; }
+    __device__ __forceinline__ void load(const WinEntry*) {}
+#endif
+    __device__ __forceinline__ float a(int j) const { return c_window[j].a; }
+    __device__ __forceinline__ float b(int j) const { return c_window[j].b; }
+};
+#ifndef MPPI_ROLL_MIN_BLOCKS
+#define MPPI_ROLL_MIN_BLOCKS (MPPI_NS == 1 ? 3 : 2)
+#endif
+#ifndef MPPI_ROLL_MIN_BLOCKS_CONST
+#define MPPI_ROLL_MIN_BLOCKS_CONST 4
+#endif
+constexpr int kNS = MPPI_NS;
+
+template <int NOISE, bool CONSTWIN>
+__global__ void __launch_bounds__(kRollThreads, CONSTWIN ? MPPI_ROLL_MIN_BLOCKS_CONST : MPPI_ROLL_MIN_BLOCKS)
 mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const char* __restrict__ step_blocks,
                     const float* __restrict__ eps, float* __restrict__ S_out, float* __restrict__ block_min) {
     extern __shared__ __align__(128) unsigned char smem_roll[];
@@ -189,25 +225,42 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
     mbar_wait(&bar, 0);
     const StepBlockView sb = view_step_block(smem);
     const StepHeader hd = *sb.hd;
-    float wa[kWindow], wb[kWindow], wc[kWindow];
-#pragma unroll
-    for (int j = 0; j < kWindow; ++j) { const WinEntry w = sb.win[j]; wa[j] = w.a; wb[j] = w.b; wc[j] = w.c; }
+    typename std::conditional<CONSTWIN, WinConst, WinRegs>::type win;
+    win.load(sb.win);
 
     float tmin = INFINITY;
     const int T = cfg.T;
-    for (int kl = blockIdx.x * kRollThreads + tid; kl < cfg.K_local; kl += gridDim.x * kRollThreads) {
-        const int kg = cfg.k_offset + kl;
-        const float um = kg < cfg.n_exploit ? 1.0f : 0.0f;
-        float S;
-        if (NOISE == 0) {
-            PhiloxNoise nz; nz.nc = cfg.noise; nz.nc.step = (uint32_t)(*step_ctr); nz.env = (uint32_t)e; nz.k = (uint32_t)kg;
-            S = rollout_cost(hd, cfg.arm, cfg.cost, wa, wb, wc, sb.rows, sb.ctl, T, um, nz);
-        } else {
-            InjectedNoise nz; nz.row = (const float2*)eps + ((size_t)e * cfg.K_local + kl) * T;
-            S = rollout_cost(hd, cfg.arm, cfg.cost, wa, wb, wc, sb.rows, sb.ctl, T, um, nz);
+    // thread handles samples kl0 + s*kRollThreads (s < NS): consecutive lanes -> consecutive samples
+    for (int kl0 = blockIdx.x * (kRollThreads * kNS) + tid; kl0 < cfg.K_local; kl0 += gridDim.x * kRollThreads * kNS) {
+        float um[kNS], S[kNS];
+        int kl[kNS];
+#pragma unroll
+        for (int s = 0; s < kNS; ++s) {
+            // a padding sample past the end recomputes the last one (its result is not stored)
+            kl[s] = min(kl0 + s * kRollThreads, cfg.K_local - 1);
+            um[s] = (cfg.k_offset + kl[s]) < cfg.n_exploit ? 1.0f : 0.0f;
         }
-        S_out[(size_t)e * cfg.K_local + kl] = S;
-        if (finite_(S)) tmin = fminf(tmin, S);
+        if (NOISE == 0) {
+            PhiloxNoise nz[kNS];
+#pragma unroll
+            for (int s = 0; s < kNS; ++s) {
+                nz[s].nc = cfg.noise; nz[s].nc.step = (uint32_t)(*step_ctr); nz[s].env = (uint32_t)e;
+                nz[s].k = (uint32_t)(cfg.k_offset + kl[s]);
+            }
+            rollout_cost_n<kNS>(hd, cfg.arm, cfg.cost, win, sb.rows, sb.ctl, T, um, nz, S);
+        } else {
+            InjectedNoise nz[kNS];
+#pragma unroll
+            for (int s = 0; s < kNS; ++s) nz[s].row = (const float2*)eps + ((size_t)e * cfg.K_local + kl[s]) * T;
+            rollout_cost_n<kNS>(hd, cfg.arm, cfg.cost, win, sb.rows, sb.ctl, T, um, nz, S);
+        }
+#pragma unroll
+        for (int s = 0; s < kNS; ++s) {
+            if (kl0 + s * kRollThreads < cfg.K_local) {
+                S_out[(size_t)e * cfg.K_local + kl[s]] = S[s];
+                if (finite_(S[s])) tmin = fminf(tmin, S[s]);
+            }
+        }
     }
     tmin = warp_min(tmin);
     if ((tid & 31) == 0) red[tid >> 5] = tmin;
@@ -406,27 +459,41 @@ mppi_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const
 // 5. reduce: this GPU's partial triple per environment, FP64, fixed summation order.
 //    partial[e] = { rho_g, eta_g, V_g[2T] }
 // ================================================================================================
-__global__ void __launch_bounds__(256)
+constexpr int kReduceThreads = 1024;
+
+__global__ void __launch_bounds__(kReduceThreads)
 mppi_reduce_sm100a(DevCfg cfg, const float* __restrict__ rho, const double* __restrict__ eta_part,
                    const float* __restrict__ v_part, double* __restrict__ partial) {
-    __shared__ double red[8];
+    __shared__ double red[kReduceThreads / 32];
+    __shared__ double colsum[kReduceThreads];
     const int e = blockIdx.x, tid = threadIdx.x;
     double* out = partial + (size_t)e * (2 + 2 * cfg.T);
     double a = 0.0;
-    for (int i = tid; i < cfg.g_soft; i += 256) a += eta_part[(size_t)e * cfg.g_soft + i];
+    for (int i = tid; i < cfg.g_soft; i += kReduceThreads) a += eta_part[(size_t)e * cfg.g_soft + i];
     a = warp_sum(a);
     if ((tid & 31) == 0) red[tid >> 5] = a;
     __syncthreads();
     if (tid == 0) {
         double s = 0.0;
-        for (int i = 0; i < 8; ++i) s += red[i];
+        for (int i = 0; i < kReduceThreads / 32; ++i) s += red[i];
         out[0] = (double)rho[e]; out[1] = s;
     }
-    for (int c = tid; c < 2 * cfg.T; c += 256) {
-        double s = 0.0;
-        const float* src = v_part + (size_t)e * cfg.g_wsum * 2 * cfg.T + c;
-        for (int b = 0; b < cfg.g_wsum; ++b) s += (double)src[(size_t)b * 2 * cfg.T];
-        out[2 + c] = s;
+    // V_g[c] = sum over the weighted-sum kernel's blocks: thread (slice, c) adds every n_slice-th
+    // block, then the slices are added in a fixed order
+    const int C = 2 * cfg.T;
+    const int n_slice = kReduceThreads / C;                 // >= 2 because C <= 512
+    const int slice = tid / C, c = tid - slice * C;
+    double s = 0.0;
+    if (slice < n_slice) {
+        const float* src = v_part + (size_t)e * cfg.g_wsum * C + c;
+        for (int b = slice; b < cfg.g_wsum; b += n_slice) s += (double)src[(size_t)b * C];
+        colsum[slice * C + c] = s;
+    }
+    __syncthreads();
+    if (tid < C) {
+        double t = colsum[tid];
+        for (int i = 1; i < n_slice; ++i) t += colsum[i * C + tid];
+        out[2 + tid] = t;
     }
 }
 

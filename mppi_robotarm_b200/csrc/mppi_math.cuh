@@ -264,18 +264,33 @@ struct StepHeader {            // first 64 bytes of a step block (one per enviro
 };
 static_assert(sizeof(StepHeader) == 64, "header is 64 bytes");
 
+// Where the 30 x (a, b, c) window coefficients live.  WinRegs: per-thread registers (any number of
+// environments).  The kernels add WinConst: the constant bank, read as immediate FFMA operands.
+struct WinRegs {
+    float wa[kWindow], wb[kWindow], wc[kWindow];
+    MPPI_HD float a(int j) const { return wa[j]; }
+    MPPI_HD float b(int j) const { return wb[j]; }
+    MPPI_HD float c(int j) const { return wc[j]; }
+    MPPI_HD void load(const WinEntry* tab) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < kWindow; ++j) { const WinEntry w = tab[j]; wa[j] = w.a; wb[j] = w.b; wc[j] = w.c; }
+    }
+};
+
 // Nearest-waypoint search (control.py:208-215): first arg-min over the 30 window candidates.
 // Exact FP32 comparisons on d_j - |p'|^2 = c_j + a_j x' + b_j y', as a tournament tree of depth 5;
 // `<` is strict and the right operand always carries the larger index, so ties keep the first
 // candidate like list.index(min(d)) does.
-MPPI_HD int nearest_candidate(const float (&wa)[kWindow], const float (&wb)[kWindow],
-                              const float (&wc)[kWindow], float xl, float yl) {
+template <class Win>
+MPPI_HD int nearest_candidate(const Win& win, float xl, float yl) {
     float d[kWindowPad];
     int id[kWindowPad];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int j = 0; j < kWindow; ++j) { d[j] = fma_(wa[j], xl, fma_(wb[j], yl, wc[j])); id[j] = j; }
+    for (int j = 0; j < kWindow; ++j) { d[j] = fma_(win.a(j), xl, fma_(win.b(j), yl, win.c(j))); id[j] = j; }
     d[30] = kSentinel; d[31] = kSentinel; id[30] = 30; id[31] = 31;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -293,37 +308,147 @@ MPPI_HD int nearest_candidate(const float (&wa)[kWindow], const float (&wb)[kWin
     return id[0];
 }
 
-template <class Noise>
-MPPI_HD float rollout_cost(const StepHeader& hd, const ArmF& A, const CostW& W,
-                           const float (&wa)[kWindow], const float (&wb)[kWindow],
-                           const float (&wc)[kWindow], const RefRow* rows, const StepCtl* ctl,
-                           int T, float um, Noise& noise) {
-    ArmState st;
-    arm_init(st, hd.q1, hd.q2, hd.d1, hd.d2);
-    float S = 0.0f, kS = 0.0f;
-    float ex = 0.f, ey = 0.f, e1 = 0.f, e2 = 0.f;
-    for (int t = 0; t < T; ++t) {
-        float n1, n2;
-        noise(t, n1, n2);
-        const StepCtl c = ctl[t];
-        float v1 = fma_(um, c.u1, n1);             // control.py:98-101 (um = 0 for exploration samples)
-        float v2 = fma_(um, c.u2, n2);
-        arm_step(st, A, v1, v2);
-        float xl, yl;
-        fk_local(st, A, hd.ox, hd.oy, xl, yl);
-        const int j = nearest_candidate(wa, wb, wc, xl, yl);
-        const RefRow r = rows[j];
-        residuals(st, xl, yl, r, ex, ey, e1, e2);
-        float cst = wsq(W.s0, W.s1, W.s2, W.s3, ex, ey, e1, e2);
-        cst = fma_(c.g1, v1, fma_(c.g2, v2, cst)); // + gamma * u^T Sigma^-1 v  (control.py:106)
-#ifndef MPPI_NO_KAHAN
-        kahan_(S, kS, sub_(cst, kS));
-#else
-        S = add_(S, cst);
+// Variant of the search that keeps the ALU pipe (half rate on sm_100) free: the minimum VALUE comes
+// from an FMNMX3 tree, then every candidate is mapped on the FMA pipe to h_j = (d_j - m)*HUGE + j,
+// which equals j exactly where d_j == m and is >= 2^40 elsewhere, and a second FMNMX3 tree returns the
+// smallest such j — the same first-arg-min, ties included (d_j - m is exact or large by Sterbenz).
+template <class Win>
+MPPI_HD int nearest_candidate_fma(const Win& win, float xl, float yl) {
+    float d[kWindow];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
 #endif
+    for (int j = 0; j < kWindow; ++j) d[j] = fma_(win.a(j), xl, fma_(win.b(j), yl, win.c(j)));
+    float m[10];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 10; ++i) m[i] = min3_(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+    const float best = fminf(min3_(min3_(m[0], m[1], m[2]), min3_(m[3], m[4], m[5]), min3_(m[6], m[7], m[8])), m[9]);
+    float h[kWindow];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < kWindow; ++j) h[j] = fma_(sub_(d[j], best), 1.0e30f, (float)j);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 10; ++i) m[i] = min3_(h[3 * i], h[3 * i + 1], h[3 * i + 2]);
+    const float hj = fminf(min3_(min3_(m[0], m[1], m[2]), min3_(m[3], m[4], m[5]), min3_(m[6], m[7], m[8])), m[9]);
+    return (int)hj;
+}
+
+// Tournament whose index selects run on the FMA pipe: value = FMNMX, lt = FSET (1.0 / 0.0),
+// index = idxA + lt * (idxB - idxA) evaluated exactly on small integers held as floats.
+template <class Win>
+MPPI_HD int nearest_candidate_arith(const Win& win, float xl, float yl) {
+    float d[kWindowPad], id[kWindowPad];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < kWindow; ++j) { d[j] = fma_(win.a(j), xl, fma_(win.b(j), yl, win.c(j))); id[j] = (float)j; }
+    d[30] = kSentinel; d[31] = kSentinel; id[30] = 30.f; id[31] = 31.f;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int w = 1; w < kWindowPad; w *= 2) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j + w < kWindowPad; j += 2 * w) {
+            const float lt = d[j + w] < d[j] ? 1.0f : 0.0f;
+            d[j] = fminf(d[j + w], d[j]);
+            id[j] = fma_(lt, sub_(id[j + w], id[j]), id[j]);
+        }
+    }
+    return (int)id[0];
+}
+
+#ifndef MPPI_SEARCH
+#define MPPI_SEARCH 0
+#endif
+template <class Win>
+MPPI_HD int nearest_wp(const Win& win, float xl, float yl) {
+#if MPPI_SEARCH == 1
+    return nearest_candidate_fma(win, xl, yl);
+#elif MPPI_SEARCH == 2
+    return nearest_candidate_arith(win, xl, yl);
+#else
+    return nearest_candidate(win, xl, yl);
+#endif
+}
+
+// NS samples advance in lockstep inside one thread: they share the window registers, the per-step
+// constants and the loop overhead, and give the scheduler NS independent instruction streams.
+template <int NS, class Win, class Noise>
+MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
+                            const Win& win, const RefRow* rows, const StepCtl* ctl,
+                            int T, const float (&um)[NS], Noise (&noise)[NS], float (&S_out)[NS]) {
+    ArmState st[NS];
+    float S[NS], kS[NS], ex[NS], ey[NS], e1[NS], e2[NS];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int s = 0; s < NS; ++s) {
+        arm_init(st[s], hd.q1, hd.q2, hd.d1, hd.d2);
+        S[s] = 0.f; kS[s] = 0.f; ex[s] = 0.f; ey[s] = 0.f; e1[s] = 0.f; e2[s] = 0.f;
+    }
+    for (int t = 0; t < T; ++t) {
+        const StepCtl c = ctl[t];
+        float v1[NS], v2[NS], xl[NS], yl[NS];
+        int j[NS];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int s = 0; s < NS; ++s) {
+            float n1, n2;
+            noise[s](t, n1, n2);
+            v1[s] = fma_(um[s], c.u1, n1);             // control.py:98-101 (um = 0 for exploration samples)
+            v2[s] = fma_(um[s], c.u2, n2);
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int s = 0; s < NS; ++s) arm_step(st[s], A, v1[s], v2[s]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int s = 0; s < NS; ++s) {
+            fk_local(st[s], A, hd.ox, hd.oy, xl[s], yl[s]);
+            j[s] = nearest_wp(win, xl[s], yl[s]);
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int s = 0; s < NS; ++s) {
+            const RefRow r = rows[j[s]];
+            residuals(st[s], xl[s], yl[s], r, ex[s], ey[s], e1[s], e2[s]);
+            float cst = wsq(W.s0, W.s1, W.s2, W.s3, ex[s], ey[s], e1[s], e2[s]);
+            cst = fma_(c.g1, v1[s], fma_(c.g2, v2[s], cst));   // + gamma * u^T Sigma^-1 v  (control.py:106)
+#ifndef MPPI_NO_KAHAN
+            kahan_(S[s], kS[s], sub_(cst, kS[s]));
+#else
+            S[s] = add_(S[s], cst);
+#endif
+        }
     }
     // terminal cost on the same final state and the same nearest waypoint (control.py:109, Q5)
-    return add_(S, sub_(wsq(W.t0, W.t1, W.t2, W.t3, ex, ey, e1, e2), kS));
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int s = 0; s < NS; ++s)
+        S_out[s] = add_(S[s], sub_(wsq(W.t0, W.t1, W.t2, W.t3, ex[s], ey[s], e1[s], e2[s]), kS[s]));
+}
+
+template <class Win, class Noise>
+MPPI_HD float rollout_cost(const StepHeader& hd, const ArmF& A, const CostW& W,
+                           const Win& win, const RefRow* rows, const StepCtl* ctl,
+                           int T, float um, Noise& noise) {
+    const float ums[1] = { um };
+    float out[1];
+    Noise (&nz)[1] = reinterpret_cast<Noise (&)[1]>(noise);
+    rollout_cost_n<1>(hd, A, W, win, rows, ctl, T, ums, nz, out);
+    return out[0];
 }
 
 }  // namespace mppi

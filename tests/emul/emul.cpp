@@ -30,11 +30,9 @@ int emul_rollout_costs(const double* ref, int n_rows, int prev_idx, const double
     StepHeader hd{};
     hd.q1 = (float)x0[0]; hd.q2 = (float)x0[1]; hd.d1 = (float)x0[2]; hd.d2 = (float)x0[3];
     hd.ox = (float)ref[4 * p]; hd.oy = (float)ref[4 * p + 1]; hd.win_start = p;
-    float wa[kWindow], wb[kWindow], wc[kWindow]; RefRow rows[kWindowPad];
-    for (int j = 0; j < kWindowPad; ++j) {
-        WinEntry w; make_window_row(ref, n_rows, p, j, w, rows[j]);
-        if (j < kWindow) { wa[j] = w.a; wb[j] = w.b; wc[j] = w.c; }
-    }
+    WinRegs win; RefRow rows[kWindowPad]; WinEntry tab[kWindowPad];
+    for (int j = 0; j < kWindowPad; ++j) make_window_row(ref, n_rows, p, j, tab[j], rows[j]);
+    win.load(tab);
     std::vector<StepCtl> ctl(T);
     for (int t = 0; t < T; ++t) make_step_ctl(u_prev + 2 * t, gamma, sig_inv, ctl[t]);
     const double m1 = arm[0], m2 = arm[1], l1 = arm[2], l2 = arm[3], lc1 = arm[4], lc2 = arm[5], g = arm[6];
@@ -49,7 +47,7 @@ int emul_rollout_costs(const double* ref, int n_rows, int prev_idx, const double
              (float)(wt[0] * 1e4), (float)(wt[1] * 1e4), (float)(wt[2] * 1e4), (float)(wt[3] * 1e4) };
     for (int k = 0; k < K; ++k) {
         EpsArray n{ eps + (size_t)k * T * 2, T };
-        S_out[k] = rollout_cost(hd, A, W, wa, wb, wc, rows, ctl.data(), T, k < n_exploit ? 1.f : 0.f, n);
+        S_out[k] = rollout_cost(hd, A, W, win, rows, ctl.data(), T, k < n_exploit ? 1.f : 0.f, n);
     }
     return p;
 }

@@ -313,3 +313,24 @@ def test_free_running_philox_closed_loop_tracks_like_the_reference(paths):
     print("philox closed loops: mean err", means, "max err", maxs, "final idx", finals)
     assert np.median(means) <= 0.04 and max(maxs) <= 0.15
     assert all(1600 <= f <= 1900 for f in finals), finals
+
+
+def test_two_handles_in_flight_do_not_share_window_state(paths):
+    """Single-environment handles stage their window in one constant-bank table per device; steps of
+    different handles launched back to back on different streams must still see their own window."""
+    T = 20
+    a = _engine(paths, 20000, T, seed=1)
+    b = _engine(paths, 20000, T, seed=2)
+    xa, xb = np.array(cases.X0), np.array([paths["trajectory1"][900, 0], paths["trajectory1"][900, 1], 0.1, -0.1])
+    # sequential reference results
+    a.step(xa, _u0(T), 0, None); ua = a.out_u_new.copy(); ia = int(a.out_new_idx[0])
+    b.step(xb, _u0(T), 890, None); ub = b.out_u_new.copy(); ib = int(b.out_new_idx[0])
+    assert ia != ib
+    for _ in range(5):
+        a.step_counter = 0; b.step_counter = 0
+        a.write_inputs(xa, _u0(T), 0); b.write_inputs(xb, _u0(T), 890)
+        a.launch(None); b.launch(None)           # both in flight
+        b.wait(); a.wait()
+        np.testing.assert_array_equal(a.out_u_new, ua)
+        np.testing.assert_array_equal(b.out_u_new, ub)
+    a.close(); b.close()

@@ -1,0 +1,6 @@
+#!/bin/bash
+# A/B the rollout-kernel build variants in build/variants/*.so at the bench shape (K=2^20, T=100).
+for lib in build/variants/*.so; do
+  echo "== $lib"
+  MPPI_B200_LIB=$PWD/$lib python tools/profile_step.py --K 1048576 --T 100 --steps 12 --timing 2>&1 | tail -2
+done

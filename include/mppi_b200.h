@@ -132,6 +132,14 @@ int mppi_step_combine(MppiHandle* h, const double* gathered_dev, int32_t world, 
 
 int mppi_wait(MppiHandle* h);
 
+/* Caller-side CUDA-graph capture of the sharded step (mppi_step_local + the caller's collective +
+ * mppi_step_combine on one capturing stream): while capture mode is on, the library enqueues only
+ * capturable work (no event records).  Each replay of the caller's graph is bracketed by
+ * mppi_replay_begin() / mppi_replay_end() on the replay stream; mppi_wait() then works as usual. */
+int mppi_set_capture_mode(MppiHandle* h, int32_t on);
+int mppi_replay_begin(MppiHandle* h, void* stream);
+int mppi_replay_end(MppiHandle* h, void* stream);
+
 /* --- auxiliary outputs ------------------------------------------------------------------------- */
 /* Per-sample costs S (control.py:91-109) and un-normalised weights exp(-(S-rho_g)/lambda)
  * (control.py:297-314) of the last step: device float32 [n_env][K_local] each. */

@@ -55,6 +55,9 @@ SYMBOLS = {
     "mppi_step_local": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mppi_step_combine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "mppi_wait": (C.c_int, [C.c_void_p]),
+    "mppi_set_capture_mode": (C.c_int, [C.c_void_p, C.c_int32]),
+    "mppi_replay_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mppi_replay_end": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mppi_last_costs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "mppi_sampled_trajectories": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mppi_philox_noise": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),

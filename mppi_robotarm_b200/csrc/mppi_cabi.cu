@@ -53,6 +53,8 @@ struct MppiHandle {
     uint64_t graph_kernels;
     bool have_step;            // a step has run (step blocks valid)
     bool const_window;         // single environment: window coefficients go through the constant bank
+    bool capture_mode;         // caller is capturing: enqueue capturable work only
+    uint64_t capture_kernels;  // kernels enqueued while capture mode was on (= per replay)
     cudaEvent_t const_ev;      // recorded after this handle's last reader of the constant-bank window
     char err[512];
 };
@@ -408,13 +410,43 @@ int mppi_step_local(MppiHandle* h, int32_t noise_mode, const float* eps_dev, dou
     if (!h) return MPPI_ERR_INVALID;
     if (!partial_dev) return fail(h, MPPI_ERR_INVALID, "%s", "null partial_dev");
     h->timing_pending = false;
-    return enqueue_local(h, noise_mode, eps_dev, partial_dev, (cudaStream_t)stream, false);
+    const uint64_t before = h->launches;
+    int rc = enqueue_local(h, noise_mode, eps_dev, partial_dev, (cudaStream_t)stream, false, h->capture_mode);
+    if (h->capture_mode) { h->capture_kernels += h->launches - before; h->launches = before; }
+    return rc;
 }
 
 int mppi_step_combine(MppiHandle* h, const double* gathered_dev, int32_t world, void* stream) {
     if (!h) return MPPI_ERR_INVALID;
     if (!gathered_dev) return fail(h, MPPI_ERR_INVALID, "%s", "null gathered_dev");
-    return enqueue_combine(h, gathered_dev, world, (cudaStream_t)stream, false);
+    const uint64_t before = h->launches;
+    int rc = enqueue_combine(h, gathered_dev, world, (cudaStream_t)stream, false, !h->capture_mode);
+    if (h->capture_mode) { h->capture_kernels += h->launches - before; h->launches = before; }
+    return rc;
+}
+
+int mppi_set_capture_mode(MppiHandle* h, int32_t on) {
+    if (!h) return MPPI_ERR_INVALID;
+    if (on && !h->capture_mode) h->capture_kernels = 0;
+    h->capture_mode = on != 0;
+    return MPPI_OK;
+}
+
+int mppi_replay_begin(MppiHandle* h, void* stream) {
+    if (!h) return MPPI_ERR_INVALID;
+    if (h->const_window) return const_acquire(h, (cudaStream_t)stream);
+    return MPPI_OK;
+}
+
+int mppi_replay_end(MppiHandle* h, void* stream) {
+    if (!h) return MPPI_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h->const_window) { int rc = const_release(h, s); if (rc != MPPI_OK) return rc; }
+    CU(h, cudaEventRecord(h->done, s));
+    h->launches += h->capture_kernels;
+    h->have_step = true;
+    h->timing_pending = false;
+    return MPPI_OK;
 }
 
 int mppi_step(MppiHandle* h, int32_t noise_mode, const float* eps_dev, void* stream) {

@@ -125,6 +125,8 @@ class MppiEngine:
         self._eps_pin = None
         self._partial = None
         self._gathered = None
+        self._dist_graph = None
+        self.use_graph = bool(use_graph)
         self.set_ref_path(ref)
 
     # ------------------------------------------------------------------------------------------
@@ -191,9 +193,33 @@ class MppiEngine:
         self.step_counter += 1
 
     def _launch_sharded(self, mode, eps_ptr, s):
-        """rollouts on this shard -> all-gather of (rho_g, eta_g, V_g) -> identical combine on every rank."""
+        """rollouts on this shard -> all-gather of (rho_g, eta_g, V_g) -> identical combine on every rank.
+
+        In Philox mode with use_graph the whole sequence (our kernels + NCCL's all-gather) is captured
+        once into a torch.cuda.CUDAGraph and replayed: one launch per control step instead of ten."""
         torch = self.torch
         import torch.distributed as dist
+        if self.use_graph and mode == _cabi.NOISE_PHILOX:
+            if self._dist_graph is None:
+                self._sharded_eager(mode, eps_ptr, dist)          # NCCL must have run once eagerly
+                self.wait()
+                g = torch.cuda.CUDAGraph()
+                _cabi.check(self.lib.mppi_set_capture_mode(self.handle, 1), self.handle, "capture on")
+                try:
+                    with torch.cuda.graph(g, stream=self.stream, capture_error_mode="thread_local"):
+                        self._sharded_eager(mode, eps_ptr, dist)
+                finally:
+                    _cabi.check(self.lib.mppi_set_capture_mode(self.handle, 0), self.handle, "capture off")
+                self._dist_graph = g
+            _cabi.check(self.lib.mppi_replay_begin(self.handle, s), self.handle, "mppi_replay_begin")
+            with torch.cuda.stream(self.stream):
+                self._dist_graph.replay()
+            _cabi.check(self.lib.mppi_replay_end(self.handle, s), self.handle, "mppi_replay_end")
+            return
+        self._sharded_eager(mode, eps_ptr, dist)
+
+    def _sharded_eager(self, mode, eps_ptr, dist):
+        torch = self.torch
         self.launch_local(mode, eps_ptr)
         if self._gathered is None:
             self._gathered = torch.zeros(self.shard.world * self._partial.numel(), dtype=torch.float64,

@@ -334,3 +334,20 @@ def test_two_handles_in_flight_do_not_share_window_state(paths):
         np.testing.assert_array_equal(a.out_u_new, ua)
         np.testing.assert_array_equal(b.out_u_new, ub)
     a.close(); b.close()
+
+
+def test_nccl_sharded_step_matches_single_gpu():
+    """Real multi-process NCCL run (one rank per GPU); skipped on single-GPU boxes."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = 2 if n < 4 else 4
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "run_dist_gpu.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and f"DIST_OK world={n}" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]

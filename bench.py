@@ -229,6 +229,9 @@ def main():
     ap.add_argument("--no-injected", action="store_true", help="skip the injected-noise (HBM) leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if os.environ.get("BENCH_HANG_DUMP"):              # debugging aid: dump all Python stacks if we stall
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["BENCH_HANG_DUMP"]), repeat=False, exit=True)
     if args.impl == "reference":
         return main_reference(args)
 
@@ -371,11 +374,12 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"], _ = cpu_reference_rate(T_HORIZON)
-    if distributed:
-        dist.barrier()
-        dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(line), flush=True)
+    if distributed:
+        del eng, ctrl
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -133,6 +133,10 @@ class MppiEngine:
     def close(self):
         if getattr(self, "handle", None):
             self.torch.cuda.synchronize(self.device)
+            # a captured graph that contains NCCL kernels must be gone before the process group is
+            # destroyed (otherwise destroy_process_group() blocks)
+            self._dist_graph = None
+            self._gathered = self._partial = self._gathered_keepalive = None
             self.lib.mppi_destroy(self.handle)
             self.handle = None
 

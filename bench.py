@@ -10,7 +10,8 @@ Philox noise, run.py's hyper-parameters.  With N > 1 the K samples are sharded o
 A "step" is one full MPPI step: waypoint update, K rollouts, soft-min, weighted noise sum, median
 filter, sequence update, optimal-trajectory rollout.
 
-`value`   device-timed (CUDA events on the engine's stream), nothing large to pre-load in Philox mode.
+`value`   device-timed (CUDA events on the engine's stream around every step, steps enqueued back to
+          back, one host sync at the end); nothing large to pre-load in Philox mode.
 `e2e`     the same steps through MPPIControllerForPathTracking.calc_control_input with host buffers
           in and out (pinned H2D of state+sequence, D2H of the result, host sync) every step.
 `roofline` the rollout kernel against the FP32 FMA peak measured live on this GPU.
@@ -274,6 +275,10 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = eng.launch_count()
     barrier()
+    # Device throughput: the K steps are enqueued back to back (each one bracketed by its own pair of
+    # events, with the L2 flush between brackets) and the host synchronises once at the end — the
+    # synthetic batches are independent, so nothing forces a host round trip per step here.  The
+    # host-synchronised, closed-loop-style number is `e2e` below.
     with ClockSampler(local_rank) as clocks:
         for a, b in ev:
             with torch.cuda.stream(eng.stream):
@@ -282,7 +287,9 @@ def main():
             device_step()
             with torch.cuda.stream(eng.stream):
                 b.record()
-            eng.wait()
+            if not distributed:
+                eng.wait()       # single GPU: the library's per-kernel timing events are read per step
+        eng.wait()
         barrier()
     launches = eng.launch_count() - launches0
     total_ms = sum(a.elapsed_time(b) for a, b in ev)

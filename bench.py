@@ -211,6 +211,39 @@ def injected_mode_numbers(ref, torch, K=K_TOTAL, T=T_HORIZON, steps=8):
     return out
 
 
+def batched_numbers(ref, torch, B=1024, K=1024, T=64, steps=20):
+    """BASELINE.json configs[4]: B independent arm instances x K rollouts, T = 64, stepped by one launch
+    of each kernel (grid.y = environment).  On N GPUs each rank takes B/N environments; this is the
+    single-GPU figure for all B."""
+    from mppi_robotarm_b200.batched import BatchedMPPIController
+    kw = run_py_kwargs(ref, K, T)
+    bat = BatchedMPPIController(B, **kw, visualize_optimal_traj=False, seed=11)
+    rows = (np.arange(B) * (1900 // B + 1)) % 1900
+    th = 2 * np.pi * rows / (ref.shape[0] - 1)
+    x, y = 0.8 + 0.6 * np.cos(th), 0.8 + 0.6 * np.sin(th)
+    q2 = -np.arccos(np.clip((x * x + y * y - 2.0) / 2.0, -1, 1))
+    q1 = np.arctan2(y, x) - np.arctan2(np.sin(q2), 1.0 + np.cos(q2))
+    X = np.stack([q1, q2, np.zeros(B), np.zeros(B)], axis=1)          # on-path starts
+    bat.prev_waypoints_idx = rows.astype(np.int64)
+    for _ in range(3):
+        bat.calc_control_input(X)
+        bat.prev_waypoints_idx = rows.astype(np.int64)
+    bat.engine.set_timing(True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        bat.calc_control_input(X)
+        bat.prev_waypoints_idx = rows.astype(np.int64)
+    wall = (time.perf_counter() - t0) / steps
+    t = bat.engine.get_timing()
+    dev_us = sum(v for k, v in t.items() if k != "steps")
+    out = {"workload": f"C5: {B} environments x K={K}, T={T}, Philox", "device_us_per_step": dev_us,
+           "sample_steps_per_s": B * K * T / (dev_us * 1e-6), "e2e_ms_per_step": wall * 1e3,
+           "e2e_sample_steps_per_s": B * K * T / wall, "kernel_us": {k: v for k, v in t.items() if k != "steps"},
+           "finished_envs": int(bat.finished.sum())}
+    bat.close()
+    return out
+
+
 def workload_config(n_gpus):
     return {"workload": f"C4: 2-link arm, K={K_TOTAL} rollouts, T={T_HORIZON}, Philox noise in-kernel, run.py "
                         f"hyper-parameters, synthetic xydq_circle-shaped reference (2000 waypoints)",
@@ -228,6 +261,7 @@ def main():
     ap.add_argument("--no-latency", action="store_true", help="skip the config-3 latency loop")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-injected", action="store_true", help="skip the injected-noise (HBM) leg")
+    ap.add_argument("--no-batched", action="store_true", help="skip the config-5 batched-environments leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if os.environ.get("BENCH_HANG_DUMP"):              # debugging aid: dump all Python stacks if we stall
@@ -378,6 +412,10 @@ def main():
     # ---- injected-noise mode: achieved HBM GB/s of the two kernels that read the K x T x 2 tensor ----
     if rank == 0 and world == 1 and not args.no_injected:
         line["injected_noise"] = injected_mode_numbers(ref, torch)
+
+    # ---- config 5: batched multi-environment sweep (environments shard over GPUs, no collective) ----
+    if rank == 0 and world == 1 and not args.no_batched:
+        line["batched_envs"] = batched_numbers(ref, torch)
 
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"], _ = cpu_reference_rate(T_HORIZON)

@@ -99,8 +99,10 @@ void grid_sizes(const MppiConfig* c, int sm, int* g_roll, int* g_soft, int* g_ws
     if (gs > cap) gs = cap;
     if (gs < 1) gs = 1;
     *g_soft = gs;
-    int gw = (K + 4095) / 4096;
-    const int capw = (2 * sm + c->n_env - 1) / c->n_env;
+    // weighted-sum grid (upper bound; the Philox variant launches fewer blocks): enough CTAs to keep
+    // ~8 CTAs per SM streaming the injected noise tensor
+    int gw = (K + 63) / 64;
+    const int capw = (8 * sm + c->n_env - 1) / c->n_env;
     if (gw > capw) gw = capw;
     if (gw < 1) gw = 1;
     *g_wsum = gw;
@@ -236,8 +238,13 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
     if (timed) CU(h, cudaEventRecord(h->tev[2], s));
     mppi_softmin_sm100a<<<dim3(dc.g_soft, dc.n_env), kSoftThreads, 0, s>>>(dc, S, bmin, w, eta_part, rho);
     if (timed) CU(h, cudaEventRecord(h->tev[3], s));
+    int g_wsum_used = dc.g_wsum;
     {
-        dim3 grid(dc.g_wsum, dc.n_env);
+        if (noise_mode == MPPI_NOISE_PHILOX) {               // scanning weights: K/4096 blocks are plenty
+            const int want = (dc.K_local + 4095) / 4096;
+            if (want < g_wsum_used) g_wsum_used = want;
+        }
+        dim3 grid(g_wsum_used, dc.n_env);
         if (noise_mode == MPPI_NOISE_PHILOX) {
             const size_t sm = (size_t)(kWsumThreads / 32) * ((dc.T + 1) / 2) * sizeof(float4);
             mppi_wsum_philox_sm100a<<<grid, kWsumThreads, sm, s>>>(dc, step_ctr, w, v_part);
@@ -248,7 +255,7 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
         }
     }
     if (timed) CU(h, cudaEventRecord(h->tev[4], s));
-    mppi_reduce_sm100a<<<dc.n_env, kReduceThreads, 0, s>>>(dc, rho, eta_part, v_part, partial_dev);
+    mppi_reduce_sm100a<<<dc.n_env, kReduceThreads, 0, s>>>(dc, g_wsum_used, rho, eta_part, v_part, partial_dev);
     if (timed) CU(h, cudaEventRecord(h->tev[5], s));
     CU(h, cudaGetLastError());
     h->launches += 5;

@@ -355,6 +355,8 @@ template <> struct VecOps<float2> {
     static __device__ __forceinline__ float2 ld(const float2* p) { return __ldg(p); }
 };
 
+constexpr int kWsumRows = 8;          // rows (samples) in flight per thread
+
 template <typename VEC>
 __global__ void __launch_bounds__(kWsumThreads)
 mppi_wsum_injected_sm100a(DevCfg cfg, const float* __restrict__ w, const float* __restrict__ eps,
@@ -371,20 +373,21 @@ mppi_wsum_injected_sm100a(DevCfg cfg, const float* __restrict__ w, const float* 
     VEC acc = VecOps<VEC>::zero();
     if (active) {
         const int stride = R * gridDim.x;
-        int k = blockIdx.x * R + r;
-        // 4 rows in flight per thread
-        for (; k + 3 * stride < cfg.K_local; k += 4 * stride) {
-            float wk[4]; VEC v[4];
+        const int K = cfg.K_local;
+        // kWsumRows independent weight loads, then kWsumRows independent 16-byte row loads per thread:
+        // ~32 KB of loads in flight per CTA keeps HBM busy with a few CTAs per SM
+        for (int k = blockIdx.x * R + r; k < K; k += kWsumRows * stride) {
+            float wk[kWsumRows]; VEC v[kWsumRows];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) wk[i] = __ldg(we + k + i * stride);
+            for (int i = 0; i < kWsumRows; ++i) {
+                const int ki = k + i * stride;
+                wk[i] = ki < K ? __ldg(we + ki) : 0.0f;
+            }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = wk[i] != 0.0f ? VecOps<VEC>::ld(ee + (size_t)(k + i * stride) * C + c) : VecOps<VEC>::zero();
+            for (int i = 0; i < kWsumRows; ++i)
+                v[i] = wk[i] != 0.0f ? VecOps<VEC>::ld(ee + (size_t)(k + i * stride) * C + c) : VecOps<VEC>::zero();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) VecOps<VEC>::fmadd(acc, wk[i], v[i]);
-        }
-        for (; k < cfg.K_local; k += stride) {
-            const float wk = __ldg(we + k);
-            if (wk != 0.0f) VecOps<VEC>::fmadd(acc, wk, VecOps<VEC>::ld(ee + (size_t)k * C + c));
+            for (int i = 0; i < kWsumRows; ++i) VecOps<VEC>::fmadd(acc, wk[i], v[i]);
         }
         sh[r * C + c] = acc;
     }
@@ -392,7 +395,7 @@ mppi_wsum_injected_sm100a(DevCfg cfg, const float* __restrict__ w, const float* 
     if (tid < C) {                                            // fixed-order sum over the R row slots
         VEC s = sh[tid];
         for (int i = 1; i < R; ++i) VecOps<VEC>::add(s, sh[i * C + tid]);
-        ((VEC*)(v_part + ((size_t)e * gridDim.x + blockIdx.x) * 2 * cfg.T))[tid] = s;
+        ((VEC*)(v_part + ((size_t)e * cfg.g_wsum + blockIdx.x) * 2 * cfg.T))[tid] = s;
     }
 }
 
@@ -449,7 +452,7 @@ mppi_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const
             const float4 v = sh[wv * n_pairs + pr];
             s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
         }
-        float* dst = v_part + ((size_t)e * gridDim.x + blockIdx.x) * 2 * cfg.T + 4 * pr;
+        float* dst = v_part + ((size_t)e * cfg.g_wsum + blockIdx.x) * 2 * cfg.T + 4 * pr;
         dst[0] = s.x; dst[1] = s.y;
         if (2 * pr + 1 < cfg.T) { dst[2] = s.z; dst[3] = s.w; }
     }
@@ -462,7 +465,7 @@ mppi_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const
 constexpr int kReduceThreads = 1024;
 
 __global__ void __launch_bounds__(kReduceThreads)
-mppi_reduce_sm100a(DevCfg cfg, const float* __restrict__ rho, const double* __restrict__ eta_part,
+mppi_reduce_sm100a(DevCfg cfg, int n_wsum_blocks, const float* __restrict__ rho, const double* __restrict__ eta_part,
                    const float* __restrict__ v_part, double* __restrict__ partial) {
     __shared__ double red[kReduceThreads / 32];
     __shared__ double colsum[kReduceThreads];
@@ -486,7 +489,7 @@ mppi_reduce_sm100a(DevCfg cfg, const float* __restrict__ rho, const double* __re
     double s = 0.0;
     if (slice < n_slice) {
         const float* src = v_part + (size_t)e * cfg.g_wsum * C + c;
-        for (int b = slice; b < cfg.g_wsum; b += n_slice) s += (double)src[(size_t)b * C];
+        for (int b = slice; b < n_wsum_blocks; b += n_slice) s += (double)src[(size_t)b * C];
         colsum[slice * C + c] = s;
     }
     __syncthreads();

@@ -132,6 +132,18 @@ int mppi_step_combine(MppiHandle* h, const double* gathered_dev, int32_t world, 
 
 int mppi_wait(MppiHandle* h);
 
+/* Device-resident closed loop — n_steps ticks of run.py:48-59 without a host round trip (Philox noise,
+ * whole sample set on this handle).  Per tick: the MPPI step above; u = first row of the shifted
+ * sequence (what calc_control_input returns, control.py:152); plant dq += dt*Arm_Dynamic(q,dq,u),
+ * q += dt*dq in FP64 (utils.py:14-29, run.py:53-55); sequence shift (control.py:148-149).
+ * Starts from the inputs in io_host; afterwards the input fields of io_host hold the final controller
+ * state (x0, u_prev, prev_idx, step) and the output fields the last tick's results.
+ * log_dev:  device double [n_steps][n_env][8] = (q1, q2, dq1, dq2, u1, u2, waypoint index, rho) after each tick.
+ * stop_dev: device int32 [n_env] = first tick at which the end of the path was reached (control.py:76-78;
+ *           the environment is frozen from there), or >= n_steps if it never was. */
+int mppi_closed_loop(MppiHandle* h, int32_t n_steps, double plant_dt, double* log_dev, int32_t* stop_dev,
+                     void* stream);
+
 /* Caller-side CUDA-graph capture of the sharded step (mppi_step_local + the caller's collective +
  * mppi_step_combine on one capturing stream): while capture mode is on, the library enqueues only
  * capturable work (no event records).  Each replay of the caller's graph is bracketed by

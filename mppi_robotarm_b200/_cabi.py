@@ -55,6 +55,7 @@ SYMBOLS = {
     "mppi_step_local": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mppi_step_combine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "mppi_wait": (C.c_int, [C.c_void_p]),
+    "mppi_closed_loop": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mppi_set_capture_mode": (C.c_int, [C.c_void_p, C.c_int32]),
     "mppi_replay_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mppi_replay_end": (C.c_int, [C.c_void_p, C.c_void_p]),

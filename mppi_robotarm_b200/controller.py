@@ -150,6 +150,33 @@ class MPPIControllerForPathTracking:
         self.u_prev[-1] = u[-1]                           # control.py:149
         return u[0], u, optimal_traj, sampled_traj_list   # control.py:152 (u[0] is post-shift, Q2)
 
+    def run_closed_loop(self, observed_x, n_steps: int, plant_dt: float):
+        """The loop of run.py:48-59 on the GPU: n_steps x { calc_control_input; dq += dt*Arm_Dynamic(q, dq, u);
+        q += dt*dq } with no host round trip per tick (in-kernel Philox noise).
+
+        Returns a dict of float64 arrays over the executed ticks: ``state`` [n, 4] (after each tick),
+        ``u`` [n, 2] (the control applied), ``waypoint_idx`` [n], ``rho`` [n].  The controller's
+        ``u_prev`` / ``prev_waypoints_idx`` end up as after the last tick.  Raises IndexError like the
+        reference when the end of the path is reached (after returning state up to that tick in
+        ``self.last_loop``)."""
+        if self.noise != "philox":
+            raise ValueError("run_closed_loop draws its noise in-kernel: construct with noise='philox'")
+        self._check_sigma(self.Sigma, self.dim_u)
+        eng = self._engine()
+        x0 = np.asarray(observed_x, dtype=np.float64).reshape(4)
+        log, stop = eng.closed_loop(x0, self.u_prev, self.prev_waypoints_idx, n_steps, plant_dt)
+        n = int(min(n_steps, stop[0]))
+        self.u_prev[...] = eng.in_u_prev[0]
+        self.prev_waypoints_idx = int(eng.in_prev_idx[0])
+        out = dict(state=log[:n, 0, 0:4].copy(), u=log[:n, 0, 4:6].copy(),
+                   waypoint_idx=log[:n, 0, 6].astype(np.int64), rho=log[:n, 0, 7].copy(),
+                   final_state=eng.in_x0[0].copy(), ticks=n)
+        self.last_loop = out
+        if n < n_steps:
+            print("[ERROR] Reached the end of the reference path.")
+            raise IndexError
+        return out
+
     def _gather_sampled(self, eng):
         local = eng.sampled_trajectories()[0].cpu().numpy().astype(np.float64)
         if eng.shard.world == 1:

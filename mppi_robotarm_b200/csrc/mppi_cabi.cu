@@ -25,7 +25,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct Workspace {
     size_t bytes;
     size_t off_ref, off_step_blocks, off_in, off_out, off_S, off_w, off_block_min, off_eta_part,
-        off_rho, off_v_part, off_partial;
+        off_rho, off_v_part, off_partial, off_loop;
 };
 
 }  // namespace
@@ -49,6 +49,9 @@ struct MppiHandle {
     int t_steps;
     uint64_t launches;
     cudaGraphExec_t graph_exec;
+    cudaGraphExec_t tick_exec;   // one tick of the device closed loop
+    void* tick_stream;
+    uint64_t tick_kernels;
     void* graph_stream;
     uint64_t graph_kernels;
     bool have_step;            // a step has run (step blocks valid)
@@ -126,6 +129,7 @@ void carve(const MppiConfig* c, int sm, Workspace* w) {
     w->off_rho = take(E * sizeof(float));
     w->off_v_part = take(E * g_wsum * 2 * T * sizeof(float));
     w->off_partial = take(E * (2 + 2 * T) * sizeof(double));
+    w->off_loop = take(sizeof(LoopParams));
     w->bytes = off;
 }
 
@@ -166,6 +170,7 @@ void fill_dev_cfg(MppiHandle* h) {
     d.gamma = c.param_gamma; d.lambda = c.param_lambda; d.inv_lambda = 1.0 / c.param_lambda;
     for (int i = 0; i < 4; ++i) d.sig_inv[i] = c.sigma_inv[i];
     d.cost_l1 = c.cost_l1; d.cost_l2 = c.cost_l2;
+    for (int i = 0; i < 7; ++i) d.arm64[i] = c.arm[i];
 }
 
 // The constant-bank window table is one symbol per device, shared by every handle of the process.
@@ -195,7 +200,7 @@ void const_forget(MppiHandle* h) {
 
 // enqueue everything up to this shard's partial triple
 int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* partial_dev, cudaStream_t s,
-                  bool timed, bool capturing = false) {
+                  bool timed, bool capturing = false, bool copy_inputs = true) {
     const DevCfg& dc = h->dc;
     char* ws = h->dev;
     if (noise_mode != MPPI_NOISE_PHILOX && noise_mode != MPPI_NOISE_INJECTED)
@@ -213,7 +218,7 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
     float* v_part = (float*)(ws + h->ws.off_v_part);
     const double* ref = (const double*)(ws + h->ws.off_ref);
 
-    CU(h, cudaMemcpyAsync(ws + h->ws.off_in, h->host, h->in_bytes, cudaMemcpyHostToDevice, s));
+    if (copy_inputs) CU(h, cudaMemcpyAsync(ws + h->ws.off_in, h->host, h->in_bytes, cudaMemcpyHostToDevice, s));
     if (timed) CU(h, cudaEventRecord(h->tev[0], s));
     mppi_prepare_sm100a<<<dc.n_env, 32, 0, s>>>(dc, h->dio, ref, step_blocks);
     if (timed) CU(h, cudaEventRecord(h->tev[1], s));
@@ -264,12 +269,12 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
 }
 
 int enqueue_combine(MppiHandle* h, const double* gathered_dev, int world, cudaStream_t s, bool timed,
-                    bool record_done = true) {
+                    bool record_done = true, bool copy_outputs = true) {
     if (world < 1 || world > 64) return fail(h, MPPI_ERR_INVALID, "%s", "world must be in [1, 64]");
     mppi_finalize_sm100a<<<h->dc.n_env, 256, 0, s>>>(h->dc, h->dio, gathered_dev, world);
     if (timed) CU(h, cudaEventRecord(h->tev[6], s));
     CU(h, cudaGetLastError());
-    CU(h, cudaMemcpyAsync(h->host + h->out_off, h->dev + h->ws.off_out, h->out_bytes, cudaMemcpyDeviceToHost, s));
+    if (copy_outputs) CU(h, cudaMemcpyAsync(h->host + h->out_off, h->dev + h->ws.off_out, h->out_bytes, cudaMemcpyDeviceToHost, s));
     if (record_done) CU(h, cudaEventRecord(h->done, s));      // not inside a stream capture
     h->launches += 1;
     return MPPI_OK;
@@ -392,6 +397,7 @@ void mppi_destroy(MppiHandle* h) {
     cudaSetDevice(h->cfg.device);
     const_forget(h);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->tick_exec) cudaGraphExecDestroy(h->tick_exec);
     if (h->done) cudaEventDestroy(h->done);
     if (h->const_ev) cudaEventDestroy(h->const_ev);
     for (int i = 0; i <= kNumTimers; ++i)
@@ -410,6 +416,7 @@ int mppi_set_ref_path(MppiHandle* h, const double* ref, int32_t n_rows) {
     h->n_ref_rows = n_rows;
     h->dc.n_ref_rows = n_rows;
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    if (h->tick_exec) { cudaGraphExecDestroy(h->tick_exec); h->tick_exec = nullptr; }
     return MPPI_OK;
 }
 
@@ -494,6 +501,58 @@ int mppi_step(MppiHandle* h, int32_t noise_mode, const float* eps_dev, void* str
     rc = enqueue_combine(h, partial, 1, s, h->timing);
     h->timing_pending = h->timing && rc == MPPI_OK;
     return rc;
+}
+
+int mppi_closed_loop(MppiHandle* h, int32_t n_steps, double plant_dt, double* log_dev, int32_t* stop_dev,
+                     void* stream) {
+    if (!h) return MPPI_ERR_INVALID;
+    if (h->cfg.K_local != h->cfg.K_total)
+        return fail(h, MPPI_ERR_INVALID, "%s", "the device closed loop needs the whole sample set on this handle");
+    if (n_steps < 1 || !log_dev || !stop_dev || !(plant_dt > 0.0))
+        return fail(h, MPPI_ERR_INVALID, "%s", "closed loop needs n_steps >= 1, plant_dt > 0, log_dev and stop_dev");
+    if (h->n_ref_rows < 2) return fail(h, MPPI_ERR_INVALID, "%s", "mppi_set_ref_path() has not been called");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!s) return fail(h, MPPI_ERR_INVALID, "%s", "the device closed loop needs a non-default stream");
+    char* ws = h->dev;
+    LoopParams* lp_dev = (LoopParams*)(ws + h->ws.off_loop);
+    double* partial = (double*)(ws + h->ws.off_partial);
+    LoopParams lp;
+    lp.plant_dt = plant_dt; lp.log = log_dev; lp.stop = stop_dev; lp.tick = 0; lp.n_steps = n_steps;
+    // pageable source: the runtime stages it before returning, so the stack copy is safe
+    CU(h, cudaMemcpyAsync(lp_dev, &lp, sizeof(lp), cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemsetAsync(stop_dev, 0x7f, sizeof(int32_t) * h->cfg.n_env, s));
+    CU(h, cudaMemcpyAsync(ws + h->ws.off_in, h->host, h->in_bytes, cudaMemcpyHostToDevice, s));
+    if (!h->tick_exec || h->tick_stream != stream) {
+        if (h->tick_exec) { cudaGraphExecDestroy(h->tick_exec); h->tick_exec = nullptr; }
+        const uint64_t before = h->launches;
+        cudaGraph_t g = nullptr;
+        CU(h, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_local(h, MPPI_NOISE_PHILOX, nullptr, partial, s, false, true, /*copy_inputs=*/false);
+        if (rc == MPPI_OK) rc = enqueue_combine(h, partial, 1, s, false, false, /*copy_outputs=*/false);
+        if (rc == MPPI_OK) {
+            mppi_plant_sm100a<<<h->dc.n_env, 32, 0, s>>>(h->dc, h->dio, ws + h->ws.off_step_blocks, lp_dev);
+            h->launches += 1;
+        }
+        cudaError_t ce = cudaStreamEndCapture(s, &g);
+        if (rc != MPPI_OK) { if (g) cudaGraphDestroy(g); return rc; }
+        CU(h, ce);
+        CU(h, cudaGraphInstantiate(&h->tick_exec, g, 0));
+        cudaGraphDestroy(g);
+        h->tick_kernels = h->launches - before;
+        h->launches = before;
+        h->tick_stream = stream;
+    }
+    if (h->const_window) { int rc = const_acquire(h, s); if (rc != MPPI_OK) return rc; }
+    for (int i = 0; i < n_steps; ++i) CU(h, cudaGraphLaunch(h->tick_exec, s));
+    if (h->const_window) { int rc = const_release(h, s); if (rc != MPPI_OK) return rc; }
+    h->launches += h->tick_kernels * (uint64_t)n_steps;
+    // final controller state back into the caller's input fields, last tick's results into the outputs
+    CU(h, cudaMemcpyAsync(h->host, ws + h->ws.off_in, h->in_bytes, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaMemcpyAsync(h->host + h->out_off, h->dev + h->ws.off_out, h->out_bytes, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaEventRecord(h->done, s));
+    h->have_step = true;
+    h->timing_pending = false;
+    return MPPI_OK;
 }
 
 int mppi_wait(MppiHandle* h) {

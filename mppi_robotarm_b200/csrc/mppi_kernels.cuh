@@ -75,6 +75,16 @@ struct DevCfg {
     double gamma, lambda, inv_lambda;
     double sig_inv[4];
     double cost_l1, cost_l2;
+    double arm64[7];           // m1, m2, l1, l2, lc1, lc2, g for the FP64 plant of the device closed loop
+};
+
+// parameters of one mppi_closed_loop() call, kept in device memory so that the captured per-tick
+// graph is identical for every call
+struct LoopParams {
+    double plant_dt;
+    double* log;               // [n_steps][n_env][8]
+    int32_t* stop;             // [n_env] first tick at which the end of the path was reached
+    int32_t tick, n_steps;
 };
 
 struct StepBlockView {          // pointers into one environment's step block (global or shared)
@@ -614,6 +624,66 @@ mppi_sampled_traj_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, cons
         const StepCtl c = sb.ctl[tc];
         arm_step(st, cfg.arm, fma_(um, c.u1, n1), fma_(um, c.u2, n2));
         out[t] = make_float4(st.q1, st.q2, st.d1, st.d2);
+    }
+}
+
+// ================================================================================================
+// 7b. plant tick of the device-resident closed loop (run.py:53-59 with utils.py:14-29, FP64):
+//     u = first row of the shifted sequence (the reference's return value, quirk Q2),
+//     dq += dt * Arm_Dynamic(q, dq, u); q += dt * dq; then the controller state for the next tick:
+//     observed state, shifted sequence (control.py:148-149), waypoint index, step counter.
+// ================================================================================================
+__global__ void __launch_bounds__(32)
+mppi_plant_sm100a(DevCfg cfg, DevIo io, const char* __restrict__ step_blocks, LoopParams* lp_ptr) {
+    const int e = blockIdx.x, lane = threadIdx.x, T = cfg.T;
+    const LoopParams lp = *lp_ptr;
+    double* x0 = const_cast<double*>(io.x0) + 4 * e;
+    double* u_prev = const_cast<double*>(io.u_prev) + (size_t)e * 2 * T;
+    const double* u_new = io.u_new + (size_t)e * 2 * T;
+    const StepHeader* hd = (const StepHeader*)(step_blocks + (size_t)e * cfg.step_block_bytes);
+    const bool ended = (hd->status & 1) != 0;                   // control.py:76-78: the reference raises here
+    const int t1 = T > 1 ? 1 : 0;
+    const double u1 = u_new[2 * t1], u2 = u_new[2 * t1 + 1];
+    if (!ended) {
+        // shifted sequence: u_prev[:-1] = u[1:], u_prev[-1] = u[-1]
+        for (int c = lane; c < 2 * T; c += 32) {
+            const int t = c >> 1;
+            u_prev[c] = u_new[2 * (t + 1 < T ? t + 1 : T - 1) + (c & 1)];
+        }
+    }
+    if (lane == 0) {
+        double q1 = x0[0], q2 = x0[1], d1 = x0[2], d2 = x0[3];
+        if (!ended) {
+            const double m1 = cfg.arm64[0], m2 = cfg.arm64[1], l1 = cfg.arm64[2], l2 = cfg.arm64[3],
+                         lc1 = cfg.arm64[4], lc2 = cfg.arm64[5], g = cfg.arm64[6];
+            const double c2 = cos(q2);
+            const double M11 = m1 * lc1 * lc1 + l1 + m2 * (l1 * l1 + lc2 * lc2 + 2 * l1 * lc2 * c2) + l2;
+            const double M22 = m2 * lc2 * lc2 + l2;
+            const double M12 = m2 * l1 * lc2 * c2 + m2 * lc2 * lc2 + l2;
+            const double hh = m2 * l1 * lc2 * sin(q2);
+            const double g1 = m1 * lc1 * g * cos(q1) + m2 * g * (lc2 * cos(q1 + q2) + l1 * cos(q1));
+            const double g2 = m2 * lc2 * g * cos(q1 + q2);
+            const double b1 = u1 - ((-hh * d2) * d1 + (-hh * d1 - hh * d2) * d2) - g1;
+            const double b2 = u2 - (hh * d1) * d1 - g2;
+            const double det = M11 * M22 - M12 * M12;
+            d1 += lp.plant_dt * ((M22 * b1 - M12 * b2) / det);
+            d2 += lp.plant_dt * ((M11 * b2 - M12 * b1) / det);
+            q1 += lp.plant_dt * d1;
+            q2 += lp.plant_dt * d2;
+            x0[0] = q1; x0[1] = q2; x0[2] = d1; x0[3] = d2;
+        } else {
+            atomicMin(lp.stop + e, lp.tick);
+        }
+        const_cast<int32_t*>(io.prev_idx)[e] = io.new_idx[e];   // control.py:230 (also when the path ended)
+        if (lp.tick < lp.n_steps) {
+            double* row = lp.log + ((size_t)lp.tick * cfg.n_env + e) * 8;
+            row[0] = q1; row[1] = q2; row[2] = d1; row[3] = d2; row[4] = u1; row[5] = u2;
+            row[6] = (double)io.new_idx[e]; row[7] = io.rho[e];
+        }
+        if (e == 0) {
+            *const_cast<uint64_t*>(io.step) += 1;                // next tick draws fresh Philox noise
+            lp_ptr->tick = lp.tick + 1;
+        }
     }
 }
 

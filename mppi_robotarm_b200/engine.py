@@ -253,6 +253,27 @@ class MppiEngine:
     def wait(self):
         _cabi.check(self.lib.mppi_wait(self.handle), self.handle, "mppi_wait")
 
+    def closed_loop(self, x0, u_prev, prev_idx, n_steps, plant_dt):
+        """n_steps ticks of the run.py loop entirely on the device (Philox noise, FP64 plant).
+
+        Returns (log, stop): log float64 [n_steps, n_env, 8] = (q1, q2, dq1, dq2, u1, u2, waypoint idx, rho)
+        after each tick, stop int32 [n_env] = first tick that hit the end of the path (>= n_steps: none).
+        Afterwards in_x0 / in_u_prev / in_prev_idx hold the final controller state."""
+        torch = self.torch
+        if self.shard.world != 1:
+            raise ValueError("the device closed loop runs on one GPU (whole sample set on this handle)")
+        self.write_inputs(x0, u_prev, prev_idx)
+        log = torch.empty((int(n_steps), self.n_env, 8), dtype=torch.float64, device=self.device)
+        stop = torch.empty((self.n_env,), dtype=torch.int32, device=self.device)
+        _cabi.check(self.lib.mppi_closed_loop(self.handle, int(n_steps), float(plant_dt), log.data_ptr(),
+                                              stop.data_ptr(), self.stream.cuda_stream), self.handle, "mppi_closed_loop")
+        self.last_mode, self.last_eps_ptr = _cabi.NOISE_PHILOX, None
+        self.wait()
+        self.step_counter = int(self.in_step[0])
+        with torch.cuda.stream(self.stream):
+            out = log.cpu().numpy(), stop.cpu().numpy()
+        return out
+
     # ------------------------------------------------------------------------------------------
     def last_costs(self):
         """(S, w~) of the last step as device tensors [n_env, K_local] (float32)."""

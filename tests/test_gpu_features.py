@@ -351,3 +351,54 @@ def test_nccl_sharded_step_matches_single_gpu():
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "run_dist_gpu.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and f"DIST_OK world={n}" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+
+
+def test_device_closed_loop_equals_host_driven_loop(paths):
+    """mppi_closed_loop (plant + loop on the GPU) against the same controller driven tick by tick from
+    the host with this repo's utils.Arm_Dynamic plant: same Philox stream, so the trajectories agree to
+    FP64 plant rounding until chaos amplifies it."""
+    from control import MPPIControllerForPathTracking
+    from utils import Arm_Dynamic
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    kw = cases.run_py_kwargs(ref, 512, 30)
+    dev = MPPIControllerForPathTracking(**kw, seed=31, verbose=False)
+    host = MPPIControllerForPathTracking(**kw, seed=31, verbose=False)
+    n, dt = 400, 0.003
+    out = dev.run_closed_loop(cases.X0, n, dt)
+    assert out["ticks"] == n and out["state"].shape == (n, 4)
+    q, dq = np.array(cases.X0[0:2]), np.array(cases.X0[2:4])
+    state = np.concatenate([q, dq])
+    hs, hu, hi = [], [], []
+    for _ in range(n):
+        u, _, _, _ = host.calc_control_input(state)
+        dq = dq + dt * Arm_Dynamic(q, dq, u)
+        q = q + dt * dq
+        state = np.concatenate([q, dq])
+        hs.append(state.copy()); hu.append(u.copy()); hi.append(host.prev_waypoints_idx)
+    hs, hu = np.array(hs), np.array(hu)
+    dev_err = np.max(np.abs(out["state"] - hs), axis=1)
+    np.testing.assert_allclose(out["state"][:25], hs[:25], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(out["u"][:25], hu[:25], rtol=0, atol=1e-7)
+    assert list(out["waypoint_idx"][:25]) == hi[:25]
+    assert dev_err.max() <= 0.5, dev_err.max()
+    assert abs(dev.prev_waypoints_idx - host.prev_waypoints_idx) <= 60
+    assert dev._engine().step_counter == n
+    # the loop can be resumed from the controller state it leaves behind
+    out2 = dev.run_closed_loop(out["final_state"], 50, dt)
+    assert out2["ticks"] == 50 and np.all(np.isfinite(out2["state"]))
+    dev.close(); host.close()
+
+
+def test_device_closed_loop_stops_at_the_end_of_the_path(paths, capsys):
+    from control import MPPIControllerForPathTracking
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    c = MPPIControllerForPathTracking(**cases.run_py_kwargs(ref, 256, 20), seed=5, verbose=False)
+    c.prev_waypoints_idx = 1960
+    x0 = [paths["trajectory1"][1960, 0], paths["trajectory1"][1960, 1], 0.0, 0.0]
+    with pytest.raises(IndexError):
+        c.run_closed_loop(x0, 400, 0.003)
+    assert "[ERROR] Reached the end of the reference path." in capsys.readouterr().out
+    assert 0 < c.last_loop["ticks"] < 400
+    assert c.prev_waypoints_idx >= ref.shape[0] - 1
+    assert np.all(np.diff(c.last_loop["waypoint_idx"]) >= 0)
+    c.close()

@@ -28,6 +28,7 @@ class BatchedMPPIController:
         self.u_prev = np.tile(np.array([10.0, -2.0]), (self.n_env, self.T, 1))       # control.py:59 per env
         self.prev_waypoints_idx = np.zeros(self.n_env, dtype=np.int64)               # control.py:65 per env
         self.finished = np.zeros(self.n_env, dtype=bool)
+        self._want_opt = bool(visualize_optimal_traj)
         # env_offset decorrelates the Philox streams of environment shards living on different ranks
         self.engine = MppiEngine(
             K=self.K, T=self.T, delta_t=delta_t, param_lambda=param_lambda, param_gamma=self.param_gamma,
@@ -37,7 +38,8 @@ class BatchedMPPIController:
             optimal_traj=bool(visualize_optimal_traj), use_graph=use_graph)
 
     def calc_control_input(self, observed_x, eps=None, strict=False):
-        """observed_x [n_env, 4] -> (u0 [n_env, 2], u_seq [n_env, T, 2], optimal_traj [n_env, T, 4]).
+        """observed_x [n_env, 4] -> (u0 [n_env, 2], u_seq [n_env, T, 2], optimal_traj [n_env, T, 4] or None
+        when visualize_optimal_traj is off).
 
         Per environment this is control.py:67-152 including the post-shift return value (Q2).
         Environments that reached the end of the path (control.py:76-78) are frozen and flagged in
@@ -54,9 +56,13 @@ class BatchedMPPIController:
         live = ~ended & ~self.finished
         self.finished |= ended
         u = self.u_prev
-        u[live] += eng.out_w_eps_filt[live]
-        opt = eng.out_opt_traj.copy()
-        u[live, :-1] = u[live, 1:]
+        if live.all():                                   # common case: plain slices, no fancy indexing
+            u += eng.out_w_eps_filt
+            u[:, :-1] = u[:, 1:]
+        else:
+            u[live] += eng.out_w_eps_filt[live]
+            u[live, :-1] = u[live, 1:]
+        opt = eng.out_opt_traj.copy() if self._want_opt else None
         return u[:, 0].copy(), u, opt
 
     def close(self):

@@ -95,3 +95,25 @@ def test_plant_helpers_match_oracle_twin():
         np.testing.assert_allclose((x1, y1), (np.cos(q[0]), np.sin(q[0])), rtol=1e-14)
     import sys_params
     assert sys_params.SYS_PARAMS() == mo.default_arm_params()
+
+
+def test_refgen_reproduces_trajectory_txt(paths):
+    from mppi_robotarm_b200 import refgen
+    gen = refgen.circle_joint_reference(3000)
+    np.testing.assert_allclose(gen, paths["trajectory"], rtol=0, atol=2e-12)      # the reference's own file
+    # forward kinematics of the generated joints lands on the generated end-effector
+    x, y = mo.end_effector(gen[:, 0], gen[:, 1])
+    np.testing.assert_allclose(np.stack([x, y], 1), gen[:, 2:4], atol=1e-12)
+
+
+def test_refgen_tracking_run_has_the_shape_of_xydq_circle(paths):
+    from mppi_robotarm_b200 import refgen
+    rec = refgen.record_tracking_run(2000)
+    ref = paths["xydq_circle"]
+    assert rec.shape == ref.shape
+    rad = np.hypot(rec[:, 0] - 0.8, rec[:, 1] - 0.8)
+    assert 0.57 <= rad.min() and rad.max() <= 0.63
+    np.testing.assert_allclose(rec[0, 0:2], [1.4, 0.8], atol=5e-3)
+    # same order of magnitude of joint rates and torques as the recorded file
+    assert 0.3 <= np.abs(rec[:, 2:4]).max() / np.abs(ref[:, 2:4]).max() <= 3.0
+    assert 0.3 <= np.abs(rec[:, 4:6]).max() / np.abs(ref[:, 4:6]).max() <= 3.0

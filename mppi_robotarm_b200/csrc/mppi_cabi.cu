@@ -160,7 +160,7 @@ void fill_dev_cfg(MppiHandle* h) {
     d.cost.s2 = (float)(c.stage_cost_weight[2] * 1e4); d.cost.s3 = (float)(c.stage_cost_weight[3] * 1e4);
     d.cost.t0 = (float)(c.terminal_cost_weight[0] * 1e4); d.cost.t1 = (float)(c.terminal_cost_weight[1] * 1e4);
     d.cost.t2 = (float)(c.terminal_cost_weight[2] * 1e4); d.cost.t3 = (float)(c.terminal_cost_weight[3] * 1e4);
-    d.noise.seed_lo = (uint32_t)(c.seed & 0xffffffffu); d.noise.seed_hi = (uint32_t)(c.seed >> 32);
+    d.noise.key = philox_expand_key((uint32_t)(c.seed & 0xffffffffu), (uint32_t)(c.seed >> 32));
     d.noise.step = 0;
     d.noise.L11 = (float)c.sigma_chol[0]; d.noise.L21 = (float)c.sigma_chol[2]; d.noise.L22 = (float)c.sigma_chol[3];
     d.K_local = c.K_local; d.K_total = c.K_total; d.k_offset = c.k_offset; d.T = c.T; d.n_env = c.n_env;

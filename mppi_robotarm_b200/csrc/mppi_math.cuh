@@ -194,7 +194,18 @@ MPPI_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
 #endif
 }
 
-MPPI_HD U4 philox4x32_10(U4 ctr, uint32_t k0, uint32_t k1) {
+// The ten round keys (k0 + i*0x9E3779B9, k1 + i*0xBB67AE85) depend only on the seed: they are
+// expanded once on the host and read as constant-bank operands instead of being re-derived by
+// every thread for every call.
+struct PhiloxKeys { uint32_t k0[10], k1[10]; };
+
+MPPI_HD PhiloxKeys philox_expand_key(uint32_t k0, uint32_t k1) {
+    PhiloxKeys k;
+    for (int i = 0; i < 10; ++i) { k.k0[i] = k0; k.k1[i] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    return k;
+}
+
+MPPI_HD U4 philox4x32_10(U4 ctr, const PhiloxKeys& key) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -202,9 +213,8 @@ MPPI_HD U4 philox4x32_10(U4 ctr, uint32_t k0, uint32_t k1) {
         uint32_t h0, l0, h1, l1;
         mulhilo(0xD2511F53u, ctr.x, h0, l0);
         mulhilo(0xCD9E8D57u, ctr.z, h1, l1);
-        U4 n = { h1 ^ ctr.y ^ k0, l1, h0 ^ ctr.w ^ k1, l0 };
+        U4 n = { h1 ^ ctr.y ^ key.k0[i], l1, h0 ^ ctr.w ^ key.k1[i], l0 };
         ctr = n;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     return ctr;
 }
@@ -212,7 +222,7 @@ MPPI_HD U4 philox4x32_10(U4 ctr, uint32_t k0, uint32_t k1) {
 // Counter layout: x = horizon pair index (t/2), y = global sample index, z = control-step counter,
 // w = environment index.  Keyed on the GLOBAL sample index so results do not depend on how samples
 // are sharded over GPUs.  One call yields the noise of two consecutive horizon steps.
-struct NoiseCfg { uint32_t seed_lo, seed_hi; uint32_t step; float L11, L21, L22; };
+struct NoiseCfg { PhiloxKeys key; uint32_t step; float L11, L21, L22; };
 
 MPPI_HD float u01_(uint32_t x) {          // (0, 1]
     return fma_((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
@@ -222,7 +232,8 @@ MPPI_HD float u01_(uint32_t x) {          // (0, 1]
 MPPI_HD void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
     float u = u01_(a), v = u01_(b);
 #if defined(__CUDA_ARCH__)
-    float r = __fsqrt_rn(mul_(-1.3862943611198906f, __log2f(u)));     // sqrt(-2 ln u)
+    float r;                                                          // sqrt(-2 ln u), MUFU.SQRT (no slow path)
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(mul_(-1.3862943611198906f, __log2f(u))));
     float sn, cs;
     __sincosf(mul_(6.2831853071795865f, v), &sn, &cs);
 #else
@@ -237,7 +248,7 @@ MPPI_HD void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
 MPPI_HD void noise_pair(const NoiseCfg& nc, uint32_t env, uint32_t k, uint32_t pair,
                         float& e0a, float& e0b, float& e1a, float& e1b) {
     U4 ctr = { pair, k, nc.step, env };
-    U4 r = philox4x32_10(ctr, nc.seed_lo, nc.seed_hi);
+    U4 r = philox4x32_10(ctr, nc.key);
     float z0, z1, z2, z3;
     box_muller(r.x, r.y, z0, z1);
     box_muller(r.z, r.w, z2, z3);
@@ -286,26 +297,35 @@ struct WinRegs {
 template <class Win>
 MPPI_HD int nearest_candidate(const Win& win, float xl, float yl) {
     float d[kWindowPad];
-    int id[kWindowPad];
+    float id[kWindowPad / 2];            // indices as small exact floats
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int j = 0; j < kWindow; ++j) { d[j] = fma_(win.a(j), xl, fma_(win.b(j), yl, win.c(j))); id[j] = j; }
-    d[30] = kSentinel; d[31] = kSentinel; id[30] = 30; id[31] = 31;
+    for (int j = 0; j < kWindow; ++j) d[j] = fma_(win.a(j), xl, fma_(win.b(j), yl, win.c(j)));
+    d[30] = kSentinel; d[31] = kSentinel;
+    // level 1: adjacent pairs; the index is 2i + [d(2i+1) < d(2i)]
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int w = 1; w < kWindowPad; w *= 2) {
+    for (int i = 0; i < kWindowPad / 2; ++i) {
+        const float lt = d[2 * i + 1] < d[2 * i] ? 1.0f : 0.0f;
+        id[i] = add_(lt, (float)(2 * i));
+        d[i] = fminf(d[2 * i + 1], d[2 * i]);     // d[i] is only overwritten after d[2i], d[2i+1] were read
+    }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int j = 0; j + w < kWindowPad; j += 2 * w) {
-            const bool lt = d[j + w] < d[j];
-            d[j] = lt ? d[j + w] : d[j];
-            id[j] = lt ? id[j + w] : id[j];
+    for (int n = kWindowPad / 4; n >= 1; n /= 2) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int i = 0; i < n; ++i) {
+            const bool lt = d[2 * i + 1] < d[2 * i];
+            id[i] = lt ? id[2 * i + 1] : id[2 * i];
+            d[i] = lt ? d[2 * i + 1] : d[2 * i];
         }
     }
-    return id[0];
+    return (int)id[0];
 }
 
 // Variant of the search that keeps the ALU pipe (half rate on sm_100) free: the minimum VALUE comes

@@ -55,12 +55,12 @@ int emul_rollout_costs(const double* ref, int n_rows, int prev_idx, const double
 void emul_sincos(const float* x, int n, float* s, float* c) { for (int i = 0; i < n; ++i) sincos_(x[i], s[i], c[i]); }
 
 void emul_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
-    U4 r = philox4x32_10(U4{c0, c1, c2, c3}, k0, k1); out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+    U4 r = philox4x32_10(U4{c0, c1, c2, c3}, philox_expand_key(k0, k1)); out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 
 void emul_noise(uint32_t seed_lo, uint32_t seed_hi, uint32_t step, const double* chol, uint32_t env,
                 uint32_t k0, int K, int T, float* eps) {
-    NoiseCfg nc{ seed_lo, seed_hi, step, (float)chol[0], (float)chol[2], (float)chol[3] };
+    NoiseCfg nc{ philox_expand_key(seed_lo, seed_hi), step, (float)chol[0], (float)chol[2], (float)chol[3] };
     for (int k = 0; k < K; ++k)
         for (int p = 0; 2 * p < T; ++p) {
             float a, b, c, d; noise_pair(nc, env, k0 + k, p, a, b, c, d);

@@ -17,9 +17,12 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--noise", default="philox", choices=["philox", "injected"])
     ap.add_argument("--timing", action="store_true")
+    ap.add_argument("--lam", type=float, default=100.0, help="param_lambda (1e9: every weight non-zero)")
     a = ap.parse_args()
     from mppi_robotarm_b200 import MPPIControllerForPathTracking
-    ctrl = MPPIControllerForPathTracking(**bench.run_py_kwargs(bench.synthetic_ref_path(), a.K, a.T), noise="philox",
+    kw = bench.run_py_kwargs(bench.synthetic_ref_path(), a.K, a.T)
+    kw["param_lambda"] = a.lam
+    ctrl = MPPIControllerForPathTracking(**kw, noise="philox",
                                          seed=1, verbose=False, use_graph=False)
     eng = ctrl._engine()
     eps = eng.philox_noise(step=0) if a.noise == "injected" else None

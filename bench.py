@@ -36,6 +36,8 @@ sys.path.insert(0, ROOT)
 K_TOTAL = 1 << 20
 T_HORIZON = 100
 FLOPS_PER_SAMPLE_STEP = 254.0          # 70 + 6*30 + 4
+NCU_ROLLOUT_DRAM_BYTES = 22272         # dram__bytes_read+write of the rollout kernel, one ncu --set full capture
+NCU_WSUM_DRAM_BYTES = 843073280 + 3861504   # same for mppi_wsum_injected_sm100a (algorithmic: K*T*8 = 838,860,800)
 LAT_K, LAT_T = 16384, 50               # BASELINE.json configs[2]
 
 
@@ -370,7 +372,10 @@ def main():
             roll_us = timing["rollout"]
             ach = FLOPS_PER_SAMPLE_STEP * eng.K_local * T_HORIZON / (roll_us * 1e-6) / 1e12
             line["roofline"] = {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                                "traffic": None, "kernel": "mppi_rollout_sm100a<philox>",
+                                "traffic": NCU_ROLLOUT_DRAM_BYTES,
+                                "traffic_source": "ncu --set full, profiles/r1c_rollout_ncu_summary.txt "
+                                                  "(dram read 22,272 B + write 0 B per launch at K=2^20, T=100)",
+                                "kernel": "mppi_rollout_sm100a<philox>",
                                 "kernel_us": roll_us, "peak_source": "mppi_probe_fp32 FMA chain, this GPU, this run",
                                 "mufu_peak_gops": mufu.value / 1e9,
                                 "flops_per_sample_step": FLOPS_PER_SAMPLE_STEP,
@@ -411,7 +416,15 @@ def main():
 
     # ---- injected-noise mode: achieved HBM GB/s of the two kernels that read the K x T x 2 tensor ----
     if rank == 0 and world == 1 and not args.no_injected:
-        line["injected_noise"] = injected_mode_numbers(ref, torch)
+        inj = injected_mode_numbers(ref, torch)
+        line["injected_noise"] = inj
+        a = inj["all_weights_nonzero"]
+        # second roofline: the HBM-bound kernel of the noise-read mode (north_star: achieved HBM GB/s)
+        line["roofline_hbm"] = {"bound": "hbm", "kernel": "mppi_wsum_injected_sm100a<float4>", "achieved": a["wsum_gbs"],
+                                "peak": inj["hbm_peak_gbs"], "unit": "GB/s", "frac": a["wsum_frac_of_hbm_peak"],
+                                "traffic": NCU_WSUM_DRAM_BYTES, "peak_source": inj["hbm_peak_source"],
+                                "traffic_source": "ncu --set full, profiles/r1c_wsum_injected_ncu_summary.txt",
+                                "algorithmic_bytes": inj["tensor_bytes"], "kernel_us": a["wsum_us"]}
 
     # ---- config 5: batched multi-environment sweep (environments shard over GPUs, no collective) ----
     if rank == 0 and world == 1 and not args.no_batched:

@@ -25,7 +25,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct Workspace {
     size_t bytes;
     size_t off_ref, off_step_blocks, off_in, off_out, off_S, off_w, off_block_min, off_eta_part,
-        off_rho, off_v_part, off_partial, off_loop;
+        off_rho, off_v_part, off_partial, off_loop, off_eta_fused, off_tickets;
 };
 
 }  // namespace
@@ -56,6 +56,9 @@ struct MppiHandle {
     uint64_t graph_kernels;
     bool have_step;            // a step has run (step blocks valid)
     bool const_window;         // single environment: window coefficients go through the constant bank
+    int ns;                    // samples per thread of the rollout kernel
+    bool zero_copy;            // kernels read / write the caller's pinned block directly (no memcpy nodes)
+    DevIo dio_dev;             // same as dio but never touching the pinned block (device closed loop)
     bool capture_mode;         // caller is capturing: enqueue capturable work only
     uint64_t capture_kernels;  // kernels enqueued while capture mode was on (= per replay)
     cudaEvent_t const_ev;      // recorded after this handle's last reader of the constant-bank window
@@ -92,9 +95,15 @@ bool valid_cfg(const MppiConfig* c, const char** why) {
     return true;
 }
 
+// samples per thread of the rollout kernel: 2 when there is enough work to fill the GPU that way
+int pick_ns(const MppiConfig* c) {
+    return ((long long)c->K_local * c->n_env >= 131072) ? 2 : 1;
+}
+
 void grid_sizes(const MppiConfig* c, int sm, int* g_roll, int* g_soft, int* g_wsum) {
     const int K = c->K_local;
-    int gr = (K + kRollThreads * kNS - 1) / (kRollThreads * kNS);
+    const int ns = pick_ns(c);
+    int gr = (K + kRollThreads * ns - 1) / (kRollThreads * ns);
     if (gr > 32768) gr = 32768;
     *g_roll = gr;
     int gs = (K + kSoftThreads * 4 - 1) / (kSoftThreads * 4);
@@ -130,6 +139,8 @@ void carve(const MppiConfig* c, int sm, Workspace* w) {
     w->off_v_part = take(E * g_wsum * 2 * T * sizeof(float));
     w->off_partial = take(E * (2 + 2 * T) * sizeof(double));
     w->off_loop = take(sizeof(LoopParams));
+    w->off_eta_fused = take(E * g_wsum * sizeof(double));
+    w->off_tickets = take(E * sizeof(unsigned int));
     w->bytes = off;
 }
 
@@ -218,52 +229,60 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
     float* v_part = (float*)(ws + h->ws.off_v_part);
     const double* ref = (const double*)(ws + h->ws.off_ref);
 
-    if (copy_inputs) CU(h, cudaMemcpyAsync(ws + h->ws.off_in, h->host, h->in_bytes, cudaMemcpyHostToDevice, s));
+    // host_io = false: the step works on the device mirror only (ticks of the device closed loop)
+    const bool zc = h->zero_copy && copy_inputs;
+    const DevIo& dio = copy_inputs ? h->dio : h->dio_dev;
+    if (copy_inputs && !h->zero_copy)
+        CU(h, cudaMemcpyAsync(ws + h->ws.off_in, h->host, h->in_bytes, cudaMemcpyHostToDevice, s));
     if (timed) CU(h, cudaEventRecord(h->tev[0], s));
-    mppi_prepare_sm100a<<<dc.n_env, 32, 0, s>>>(dc, h->dio, ref, step_blocks);
+    mppi_prepare_sm100a<<<dc.n_env, 32, 0, s>>>(dc, dio, ref, step_blocks, zc);
     if (timed) CU(h, cudaEventRecord(h->tev[1], s));
     {
         dim3 grid(dc.g_roll, dc.n_env);
+        const bool ph = noise_mode == MPPI_NOISE_PHILOX;
         if (h->const_window) {
-            // single environment: stage this step's window coefficients in the constant bank
+            // single environment, large K: stage this step's window coefficients in the constant bank
             if (!capturing) { int rc = const_acquire(h, s); if (rc != MPPI_OK) return rc; }
             CU(h, cudaMemcpyToSymbolAsync(c_window, step_blocks + 64, sizeof(WinEntry) * kWindowPad, 0,
                                           cudaMemcpyDeviceToDevice, s));
-            if (noise_mode == MPPI_NOISE_PHILOX)
-                mppi_rollout_sm100a<0, true><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, nullptr, S, bmin);
-            else
-                mppi_rollout_sm100a<1, true><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, eps_dev, S, bmin);
-            if (!capturing) { int rc = const_release(h, s); if (rc != MPPI_OK) return rc; }
-        } else if (noise_mode == MPPI_NOISE_PHILOX) {
-            mppi_rollout_sm100a<0, false><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, nullptr, S, bmin);
-        } else {
-            mppi_rollout_sm100a<1, false><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, eps_dev, S, bmin);
         }
+#define MPPI_LAUNCH_ROLL(NOISE, CW, NS_) \
+        mppi_rollout_sm100a<NOISE, CW, NS_><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, ph ? nullptr : eps_dev, S, bmin)
+        if (h->const_window) {
+            if (h->ns == 2) { if (ph) MPPI_LAUNCH_ROLL(0, true, 2); else MPPI_LAUNCH_ROLL(1, true, 2); }
+            else { if (ph) MPPI_LAUNCH_ROLL(0, true, 1); else MPPI_LAUNCH_ROLL(1, true, 1); }
+            if (!capturing) { int rc = const_release(h, s); if (rc != MPPI_OK) return rc; }
+        } else {
+            if (h->ns == 2) { if (ph) MPPI_LAUNCH_ROLL(0, false, 2); else MPPI_LAUNCH_ROLL(1, false, 2); }
+            else { if (ph) MPPI_LAUNCH_ROLL(0, false, 1); else MPPI_LAUNCH_ROLL(1, false, 1); }
+        }
+#undef MPPI_LAUNCH_ROLL
     }
     if (timed) CU(h, cudaEventRecord(h->tev[2], s));
-    mppi_softmin_sm100a<<<dim3(dc.g_soft, dc.n_env), kSoftThreads, 0, s>>>(dc, S, bmin, w, eta_part, rho);
-    if (timed) CU(h, cudaEventRecord(h->tev[3], s));
-    int g_wsum_used = dc.g_wsum;
-    {
-        if (noise_mode == MPPI_NOISE_PHILOX) {               // scanning weights: K/4096 blocks are plenty
-            const int want = (dc.K_local + 4095) / 4096;
-            if (want < g_wsum_used) g_wsum_used = want;
-        }
-        dim3 grid(g_wsum_used, dc.n_env);
-        if (noise_mode == MPPI_NOISE_PHILOX) {
-            const size_t sm = (size_t)(kWsumThreads / 32) * ((dc.T + 1) / 2) * sizeof(float4);
-            mppi_wsum_philox_sm100a<<<grid, kWsumThreads, sm, s>>>(dc, step_ctr, w, v_part);
-        } else if ((dc.T & 1) == 0 && (((uintptr_t)eps_dev) & 15) == 0) {
+    if (noise_mode == MPPI_NOISE_PHILOX) {
+        // fused: soft-min weights + weighted sum + this GPU's partial triple
+        int g = (dc.K_local + 4095) / 4096;
+        if (g > dc.g_wsum) g = dc.g_wsum;
+        const size_t sm = (size_t)(kWsumThreads / 32) * ((dc.T + 1) / 2) * sizeof(float4);
+        mppi_softmin_wsum_philox_sm100a<<<dim3(g, dc.n_env), kWsumThreads, sm, s>>>(
+            dc, step_ctr, S, bmin, w, (double*)(ws + h->ws.off_eta_fused), v_part,
+            (unsigned int*)(ws + h->ws.off_tickets), rho, partial_dev);
+        if (timed) { CU(h, cudaEventRecord(h->tev[3], s)); CU(h, cudaEventRecord(h->tev[4], s)); }
+        h->launches += 3;
+    } else {
+        mppi_softmin_sm100a<<<dim3(dc.g_soft, dc.n_env), kSoftThreads, 0, s>>>(dc, S, bmin, w, eta_part, rho);
+        if (timed) CU(h, cudaEventRecord(h->tev[3], s));
+        dim3 grid(dc.g_wsum, dc.n_env);
+        if ((dc.T & 1) == 0 && (((uintptr_t)eps_dev) & 15) == 0)
             mppi_wsum_injected_sm100a<float4><<<grid, kWsumThreads, kWsumThreads * sizeof(float4), s>>>(dc, w, eps_dev, v_part);
-        } else {
+        else
             mppi_wsum_injected_sm100a<float2><<<grid, kWsumThreads, kWsumThreads * sizeof(float2), s>>>(dc, w, eps_dev, v_part);
-        }
+        if (timed) CU(h, cudaEventRecord(h->tev[4], s));
+        mppi_reduce_sm100a<<<dc.n_env, kReduceThreads, 0, s>>>(dc, dc.g_wsum, rho, eta_part, v_part, partial_dev);
+        h->launches += 5;
     }
-    if (timed) CU(h, cudaEventRecord(h->tev[4], s));
-    mppi_reduce_sm100a<<<dc.n_env, kReduceThreads, 0, s>>>(dc, g_wsum_used, rho, eta_part, v_part, partial_dev);
     if (timed) CU(h, cudaEventRecord(h->tev[5], s));
     CU(h, cudaGetLastError());
-    h->launches += 5;
     h->have_step = true;
     return MPPI_OK;
 }
@@ -271,10 +290,10 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
 int enqueue_combine(MppiHandle* h, const double* gathered_dev, int world, cudaStream_t s, bool timed,
                     bool record_done = true, bool copy_outputs = true) {
     if (world < 1 || world > 64) return fail(h, MPPI_ERR_INVALID, "%s", "world must be in [1, 64]");
-    mppi_finalize_sm100a<<<h->dc.n_env, 256, 0, s>>>(h->dc, h->dio, gathered_dev, world);
+    mppi_finalize_sm100a<<<h->dc.n_env, 256, 0, s>>>(h->dc, copy_outputs ? h->dio : h->dio_dev, gathered_dev, world);
     if (timed) CU(h, cudaEventRecord(h->tev[6], s));
     CU(h, cudaGetLastError());
-    if (copy_outputs) CU(h, cudaMemcpyAsync(h->host + h->out_off, h->dev + h->ws.off_out, h->out_bytes, cudaMemcpyDeviceToHost, s));
+    if (copy_outputs && !h->zero_copy) CU(h, cudaMemcpyAsync(h->host + h->out_off, h->dev + h->ws.off_out, h->out_bytes, cudaMemcpyDeviceToHost, s));
     if (record_done) CU(h, cudaEventRecord(h->done, s));      // not inside a stream capture
     h->launches += 1;
     return MPPI_OK;
@@ -379,7 +398,30 @@ int mppi_create(const MppiConfig* c, void* workspace, size_t workspace_bytes, vo
     h->dio.u_new = (double*)(dout + h->io.off_u_new);
     h->dio.opt_traj = (double*)(dout + h->io.off_opt_traj);
     h->roll_smem = (size_t)h->dc.step_block_bytes;
-    h->const_window = (c->n_env == 1) && getenv("MPPI_NO_CONST_WINDOW") == nullptr;
+    h->ns = pick_ns(c);
+    // constant-bank window: single environment and enough work to pay for the extra copy node
+    h->const_window = (c->n_env == 1) && ((long long)c->K_local * c->T >= (1ll << 21)) &&
+                      getenv("MPPI_NO_CONST_WINDOW") == nullptr;
+    h->dio_dev = h->dio;
+    h->dio_dev.host_in = nullptr; h->dio_dev.in_delta = 0; h->dio_dev.out_delta = 0;
+    h->dio.host_in = nullptr; h->dio.in_delta = 0; h->dio.out_delta = 0;
+    {   // zero-copy io: let the kernels touch the caller's pinned block directly (UVA-mapped)
+        void* dptr = nullptr;
+        if (getenv("MPPI_NO_ZERO_COPY") == nullptr &&
+            cudaHostGetDevicePointer(&dptr, io_host, 0) == cudaSuccess && dptr != nullptr) {
+            h->zero_copy = true;
+            h->dio.host_in = (const char*)dptr;
+            h->dio.in_delta = (char*)din - (char*)dptr;
+            h->dio.out_delta = (char*)dptr - dout;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    if (cudaMemset(h->dev + h->ws.off_tickets, 0, sizeof(unsigned int) * c->n_env) != cudaSuccess) {
+        snprintf(g_create_error, sizeof(g_create_error), "cudaMemset(tickets) failed");
+        delete h;
+        return MPPI_ERR_CUDA;
+    }
     cudaError_t e = cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->const_ev, cudaEventDisableTiming);
     for (int i = 0; i <= kNumTimers && e == cudaSuccess; ++i) e = cudaEventCreate(&h->tev[i]);

@@ -110,14 +110,40 @@ struct DevIo {
     double* rho; double* eta;            // [n_env]
     double* w_eps_raw; double* w_eps_filt; double* u_new;   // [n_env][T][2]
     double* opt_traj;                    // [n_env][T][4]
+    // zero-copy mode: the caller's pinned block is read / written directly by the kernels
+    const char* host_in;     // device-visible address of the pinned block's inputs, or null
+    ptrdiff_t in_delta;      // (device input mirror) - (pinned block): same field offsets in both
+    ptrdiff_t out_delta;     // (pinned block outputs) - (device output mirror), 0 = do not mirror to the host
 };
+
+// store an output to the device mirror and, in zero-copy mode, to the same field of the pinned block
+template <class TT>
+__device__ __forceinline__ void out_store(const DevIo& io, TT* dev_ptr, TT v) {
+    *dev_ptr = v;
+    if (io.out_delta != 0) *(TT*)((char*)dev_ptr + io.out_delta) = v;
+}
 
 // ================================================================================================
 // 1. prepare: one warp per environment
 // ================================================================================================
 __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, const double* __restrict__ ref,
-                                                          char* __restrict__ step_blocks) {
+                                                          char* __restrict__ step_blocks, bool pull_inputs) {
     const int e = blockIdx.x, lane = threadIdx.x;
+    if (io.host_in != nullptr && pull_inputs) {
+        // zero-copy: this environment's inputs come straight from the caller's pinned block; they are
+        // also written to the device mirror, which every later kernel of the step reads
+        const double* hx = (const double*)((const char*)io.x0 - io.in_delta) + 4 * e;
+        const double* hu = (const double*)((const char*)io.u_prev - io.in_delta) + (size_t)e * cfg.T * 2;
+        double* dx = const_cast<double*>(io.x0) + 4 * e;
+        double* du = const_cast<double*>(io.u_prev) + (size_t)e * cfg.T * 2;
+        if (lane < 4) dx[lane] = hx[lane];
+        for (int c = lane; c < 2 * cfg.T; c += 32) du[c] = hu[c];
+        if (lane == 0) {
+            const_cast<int32_t*>(io.prev_idx)[e] = *(const int32_t*)((const char*)(io.prev_idx + e) - io.in_delta);
+            if (e == 0) *const_cast<uint64_t*>(io.step) = *(const uint64_t*)((const char*)io.step - io.in_delta);
+        }
+        __syncwarp();
+    }
     const double* x0 = io.x0 + 4 * e;
     const int n = cfg.n_ref_rows;
     int p = io.prev_idx[e];
@@ -145,7 +171,7 @@ __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, 
         h.status = (p >= n - 1) ? 1 : 0;                     // control.py:76
         for (int i = 0; i < 7; ++i) h.pad[i] = 0;
         *sb.hd = h;
-        io.new_idx[e] = p;
+        out_store(io, io.new_idx + e, p);
     }
     {
         WinEntry w; RefRow r;
@@ -182,9 +208,8 @@ struct InjectedNoise {          // eps read from the caller's [K,T,2] tensor
     }
 };
 
-#ifndef MPPI_NS
-#define MPPI_NS 2                  // samples per thread in the rollout kernel (A/B on B200: profiles/r1_variants.md)
-#endif
+// samples per thread in the rollout kernel: 2 for throughput (A/B on B200: profiles/r1_variants.md),
+// 1 when there are too few samples to fill the GPU twice over (latency runs)
 
 // Single-environment fast path: the window coefficients of the current step are copied (device to
 // device, in stream order after the prepare kernel) into this constant-bank table, and the search's
@@ -209,16 +234,12 @@ struct WinConst {
     __device__ __forceinline__ float a(int j) const { return c_window[j].a; }
     __device__ __forceinline__ float b(int j) const { return c_window[j].b; }
 };
-#ifndef MPPI_ROLL_MIN_BLOCKS
-#define MPPI_ROLL_MIN_BLOCKS (MPPI_NS == 1 ? 3 : 2)
-#endif
 #ifndef MPPI_ROLL_MIN_BLOCKS_CONST
 #define MPPI_ROLL_MIN_BLOCKS_CONST 4
 #endif
-constexpr int kNS = MPPI_NS;
 
-template <int NOISE, bool CONSTWIN>
-__global__ void __launch_bounds__(kRollThreads, CONSTWIN ? MPPI_ROLL_MIN_BLOCKS_CONST : MPPI_ROLL_MIN_BLOCKS)
+template <int NOISE, bool CONSTWIN, int kNS>
+__global__ void __launch_bounds__(kRollThreads, CONSTWIN ? MPPI_ROLL_MIN_BLOCKS_CONST : (kNS == 1 ? 3 : 2))
 mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const char* __restrict__ step_blocks,
                     const float* __restrict__ eps, float* __restrict__ S_out, float* __restrict__ block_min) {
     extern __shared__ __align__(128) unsigned char smem_roll[];
@@ -469,6 +490,127 @@ mppi_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const
 }
 
 // ================================================================================================
+// 4c. Philox mode, fused: soft-min weights + weighted noise sum + this GPU's partial triple in ONE
+//     launch (three launches less per control step, which is what bounds the 1 kHz loop and the
+//     8-GPU strong-scaling run).  Same arithmetic and summation order as kernels 3, 4b and 5: every
+//     block derives rho from the rollout's block minima, weights its slice of samples, regenerates
+//     eps for the non-zero weights, writes its partials; the block that arrives last (atomic ticket)
+//     adds the partials of all blocks in block order, so the result does not depend on arrival order.
+// ================================================================================================
+__global__ void __launch_bounds__(kWsumThreads)
+mppi_softmin_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const float* __restrict__ S,
+                                const float* __restrict__ block_min, float* __restrict__ w,
+                                double* __restrict__ eta_part, float* __restrict__ v_part,
+                                unsigned int* __restrict__ tickets, float* __restrict__ rho_out,
+                                double* __restrict__ partial) {
+    extern __shared__ __align__(16) unsigned char smem_wsum[];
+    float4* sh = (float4*)smem_wsum;                          // [warps][pairs]
+    __shared__ float redf[kWsumThreads / 32];
+    __shared__ double redd[kWsumThreads / 32];
+    __shared__ float rho_s;
+    __shared__ bool is_last;
+    const int e = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_pairs = (cfg.T + 1) >> 1;
+    // rho = min over the rollout kernel's block minima
+    float m = INFINITY;
+    for (int i = tid; i < cfg.g_roll; i += kWsumThreads) m = fminf(m, block_min[(size_t)e * cfg.g_roll + i]);
+    m = warp_min(m);
+    if (lane == 0) redf[warp] = m;
+    __syncthreads();
+    if (tid == 0) {
+        float r = redf[0];
+#pragma unroll
+        for (int i = 1; i < kWsumThreads / 32; ++i) r = fminf(r, redf[i]);
+        rho_s = r;
+        if (blockIdx.x == 0) rho_out[e] = r;
+    }
+    __syncthreads();
+    const float rho = rho_s;
+    const float nil = (float)(-cfg.inv_lambda);
+    NoiseCfg nc = cfg.noise; nc.step = (uint32_t)(*step_ctr);
+    const float* Se = S + (size_t)e * cfg.K_local;
+    float* we = w + (size_t)e * cfg.K_local;
+    float4 acc[kPairSlots];
+#pragma unroll
+    for (int i = 0; i < kPairSlots; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    double eta = 0.0;
+    const int warps_total = gridDim.x * (kWsumThreads / 32);
+    for (int k0 = (blockIdx.x * (kWsumThreads / 32) + warp) * 32; k0 < cfg.K_local; k0 += warps_total * 32) {
+        const int k = k0 + lane;
+        float wk = 0.0f;
+        if (k < cfg.K_local) {
+            const float s = Se[k];
+            const float x = expf((s - rho) * nil);
+            wk = finite_(s) ? x : 0.0f;
+            we[k] = wk;
+            eta += (double)wk;
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, wk != 0.0f);
+        while (mask) {
+            const int b = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float wb = __shfl_sync(0xffffffffu, wk, b);
+            const uint32_t kg = (uint32_t)(cfg.k_offset + k0 + b);
+#pragma unroll
+            for (int i = 0; i < kPairSlots; ++i) {
+                const int pr = lane + 32 * i;
+                if (pr < n_pairs) {
+                    float a0, a1, b0, b1;
+                    noise_pair(nc, (uint32_t)e, kg, (uint32_t)pr, a0, a1, b0, b1);
+                    acc[i].x = fmaf(wb, a0, acc[i].x); acc[i].y = fmaf(wb, a1, acc[i].y);
+                    acc[i].z = fmaf(wb, b0, acc[i].z); acc[i].w = fmaf(wb, b1, acc[i].w);
+                }
+            }
+        }
+    }
+    eta = warp_sum(eta);
+    if (lane == 0) redd[warp] = eta;
+#pragma unroll
+    for (int i = 0; i < kPairSlots; ++i) {
+        const int pr = lane + 32 * i;
+        if (pr < n_pairs) sh[warp * n_pairs + pr] = acc[i];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double r = 0.0;
+#pragma unroll
+        for (int i = 0; i < kWsumThreads / 32; ++i) r += redd[i];
+        eta_part[(size_t)e * cfg.g_soft + blockIdx.x] = r;
+    }
+    float* vrow = v_part + ((size_t)e * cfg.g_wsum + blockIdx.x) * 2 * cfg.T;
+    for (int pr = tid; pr < n_pairs; pr += kWsumThreads) {
+        float4 s4 = sh[pr];
+        for (int wv = 1; wv < kWsumThreads / 32; ++wv) {
+            const float4 v = sh[wv * n_pairs + pr];
+            s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+        }
+        vrow[4 * pr] = s4.x; vrow[4 * pr + 1] = s4.y;
+        if (2 * pr + 1 < cfg.T) { vrow[4 * pr + 2] = s4.z; vrow[4 * pr + 3] = s4.w; }
+    }
+    // ---- last block: this GPU's partial (rho_g, eta_g, V_g), fixed summation order ----------------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = (atomicAdd(&tickets[e], 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double* out = partial + (size_t)e * (2 + 2 * cfg.T);
+    const int G = gridDim.x;
+    if (warp == 0) {
+        double a = 0.0;
+        for (int i = lane; i < G; i += 32) a += __ldcg(eta_part + (size_t)e * cfg.g_soft + i);
+        a = warp_sum(a);
+        if (lane == 0) { out[0] = (double)rho; out[1] = a; tickets[e] = 0u; }
+    }
+    for (int c = tid; c < 2 * cfg.T; c += kWsumThreads) {
+        double a = 0.0;
+        const float* src = v_part + (size_t)e * cfg.g_wsum * 2 * cfg.T + c;
+        for (int b = 0; b < G; ++b) a += (double)__ldcg(src + (size_t)b * 2 * cfg.T);
+        out[2 + c] = a;
+    }
+}
+
+// ================================================================================================
 // 5. reduce: this GPU's partial triple per environment, FP64, fixed summation order.
 //    partial[e] = { rho_g, eta_g, V_g[2T] }
 // ================================================================================================
@@ -540,7 +682,7 @@ mppi_finalize_sm100a(DevCfg cfg, DevIo io, const double* __restrict__ gathered, 
             eta += sg * g0[g * stride_rank + 1];
         }
         eta_s = eta;
-        io.rho[e] = rho; io.eta[e] = eta;
+        out_store(io, io.rho + e, rho); out_store(io, io.eta + e, eta);
     }
     __syncthreads();
     for (int c = tid; c < 2 * T; c += blockDim.x) {
@@ -551,7 +693,7 @@ mppi_finalize_sm100a(DevCfg cfg, DevIo io, const double* __restrict__ gathered, 
         }
         v /= eta_s;
         raw[c] = v;
-        io.w_eps_raw[(size_t)e * 2 * T + c] = v;
+        out_store(io, io.w_eps_raw + (size_t)e * 2 * T + c, v);
     }
     __syncthreads();
     // scipy.ndimage.median_filter(size=10, mode='reflect') per column (control.py:319-327):
@@ -571,8 +713,8 @@ mppi_finalize_sm100a(DevCfg cfg, DevIo io, const double* __restrict__ gathered, 
         }
         const double u = io.u_prev[(size_t)e * 2 * T + c] + med;        // control.py:126
         unew[c] = u;
-        io.w_eps_filt[(size_t)e * 2 * T + c] = med;
-        io.u_new[(size_t)e * 2 * T + c] = u;
+        out_store(io, io.w_eps_filt + (size_t)e * 2 * T + c, med);
+        out_store(io, io.u_new + (size_t)e * 2 * T + c, u);
     }
     __syncthreads();
     // control.py:129-134: x <- F(x, u[t-1]) for t = 0..T-1 (t = 0 wraps to the last control, Q3)
@@ -584,12 +726,14 @@ mppi_finalize_sm100a(DevCfg cfg, DevIo io, const double* __restrict__ gathered, 
             for (int t = 0; t < T; ++t) {
                 const int tc = t == 0 ? T - 1 : t - 1;
                 arm_step(st, cfg.arm, (float)unew[2 * tc], (float)unew[2 * tc + 1]);
-                o[4 * t + 0] = (double)st.q1 - (double)st.kq1; o[4 * t + 1] = (double)st.q2 - (double)st.kq2;
-                o[4 * t + 2] = (double)st.d1 - (double)st.kd1; o[4 * t + 3] = (double)st.d2 - (double)st.kd2;
+                out_store(io, o + 4 * t + 0, (double)st.q1 - (double)st.kq1);
+                out_store(io, o + 4 * t + 1, (double)st.q2 - (double)st.kq2);
+                out_store(io, o + 4 * t + 2, (double)st.d1 - (double)st.kd1);
+                out_store(io, o + 4 * t + 3, (double)st.d2 - (double)st.kd2);
             }
         }
     } else {
-        for (int c = tid; c < 4 * T; c += blockDim.x) io.opt_traj[(size_t)e * 4 * T + c] = 0.0;
+        for (int c = tid; c < 4 * T; c += blockDim.x) out_store(io, io.opt_traj + (size_t)e * 4 * T + c, 0.0);
     }
 }
 

@@ -407,7 +407,8 @@ int mppi_create(const MppiConfig* c, void* workspace, size_t workspace_bytes, vo
     h->dio.host_in = nullptr; h->dio.in_delta = 0; h->dio.out_delta = 0;
     {   // zero-copy io: let the kernels touch the caller's pinned block directly (UVA-mapped)
         void* dptr = nullptr;
-        if (getenv("MPPI_NO_ZERO_COPY") == nullptr &&
+        // (only while the block is small: for many environments a DMA copy beats PCIe loads/stores)
+        if (getenv("MPPI_NO_ZERO_COPY") == nullptr && h->io.bytes <= 65536 &&
             cudaHostGetDevicePointer(&dptr, io_host, 0) == cudaSuccess && dptr != nullptr) {
             h->zero_copy = true;
             h->dio.host_in = (const char*)dptr;

@@ -136,12 +136,19 @@ __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, 
         const double* hu = (const double*)((const char*)io.u_prev - io.in_delta) + (size_t)e * cfg.T * 2;
         double* dx = const_cast<double*>(io.x0) + 4 * e;
         double* du = const_cast<double*>(io.u_prev) + (size_t)e * cfg.T * 2;
-        if (lane < 4) dx[lane] = hx[lane];
-        for (int c = lane; c < 2 * cfg.T; c += 32) du[c] = hu[c];
-        if (lane == 0) {
-            const_cast<int32_t*>(io.prev_idx)[e] = *(const int32_t*)((const char*)(io.prev_idx + e) - io.in_delta);
-            if (e == 0) *const_cast<uint64_t*>(io.step) = *(const uint64_t*)((const char*)io.step - io.in_delta);
-        }
+        // issue every PCIe read before using any of them: one round trip instead of several
+        constexpr int kSlots = (2 * MPPI_MAX_T_INTERNAL + 31) / 32;
+        double vu[kSlots];
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i) { const int c = lane + 32 * i; vu[i] = c < 2 * cfg.T ? hu[c] : 0.0; }
+        const double vx = lane < 4 ? hx[lane] : 0.0;
+        const int32_t pidx = lane == 4 ? *(const int32_t*)((const char*)(io.prev_idx + e) - io.in_delta) : 0;
+        const uint64_t stp = (lane == 5 && e == 0) ? *(const uint64_t*)((const char*)io.step - io.in_delta) : 0;
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i) { const int c = lane + 32 * i; if (c < 2 * cfg.T) du[c] = vu[i]; }
+        if (lane < 4) dx[lane] = vx;
+        if (lane == 4) const_cast<int32_t*>(io.prev_idx)[e] = pidx;
+        if (lane == 5 && e == 0) *const_cast<uint64_t*>(io.step) = stp;
         __syncwarp();
     }
     const double* x0 = io.x0 + 4 * e;

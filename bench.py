@@ -67,10 +67,18 @@ X0 = np.array([1.152198236517471885, -1.266101672070702344, 0.0, 0.0])
 # clocks sampler (NVML) — runs during the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    def __init__(self, index):
+    """NVML clocks / throttle reasons of one GPU during the timed region.  NVML queries go through the
+    driver's global lock, so they are kept sparse (first sample 5 ms into the region, then every 200 ms,
+    like `nvidia-smi -lms 200`) and only rank 0 samples: eight ranks polling at 20 Hz measurably slowed
+    the 8-GPU run (steps of 0.3 ms)."""
+
+    def __init__(self, index, enabled=True):
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._thr = None
+        self.nv = None
+        if not enabled:
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -84,6 +92,8 @@ class ClockSampler:
         nv = self.nv
         names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                  0x80: "hw_power_brake_slowdown"}
+        if self._stop.wait(0.005):
+            return
         while not self._stop.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
@@ -93,7 +103,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.2)
 
     def __enter__(self):
         if self.nv:
@@ -315,7 +325,7 @@ def main():
     # events, with the L2 flush between brackets) and the host synchronises once at the end — the
     # synthetic batches are independent, so nothing forces a host round trip per step here.  The
     # host-synchronised, closed-loop-style number is `e2e` below.
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank, enabled=(rank == 0)) as clocks:
         for a, b in ev:
             with torch.cuda.stream(eng.stream):
                 flush.zero_()
@@ -328,7 +338,8 @@ def main():
         eng.wait()
         barrier()
     launches = eng.launch_count() - launches0
-    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    per_step = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(per_step)
     timing = eng.get_timing() if not distributed else None
     eng.set_timing(False)
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
@@ -360,7 +371,8 @@ def main():
     line = {"metric": "mppi_sample_steps_per_s", "value": value, "unit": "sample-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world), "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches)}
+            "config": workload_config(world), "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            "ms_per_step_stats_rank0": {"min": min(per_step), "median": float(np.median(per_step)), "max": max(per_step)}}
 
     if rank == 0:
         # ---- roofline of the dominant kernel (rollout) against the measured FP32 peak ----------

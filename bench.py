@@ -335,6 +335,9 @@ def main():
         device_step(); eng.wait()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = eng.launch_count()
+    # nvmlInit() takes milliseconds: construct the sampler BEFORE the barrier, or rank 0 starts late and
+    # every other rank's first bracket contains the wait
+    clock_sampler = ClockSampler(local_rank, enabled=(rank == 0), threaded=not distributed)
     barrier()
     # Device throughput: the K steps are enqueued back to back (each one bracketed by its own pair of
     # events, with the L2 flush between brackets) and the host synchronises once at the end — the
@@ -344,7 +347,7 @@ def main():
     # samples from the main thread while the GPUs work through the queue — an NVML query takes the
     # driver's global lock for milliseconds, and one late rank makes every other rank wait in the
     # all-gather (measured: +90 us per step averaged over 50 steps of 0.23 ms).
-    with ClockSampler(local_rank, enabled=(rank == 0), threaded=not distributed) as clocks:
+    with clock_sampler as clocks:
         for a, b in ev:
             with torch.cuda.stream(eng.stream):
                 flush.zero_()

@@ -57,7 +57,6 @@ struct MppiHandle {
     bool have_step;            // a step has run (step blocks valid)
     bool const_window;         // single environment: window coefficients go through the constant bank
     int ns;                    // samples per thread of the rollout kernel
-    int roll_threads;          // CTA size of the rollout kernel (64 or 128)
     bool zero_copy;            // kernels read / write the caller's pinned block directly (no memcpy nodes)
     DevIo dio_dev;             // same as dio but never touching the pinned block (device closed loop)
     bool capture_mode;         // caller is capturing: enqueue capturable work only
@@ -101,26 +100,10 @@ int pick_ns(const MppiConfig* c) {
     return ((long long)c->K_local * c->n_env >= 131072) ? 2 : 1;
 }
 
-bool pick_const_window(const MppiConfig* c) {
-    // constant-bank window: single environment and enough work to pay for the extra copy node
-    return (c->n_env == 1) && ((long long)c->K_local * c->T >= (1ll << 21)) && getenv("MPPI_NO_CONST_WINDOW") == nullptr;
-}
-
-// CTA size of the rollout kernel: 128 threads, or 64 when the 128-thread grid would be less than two
-// full waves — twice as many, half as large CTAs spread a partial wave evenly over the SMs
-int pick_roll_threads(const MppiConfig* c, int sm) {
-    if (const char* f = getenv("MPPI_ROLL_THREADS")) { const int v = atoi(f); if (v == 64 || v == 128) return v; }
-    const int ns = pick_ns(c);
-    const int per_sm = pick_const_window(c) ? 4 : (ns == 1 ? 3 : 2);
-    const long long g128 = ((long long)c->K_local + 128 * ns - 1) / (128 * ns) * c->n_env;
-    return (g128 < 2ll * sm * per_sm && c->K_local >= 64 * ns) ? 64 : 128;
-}
-
 void grid_sizes(const MppiConfig* c, int sm, int* g_roll, int* g_soft, int* g_wsum) {
     const int K = c->K_local;
     const int ns = pick_ns(c);
-    const int bt = pick_roll_threads(c, sm);
-    int gr = (K + bt * ns - 1) / (bt * ns);
+    int gr = (K + kRollThreads * ns - 1) / (kRollThreads * ns);
     if (gr > 32768) gr = 32768;
     *g_roll = gr;
     int gs = (K + kSoftThreads * 4 - 1) / (kSoftThreads * 4);
@@ -264,7 +247,7 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
                                           cudaMemcpyDeviceToDevice, s));
         }
 #define MPPI_LAUNCH_ROLL(NOISE, CW, NS_) \
-        mppi_rollout_sm100a<NOISE, CW, NS_><<<grid, h->roll_threads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, ph ? nullptr : eps_dev, S, bmin)
+        mppi_rollout_sm100a<NOISE, CW, NS_><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, ph ? nullptr : eps_dev, S, bmin)
         if (h->const_window) {
             if (h->ns == 2) { if (ph) MPPI_LAUNCH_ROLL(0, true, 2); else MPPI_LAUNCH_ROLL(1, true, 2); }
             else { if (ph) MPPI_LAUNCH_ROLL(0, true, 1); else MPPI_LAUNCH_ROLL(1, true, 1); }
@@ -416,8 +399,9 @@ int mppi_create(const MppiConfig* c, void* workspace, size_t workspace_bytes, vo
     h->dio.opt_traj = (double*)(dout + h->io.off_opt_traj);
     h->roll_smem = (size_t)h->dc.step_block_bytes;
     h->ns = pick_ns(c);
-    h->roll_threads = pick_roll_threads(c, h->sm_count);
-    h->const_window = pick_const_window(c);
+    // constant-bank window: single environment and enough work to pay for the extra copy node
+    h->const_window = (c->n_env == 1) && ((long long)c->K_local * c->T >= (1ll << 21)) &&
+                      getenv("MPPI_NO_CONST_WINDOW") == nullptr;
     h->dio_dev = h->dio;
     h->dio_dev.host_in = nullptr; h->dio_dev.in_delta = 0; h->dio_dev.out_delta = 0;
     h->dio.host_in = nullptr; h->dio.in_delta = 0; h->dio.out_delta = 0;

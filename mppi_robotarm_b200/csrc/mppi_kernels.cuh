@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, 
 // 2. fused rollout kernel: one thread per sample, step block staged in shared memory by TMA,
 //    window coefficients held in registers, only S[k] and one block-min reach HBM.
 // ================================================================================================
-constexpr int kRollThreads = 128;     // maximum; launched with 64 when that balances a partial wave better
+constexpr int kRollThreads = 128;
 
 struct PhiloxNoise {            // eps drawn in-kernel: one Philox call serves two horizon steps
     NoiseCfg nc; uint32_t env, k;
@@ -268,15 +268,14 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
 
     float tmin = INFINITY;
     const int T = cfg.T;
-    // thread handles samples kl0 + s*blockDim.x (s < NS): consecutive lanes -> consecutive samples
-    const int BT = blockDim.x;
-    for (int kl0 = blockIdx.x * (BT * kNS) + tid; kl0 < cfg.K_local; kl0 += gridDim.x * BT * kNS) {
+    // thread handles samples kl0 + s*kRollThreads (s < NS): consecutive lanes -> consecutive samples
+    for (int kl0 = blockIdx.x * (kRollThreads * kNS) + tid; kl0 < cfg.K_local; kl0 += gridDim.x * kRollThreads * kNS) {
         float um[kNS], S[kNS];
         int kl[kNS];
 #pragma unroll
         for (int s = 0; s < kNS; ++s) {
             // a padding sample past the end recomputes the last one (its result is not stored)
-            kl[s] = min(kl0 + s * BT, cfg.K_local - 1);
+            kl[s] = min(kl0 + s * kRollThreads, cfg.K_local - 1);
             um[s] = (cfg.k_offset + kl[s]) < cfg.n_exploit ? 1.0f : 0.0f;
         }
         if (NOISE == 0) {
@@ -295,7 +294,7 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
         }
 #pragma unroll
         for (int s = 0; s < kNS; ++s) {
-            if (kl0 + s * BT < cfg.K_local) {
+            if (kl0 + s * kRollThreads < cfg.K_local) {
                 S_out[(size_t)e * cfg.K_local + kl[s]] = S[s];
                 if (finite_(S[s])) tmin = fminf(tmin, S[s]);
             }
@@ -306,7 +305,8 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
     __syncthreads();
     if (tid == 0) {
         float m = red[0];
-        for (int i = 1; i < BT / 32; ++i) m = fminf(m, red[i]);
+#pragma unroll
+        for (int i = 1; i < kRollThreads / 32; ++i) m = fminf(m, red[i]);
         block_min[(size_t)e * gridDim.x + blockIdx.x] = m;
     }
 }

@@ -152,3 +152,49 @@ def test_nonfinite_samples_get_zero_weight(paths):
     raw = np.einsum("k,ktm->tm", wts, eps.astype(np.float64)[keep])
     assert np.max(np.abs(eng.out_w_eps_raw[0] - raw)) <= TOL_U * 10.0
     ctrl.close()
+
+
+def test_full_size_config4_properties(paths):
+    """BASELINE config 4 at full size (K = 2^20, T = 100, Philox): size-independent properties.
+    (1) the costs of a random subset of samples equal the oracle's on the exported noise of exactly those
+    samples; (2) rho is the minimum cost, the weights are exp(-(S - rho)/lambda) and eta their sum;
+    (3) the raw update equals the weighted noise sum recomputed from the (few) non-zero weights;
+    (4) the same seed and step reproduce the step bit for bit."""
+    import torch
+    from mppi_robotarm_b200 import MppiEngine
+    from mppi_robotarm_b200.arm_params import SYS_PARAMS
+    K, T = 1 << 20, 100
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    kw = cases.run_py_kwargs(ref, K, T, visualize_optimal_traj=False)
+    mk = lambda: MppiEngine(K=K, T=T, delta_t=0.006, param_lambda=100.0, param_gamma=2.0, sigma=np.eye(2) * 20.0,   # noqa: E731
+                            stage_cost_weight=[0.5, 0.5, 5, 5], terminal_cost_weight=[5, 5, 50, 50],
+                            arm_params=SYS_PARAMS(), ref_path=ref, seed=4242, optimal_traj=False)
+    eng = mk()
+    u = np.tile([10.0, -2.0], (T, 1))
+    eps = eng.philox_noise(step=0)[0]                                  # [K, T, 2] on the device (0.84 GB)
+    eng.step(cases.X0, u, 0, None)
+    S, w = (t[0].clone() for t in eng.last_costs())
+    # (1) oracle on a random subset
+    idx = torch.randperm(K, device=S.device)[:3000].sort().values
+    c = mo.OracleMPPI(**kw)
+    S64 = mo.rollout_costs(c, np.array(cases.X0), eps[idx].cpu().numpy().astype(np.float64), prev_idx=int(eng.out_new_idx[0]))
+    assert H.rel_err(S[idx].cpu().numpy().astype(np.float64), S64) <= TOL_S
+    # (2) weights
+    rho = float(S[torch.isfinite(S)].min())
+    assert eng.out_rho[0] == rho
+    wd = torch.exp(-(S.double() - rho) / 100.0)
+    np.testing.assert_allclose(w.double().cpu().numpy(), wd.cpu().numpy(), rtol=3e-5, atol=1e-30)
+    np.testing.assert_allclose(eng.out_eta[0], float(w.double().sum()), rtol=1e-6)
+    # (3) weighted sum from the non-zero weights
+    nz = torch.nonzero(w).ravel()
+    assert 1 <= nz.numel() < K // 100                                  # winner-take-all regime at lambda = 100
+    raw = (w[nz].double()[:, None, None] * eps[nz].double()).sum(0) / float(w.double().sum())
+    np.testing.assert_allclose(eng.out_w_eps_raw[0], raw.cpu().numpy(), rtol=0, atol=2e-6 * float(raw.abs().max()) + 1e-12)
+    u_new = eng.out_u_new[0].copy()
+    eng.close()
+    # (4) reproducible
+    eng2 = mk()
+    eng2.step(cases.X0, u, 0, None)
+    np.testing.assert_array_equal(eng2.out_u_new[0], u_new)
+    assert bool((eng2.last_costs()[0][0] == S).all())
+    eng2.close()

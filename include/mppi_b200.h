@@ -49,7 +49,9 @@ enum {
 
 enum {
     MPPI_FLAG_OPTIMAL_TRAJ = 1, /* control.py:129-134: roll the updated sequence out             */
-    MPPI_FLAG_DEVICE_GRAPH = 2  /* replay the step as one CUDA graph (Philox mode only)          */
+    MPPI_FLAG_DEVICE_GRAPH = 2, /* replay the step as one CUDA graph (Philox mode only)          */
+    MPPI_FLAG_SMOOTH_AVERAGE = 4, /* smooth the update with control.py:329-344 instead of the median filter (needs T >= 10) */
+    MPPI_FLAG_SMOOTH_NONE = 8   /* no smoothing of the weighted noise sum                        */
 };
 
 /* Hyper-parameters: control.py:21-65 + sys_params.py:3-10, fixed for the life of a handle. */
@@ -160,6 +162,11 @@ int mppi_last_costs(MppiHandle* h, const float** S_dev, const float** w_dev);
  * state / sequence / window of the last step.  traj_dev: float32 [n_env][K_local][T][4]. */
 int mppi_sampled_trajectories(MppiHandle* h, int32_t noise_mode, const float* eps_dev,
                               float* traj_dev, void* stream);
+/* The same for a chosen subset of samples (e.g. the n lowest-cost ones, which is the order in which
+ * control.py:138-145 walks them): subset_dev int32 [n_env][n_subset] local sample indices,
+ * traj_dev float32 [n_env][n_subset][T][4]. */
+int mppi_sampled_trajectories_subset(MppiHandle* h, int32_t noise_mode, const float* eps_dev,
+                                     const int32_t* subset_dev, int32_t n_subset, float* traj_dev, void* stream);
 /* The Philox noise tensor the kernels draw for control step `step`: float32 [n_env][K_local][T][2]. */
 int mppi_philox_noise(MppiHandle* h, uint64_t step, float* eps_dev, void* stream);
 /* Number of kernels launched by this handle so far (graph replays count their kernel nodes). */

@@ -17,6 +17,8 @@ NOISE_PHILOX = 0
 NOISE_INJECTED = 1
 FLAG_OPTIMAL_TRAJ = 1
 FLAG_DEVICE_GRAPH = 2
+FLAG_SMOOTH_AVERAGE = 4
+FLAG_SMOOTH_NONE = 8
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_WORKSPACE = 0, -1, -2, -3, -4
 
@@ -61,6 +63,8 @@ SYMBOLS = {
     "mppi_replay_end": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mppi_last_costs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "mppi_sampled_trajectories": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mppi_sampled_trajectories_subset": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                                   C.c_void_p, C.c_void_p]),
     "mppi_philox_noise": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "mppi_launch_count": (C.c_uint64, [C.c_void_p]),
     "mppi_set_timing": (C.c_int, [C.c_void_p, C.c_int32]),

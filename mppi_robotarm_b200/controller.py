@@ -49,6 +49,8 @@ class MPPIControllerForPathTracking:
             use_graph: bool = True,     # replay the step as a CUDA graph
             distributed: bool = False,  # shard the K samples over torch.distributed ranks
             process_group=None,
+            sampled_traj_top_n=None,    # with visualze_sampled_trajs: return only the n best, best first
+            smoother: str = "median",  # "median" (control.py:122), "average" (control.py:329-344) or "none"
     ) -> None:
         # same attributes as control.py:37-65
         self.dim_x = 4
@@ -80,6 +82,8 @@ class MPPIControllerForPathTracking:
         self._use_graph = use_graph
         self._distributed = distributed
         self._group = process_group
+        self.sampled_traj_top_n = sampled_traj_top_n
+        self.smoother = smoother
         self._engine_obj = None
         self.last = {}               # intermediates of the last step (rho, eta, raw / filtered update)
 
@@ -99,7 +103,7 @@ class MPPIControllerForPathTracking:
                 ref_path=self.ref_path, param_exploration=self.param_exploration,
                 cost_l1=self.l1, cost_l2=self.l2, n_env=1, seed=self.seed, device=self._device,
                 optimal_traj=bool(self.visualize_optimal_traj), use_graph=self._use_graph,
-                shard=self._shard(), process_group=self._group)
+                smoother=self.smoother, shard=self._shard(), process_group=self._group)
         return self._engine_obj
 
     def close(self):
@@ -178,6 +182,12 @@ class MPPIControllerForPathTracking:
         return out
 
     def _gather_sampled(self, eng):
+        if self.sampled_traj_top_n and eng.shard.world == 1:
+            # opt-in deviation from the reference's (K, T, 4): only the n lowest-cost samples, ordered
+            # like np.argsort(S) (control.py:138); their sample indices are kept in self.last
+            idx, traj = eng.best_sampled_trajectories(self.sampled_traj_top_n)
+            self.last["sampled_idx"] = idx[0]
+            return traj[0].cpu().numpy().astype(np.float64)
         local = eng.sampled_trajectories()[0].cpu().numpy().astype(np.float64)
         if eng.shard.world == 1:
             return local

@@ -621,22 +621,29 @@ int mppi_last_costs(MppiHandle* h, const float** S_dev, const float** w_dev) {
     return MPPI_OK;
 }
 
-int mppi_sampled_trajectories(MppiHandle* h, int32_t noise_mode, const float* eps_dev, float* traj_dev, void* stream) {
+int mppi_sampled_trajectories_subset(MppiHandle* h, int32_t noise_mode, const float* eps_dev, const int32_t* subset_dev,
+                                     int32_t n_subset, float* traj_dev, void* stream) {
     if (!h) return MPPI_ERR_INVALID;
     if (!h->have_step) return fail(h, MPPI_ERR_INVALID, "%s", "no step has run yet");
     if (!traj_dev) return fail(h, MPPI_ERR_INVALID, "%s", "null traj_dev");
     if (noise_mode == MPPI_NOISE_INJECTED && !eps_dev) return fail(h, MPPI_ERR_INVALID, "%s", "injected noise mode needs eps_dev");
+    if (subset_dev && n_subset < 1) return fail(h, MPPI_ERR_INVALID, "%s", "empty subset");
     cudaStream_t s = (cudaStream_t)stream;
     const uint64_t* step_ctr = (const uint64_t*)(h->dev + h->ws.off_in + h->io.off_step);
     const char* step_blocks = h->dev + h->ws.off_step_blocks;
-    dim3 grid((h->dc.K_local + 127) / 128, h->dc.n_env);
+    const int n_rows = subset_dev ? n_subset : h->dc.K_local;
+    dim3 grid((n_rows + 127) / 128, h->dc.n_env);
     if (noise_mode == MPPI_NOISE_PHILOX)
-        mppi_sampled_traj_sm100a<0><<<grid, 128, 0, s>>>(h->dc, step_ctr, step_blocks, nullptr, traj_dev);
+        mppi_sampled_traj_sm100a<0><<<grid, 128, 0, s>>>(h->dc, step_ctr, step_blocks, nullptr, subset_dev, n_rows, traj_dev);
     else
-        mppi_sampled_traj_sm100a<1><<<grid, 128, 0, s>>>(h->dc, step_ctr, step_blocks, eps_dev, traj_dev);
+        mppi_sampled_traj_sm100a<1><<<grid, 128, 0, s>>>(h->dc, step_ctr, step_blocks, eps_dev, subset_dev, n_rows, traj_dev);
     CU(h, cudaGetLastError());
     h->launches += 1;
     return MPPI_OK;
+}
+
+int mppi_sampled_trajectories(MppiHandle* h, int32_t noise_mode, const float* eps_dev, float* traj_dev, void* stream) {
+    return mppi_sampled_trajectories_subset(h, noise_mode, eps_dev, nullptr, 0, traj_dev, stream);
 }
 
 int mppi_philox_noise(MppiHandle* h, uint64_t step, float* eps_dev, void* stream) {

@@ -707,16 +707,32 @@ mppi_finalize_sm100a(DevCfg cfg, DevIo io, const double* __restrict__ gathered, 
     // window offsets -5..+4, output = element of rank 5 of the sorted window
     for (int c = tid; c < 2 * T; c += blockDim.x) {
         const int t = c >> 1, m = c & 1;
-        double win[kFilter];
+        double med;
+        if (cfg.flags & 8) {                                  // MPPI_FLAG_SMOOTH_NONE
+            med = raw[c];
+        } else if (cfg.flags & 4) {                           // MPPI_FLAG_SMOOTH_AVERAGE, control.py:329-344
+            // np.convolve(x, ones/10, 'same') = sum of x/10 over [t-5, t+4] clipped to the array, then the
+            // first and last ceil(10/2)-1 rows (and row 0) rescaled by 10/(number of terms)
+            const int lo = max(0, t - kFilter / 2), hi = min(T - 1, t + (kFilter - 1) / 2);
+            double acc = 0.0;
+            for (int k = lo; k <= hi; ++k) acc += raw[2 * k + m] * (1.0 / kFilter);
+            const int n_conv = (kFilter + 1) / 2;
+            if (t == 0) acc *= (double)kFilter / n_conv;
+            else if (t < n_conv) acc *= (double)kFilter / (t + n_conv);
+            if (t > T - n_conv && t != 0) acc *= (double)kFilter / ((T - t) + n_conv - (kFilter % 2));
+            med = acc;
+        } else {
+            double win[kFilter];
 #pragma unroll
-        for (int o = 0; o < kFilter; ++o) win[o] = raw[2 * reflect_idx(t + o - kFilter / 2, T) + m];
-        double med = win[0];
+            for (int o = 0; o < kFilter; ++o) win[o] = raw[2 * reflect_idx(t + o - kFilter / 2, T) + m];
+            med = win[0];
 #pragma unroll
-        for (int a = 0; a < kFilter; ++a) {
-            int rank = 0;
+            for (int a = 0; a < kFilter; ++a) {
+                int rank = 0;
 #pragma unroll
-            for (int b = 0; b < kFilter; ++b) rank += (win[b] < win[a]) || (win[b] == win[a] && b < a);
-            if (rank == kFilter / 2) med = win[a];
+                for (int b = 0; b < kFilter; ++b) rank += (win[b] < win[a]) || (win[b] == win[a] && b < a);
+                if (rank == kFilter / 2) med = win[a];
+            }
         }
         const double u = io.u_prev[(size_t)e * 2 * T + c] + med;        // control.py:126
         unew[c] = u;
@@ -750,17 +766,21 @@ mppi_finalize_sm100a(DevCfg cfg, DevIo io, const double* __restrict__ gathered, 
 template <int NOISE>
 __global__ void __launch_bounds__(128)
 mppi_sampled_traj_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const char* __restrict__ step_blocks,
-                         const float* __restrict__ eps, float* __restrict__ traj) {
+                         const float* __restrict__ eps, const int32_t* __restrict__ subset, int n_rows,
+                         float* __restrict__ traj) {
+    // row i of the output is sample i (subset == nullptr, n_rows = K_local) or sample subset[e][i]
     const int e = blockIdx.y;
-    const int kl = blockIdx.x * blockDim.x + threadIdx.x;
-    if (kl >= cfg.K_local) return;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const int kl = subset ? subset[(size_t)e * n_rows + row] : row;
+    if (kl < 0 || kl >= cfg.K_local) return;
     const StepBlockView sb = view_step_block((void*)(step_blocks + (size_t)e * cfg.step_block_bytes));
     const StepHeader hd = *sb.hd;
     const int kg = cfg.k_offset + kl, T = cfg.T;
     const float um = kg < cfg.n_exploit ? 1.0f : 0.0f;
     NoiseCfg nc = cfg.noise; nc.step = (uint32_t)(*step_ctr);
     ArmState st; arm_init(st, hd.q1, hd.q2, hd.d1, hd.d2);
-    float4* out = (float4*)traj + ((size_t)e * cfg.K_local + kl) * T;
+    float4* out = (float4*)traj + ((size_t)e * n_rows + row) * T;
     for (int t = 0; t < T; ++t) {
         const int tc = t == 0 ? T - 1 : t - 1;
         float n1, n2;

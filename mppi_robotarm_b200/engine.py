@@ -46,7 +46,7 @@ def exploit_count(K: int, exploration: float) -> int:
 class MppiEngine:
     def __init__(self, *, K, T, delta_t, param_lambda, param_gamma, sigma, stage_cost_weight,
                  terminal_cost_weight, arm_params, ref_path, param_exploration=0.0, cost_l1=1.0, cost_l2=1.0,
-                 n_env=1, seed=0, device=None, optimal_traj=True, use_graph=True,
+                 n_env=1, seed=0, device=None, optimal_traj=True, use_graph=True, smoother="median",
                  shard: ShardSpec | None = None, process_group=None, max_ref_rows=None):
         import torch
         self.torch = torch
@@ -75,7 +75,12 @@ class MppiEngine:
         cfg.K_total, cfg.K_local, cfg.k_offset = self.K, K_local, k_offset
         cfg.T = self.T
         cfg.n_exploit = exploit_count(self.K, param_exploration)
-        cfg.flags = (_cabi.FLAG_OPTIMAL_TRAJ if optimal_traj else 0) | (_cabi.FLAG_DEVICE_GRAPH if use_graph else 0)
+        if smoother not in ("median", "average", "none"):
+            raise ValueError("smoother must be 'median', 'average' or 'none'")
+        if smoother == "average" and self.T < 10:
+            raise ValueError("the moving-average smoother needs horizon_step_T >= 10 (np.convolve 'same', control.py:338)")
+        cfg.flags = ((_cabi.FLAG_OPTIMAL_TRAJ if optimal_traj else 0) | (_cabi.FLAG_DEVICE_GRAPH if use_graph else 0)
+                     | {"median": 0, "average": _cabi.FLAG_SMOOTH_AVERAGE, "none": _cabi.FLAG_SMOOTH_NONE}[smoother])
         cfg.max_ref_rows = int(max_ref_rows or ref.shape[0])
         cfg.delta_t, cfg.param_lambda, cfg.param_gamma = float(delta_t), float(param_lambda), float(param_gamma)
         cfg.sigma_chol[:] = chol.reshape(-1).tolist()
@@ -297,6 +302,25 @@ class MppiEngine:
                     self.handle, "mppi_sampled_trajectories")
         self.stream.synchronize()
         return out
+
+    def best_sampled_trajectories(self, n):
+        """Trajectories of the n lowest-cost samples of the last step, best first (the order of
+        np.argsort(S) in control.py:138): (indices int64 [n_env, n], traj float32 tensor [n_env, n, T, 4]).
+        The ranking itself is host logic like in the reference (a partial sort of the K costs)."""
+        torch = self.torch
+        n = int(min(n, self.K_local))
+        self.stream.synchronize()
+        S = self.last_costs()[0].cpu().numpy()
+        part = np.argpartition(S, n - 1, axis=1)[:, :n] if n < self.K_local else np.tile(np.arange(n), (self.n_env, 1))
+        order = np.take_along_axis(part, np.argsort(np.take_along_axis(S, part, axis=1), axis=1, kind="stable"), axis=1)
+        idx = torch.from_numpy(order.astype(np.int32)).to(self.device)
+        out = torch.empty((self.n_env, n, self.T, 4), dtype=torch.float32, device=self.device)
+        torch.cuda.current_stream(self.device).synchronize()
+        _cabi.check(self.lib.mppi_sampled_trajectories_subset(self.handle, self.last_mode, self.last_eps_ptr,
+                                                              idx.data_ptr(), n, out.data_ptr(), self.stream.cuda_stream),
+                    self.handle, "mppi_sampled_trajectories_subset")
+        self.stream.synchronize()
+        return order.astype(np.int64), out
 
     def philox_noise(self, step=None):
         """The noise tensor the kernels draw at control step ``step``: [n_env, K_local, T, 2] float32."""

@@ -55,6 +55,7 @@ class OracleMPPI:
     terminal_cost_weight: np.ndarray
     visualize_optimal_traj: bool = True
     visualze_sampled_trajs: bool = False
+    smoother: str = "median"          # "median" = control.py:122; "average" = control.py:329-344; "none"
     arm: dict = field(default_factory=default_arm_params)
     cost_l1: float = 1.0      # control.py:55
     cost_l2: float = 1.0      # control.py:56
@@ -160,6 +161,27 @@ def filter_columns(xx: np.ndarray, size: int = FILTER_WINDOW) -> np.ndarray:
     return np.stack([median_filter_reflect(xx[:, d], size) for d in range(xx.shape[1])], axis=1)
 
 
+def moving_average_columns(xx: np.ndarray, size: int = FILTER_WINDOW) -> np.ndarray:
+    """control.py:329-344 (`_moving_average_filter`, unused by the reference's step but kept as an
+    option): np.convolve(x, ones/size, 'same') with the edge rows rescaled to proper means, i.e. the mean
+    of x over [n - size//2, n + (size-1)//2] clipped to the array.  Needs len(x) >= size."""
+    T = xx.shape[0]
+    back, fwd = size // 2, (size - 1) // 2
+    out = np.zeros_like(xx)
+    n_conv = -(-size // 2)
+    for n in range(T):
+        lo, hi = max(0, n - back), min(T - 1, n + fwd)
+        acc = np.zeros(xx.shape[1])
+        for k in range(lo, hi + 1):
+            acc = acc + xx[k] * (1.0 / size)
+        out[n] = acc
+    out[0] *= size / n_conv
+    for i in range(1, n_conv):
+        out[i] *= size / (i + n_conv)
+        out[-i] *= size / (i + n_conv - (size % 2))
+    return out
+
+
 def exploit_count(K: int, exploration: float) -> int:
     """Number of leading samples with ``k < (1-exploration)*K`` (control.py:98)."""
     thr = (1.0 - exploration) * K
@@ -204,7 +226,7 @@ def _visual_rollouts(c, x0, u, v):
 def _finish(c, x0, eps, v, S, out):
     w, rho, eta = softmin_weights(S, c.param_lambda)
     raw = np.einsum("k,ktm->tm", w, eps) if eps.shape[0] > 512 else _weighted_sum_loops(w, eps)
-    filt = filter_columns(raw)
+    filt = {"median": filter_columns, "average": moving_average_columns, "none": lambda a: a.copy()}[c.smoother](raw)
     u = c.u_prev                                   # alias (Q1)
     u += filt                                      # control.py:126
     u_new = u.copy()

@@ -55,6 +55,9 @@ def single_cases(paths: dict) -> list:
         dict(name="line_path", file="xydq.txt", K=64, T=30, seed=18, x0=[0.05, -0.1, 0.0, 0.0]),
         dict(name="no_opt_traj", file="xydq_circle.txt", K=32, T=10, seed=19, x0=X0,
              ctor=dict(visualize_optimal_traj=False)),
+        # the reference's other smoother (control.py:329-344) swapped in for the median filter
+        dict(name="avg_filter", file="xydq_circle.txt", K=96, T=30, seed=21, x0=X0, steps=2, smoother="average",
+             ctor=dict(param_lambda=4.0e4)),
         dict(name="mid_path", file="xydq_circle.txt", K=128, T=30, seed=20, prev_idx=700,
              x0=[0.9, 0.6, 0.3, -0.2],
              u_prev=(np.array([[3.0, 1.0]]) * np.linspace(1, 2, 30)[:, None]).tolist()),

@@ -35,6 +35,17 @@ KEYS = ["S", "w", "w_eps_raw", "w_eps_filt", "u_new", "u0", "optimal_traj", "u_p
 def run_case(case):
     kw = cases.ctor_kwargs(case, PATHS)
     probe = rh.ReferenceProbe(**kw)
+    if case.get("smoother") == "average":
+        # the step calls self._moving_median_filter(xx=..., window_size=10) (control.py:122): route that call
+        # to the reference's own _moving_average_filter, keeping the probe's capture of raw / filtered
+        ref_avg = probe.ctrl._moving_average_filter
+
+        def avg(xx, window_size):
+            probe.last["w_eps_raw"] = np.array(xx, copy=True)
+            out = ref_avg(xx, window_size)
+            probe.last["w_eps_filt"] = np.array(out, copy=True)
+            return out
+        probe.ctrl._moving_median_filter = avg
     if "prev_idx" in case:
         probe.ctrl.prev_waypoints_idx = case["prev_idx"]
     if "u_prev" in case:

@@ -12,6 +12,8 @@ def make_controller(case, paths, **extra):
     """Our drop-in controller configured like a golden case, with the reference's injection seam."""
     from control import MPPIControllerForPathTracking
     kw = cases.ctor_kwargs(case, paths)
+    if "smoother" in case:
+        extra = dict(extra, smoother=case["smoother"])
     ctrl = MPPIControllerForPathTracking(**kw, noise="numpy", verbose=False, **extra)
     if "prev_idx" in case:
         ctrl.prev_waypoints_idx = case["prev_idx"]

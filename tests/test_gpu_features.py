@@ -402,3 +402,24 @@ def test_device_closed_loop_stops_at_the_end_of_the_path(paths, capsys):
     assert c.prev_waypoints_idx >= ref.shape[0] - 1
     assert np.all(np.diff(c.last_loop["waypoint_idx"]) >= 0)
     c.close()
+
+
+def test_top_n_sampled_trajectories_are_the_best_rows_of_the_full_set(paths):
+    """sampled_traj_top_n: the n lowest-cost samples in np.argsort(S) order, identical to the
+    corresponding rows of the full (K, T, 4) output of control.py:137-145."""
+    case = dict(name="topn", file="xydq_circle.txt", K=300, T=16)
+    full, kw = H.make_controller(case, paths, visualze_sampled_trajs=True)
+    top, _ = H.make_controller(case, paths, visualze_sampled_trajs=True, sampled_traj_top_n=7)
+    eps = mo.injected_noise(3, 300, 16, kw["sigma"])
+    for c in (full, top):
+        H.inject(c, eps)
+    _, _, _, all_traj = H.quiet_step(full, cases.X0)
+    _, _, _, best = H.quiet_step(top, cases.X0)
+    S = full._engine().last_costs()[0][0].cpu().numpy()
+    order = np.argsort(S, kind="stable")[:7]
+    assert best.shape == (7, 16, 4)
+    np.testing.assert_array_equal(top.last["sampled_idx"], order)
+    np.testing.assert_array_equal(best, all_traj[order])
+    o = mo.step_vectorized(mo.OracleMPPI(**{**kw, "visualze_sampled_trajs": True}), cases.X0, eps.astype(np.float64))
+    np.testing.assert_allclose(best, o["sampled_traj"][np.argsort(o["S"])[:7]], rtol=0, atol=2e-5)
+    full.close(); top.close()

@@ -85,6 +85,7 @@ class MPPIControllerForPathTracking:
         self.sampled_traj_top_n = sampled_traj_top_n
         self.smoother = smoother
         self._engine_obj = None
+        self._engine_ref_path = None
         self.last = {}               # intermediates of the last step (rho, eta, raw / filtered update)
 
     # ---- engine life cycle ---------------------------------------------------------------------
@@ -104,6 +105,11 @@ class MPPIControllerForPathTracking:
                 cost_l1=self.l1, cost_l2=self.l2, n_env=1, seed=self.seed, device=self._device,
                 optimal_traj=bool(self.visualize_optimal_traj), use_graph=self._use_graph,
                 smoother=self.smoother, shard=self._shard(), process_group=self._group)
+            self._engine_ref_path = self.ref_path
+        elif self.ref_path is not self._engine_ref_path:
+            # the reference reads self.ref_path on every call (control.py:208); follow a re-assignment
+            self._engine_obj.set_ref_path(self.ref_path)
+            self._engine_ref_path = self.ref_path
         return self._engine_obj
 
     def close(self):

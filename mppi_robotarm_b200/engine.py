@@ -153,6 +153,10 @@ class MppiEngine:
 
     def set_ref_path(self, ref):
         ref = np.ascontiguousarray(np.asarray(ref, dtype=np.float64)[:, 0:4])
+        if ref.shape[0] > self.cfg.max_ref_rows:
+            raise ValueError(f"reference path has {ref.shape[0]} rows; this engine was sized for {self.cfg.max_ref_rows} "
+                             "(pass max_ref_rows= at construction)")
+        self.torch.cuda.synchronize(self.device)
         self.n_ref_rows = ref.shape[0]
         _cabi.check(self.lib.mppi_set_ref_path(self.handle, ref.ctypes.data, ref.shape[0]), self.handle,
                     "mppi_set_ref_path")

@@ -423,3 +423,23 @@ def test_top_n_sampled_trajectories_are_the_best_rows_of_the_full_set(paths):
     o = mo.step_vectorized(mo.OracleMPPI(**{**kw, "visualze_sampled_trajs": True}), cases.X0, eps.astype(np.float64))
     np.testing.assert_allclose(best, o["sampled_traj"][np.argsort(o["S"])[:7]], rtol=0, atol=2e-5)
     full.close(); top.close()
+
+
+def test_reassigning_ref_path_is_followed(paths):
+    """The reference reads self.ref_path on every call; a re-assigned path (same length) must be used."""
+    from control import MPPIControllerForPathTracking
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    kw = cases.run_py_kwargs(ref, 256, 16)
+    eps = mo.injected_noise(8, 256, 16, kw["sigma"])
+    c = MPPIControllerForPathTracking(**kw, noise="numpy", verbose=False)
+    H.inject(c, eps)
+    H.quiet_step(c, cases.X0)
+    shifted = ref.copy()
+    shifted[:, 0] += 0.05
+    c.ref_path = shifted
+    c.u_prev[...] = [10.0, -2.0]
+    c.prev_waypoints_idx = 0
+    H.quiet_step(c, cases.X0)
+    o = mo.step_vectorized(mo.OracleMPPI(**{**kw, "ref_path": shifted}), cases.X0, eps.astype(np.float64))
+    assert H.rel_err(c._engine().out_u_new[0], o["u_new"]) <= TOL_U
+    c.close()

@@ -58,6 +58,10 @@ SYMBOLS = {
     "mppi_step_combine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "mppi_wait": (C.c_int, [C.c_void_p]),
     "mppi_closed_loop": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mppi_exchange_bytes": (C.c_size_t, [C.POINTER(MppiConfig), C.c_int32]),
+    "mppi_set_peer_exchange": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "mppi_step_sharded": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mppi_exchange_status": (C.c_int, [C.c_void_p]),
     "mppi_set_capture_mode": (C.c_int, [C.c_void_p, C.c_int32]),
     "mppi_replay_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mppi_replay_end": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -49,6 +49,7 @@ class MPPIControllerForPathTracking:
             use_graph: bool = True,     # replay the step as a CUDA graph
             distributed: bool = False,  # shard the K samples over torch.distributed ranks
             process_group=None,
+            exchange: str = "nccl",     # sharded runs: "nccl" all-gather or "p2p" (fused peer-memory exchange)
             sampled_traj_top_n=None,    # with visualze_sampled_trajs: return only the n best, best first
             smoother: str = "median",  # "median" (control.py:122), "average" (control.py:329-344) or "none"
     ) -> None:
@@ -82,6 +83,7 @@ class MPPIControllerForPathTracking:
         self._use_graph = use_graph
         self._distributed = distributed
         self._group = process_group
+        self._exchange = exchange
         self.sampled_traj_top_n = sampled_traj_top_n
         self.smoother = smoother
         self._engine_obj = None
@@ -104,7 +106,8 @@ class MPPIControllerForPathTracking:
                 ref_path=self.ref_path, param_exploration=self.param_exploration,
                 cost_l1=self.l1, cost_l2=self.l2, n_env=1, seed=self.seed, device=self._device,
                 optimal_traj=bool(self.visualize_optimal_traj), use_graph=self._use_graph,
-                smoother=self.smoother, shard=self._shard(), process_group=self._group)
+                smoother=self.smoother, shard=self._shard(), process_group=self._group,
+                exchange=self._exchange)
             self._engine_ref_path = self.ref_path
         elif self.ref_path is not self._engine_ref_path:
             # the reference reads self.ref_path on every call (control.py:208); follow a re-assignment

@@ -25,7 +25,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct Workspace {
     size_t bytes;
     size_t off_ref, off_step_blocks, off_in, off_out, off_S, off_w, off_block_min, off_eta_part,
-        off_rho, off_v_part, off_partial, off_loop, off_eta_fused, off_tickets;
+        off_rho, off_v_part, off_partial, off_loop, off_eta_fused, off_tickets, off_seq;
 };
 
 }  // namespace
@@ -59,6 +59,10 @@ struct MppiHandle {
     int ns;                    // samples per thread of the rollout kernel
     bool zero_copy;            // kernels read / write the caller's pinned block directly (no memcpy nodes)
     DevIo dio_dev;             // same as dio but never touching the pinned block (device closed loop)
+    PeerExchange px;           // peer-memory exchange (world == 0: not configured)
+    cudaGraphExec_t sharded_exec;
+    void* sharded_stream;
+    uint64_t sharded_kernels;
     bool capture_mode;         // caller is capturing: enqueue capturable work only
     uint64_t capture_kernels;  // kernels enqueued while capture mode was on (= per replay)
     cudaEvent_t const_ev;      // recorded after this handle's last reader of the constant-bank window
@@ -141,6 +145,7 @@ void carve(const MppiConfig* c, int sm, Workspace* w) {
     w->off_loop = take(sizeof(LoopParams));
     w->off_eta_fused = take(E * g_wsum * sizeof(double));
     w->off_tickets = take(E * sizeof(unsigned int));
+    w->off_seq = take(2 * sizeof(unsigned long long));       // [0] step sequence number, [1] exchange status
     w->bytes = off;
 }
 
@@ -211,7 +216,7 @@ void const_forget(MppiHandle* h) {
 
 // enqueue everything up to this shard's partial triple
 int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* partial_dev, cudaStream_t s,
-                  bool timed, bool capturing = false, bool copy_inputs = true) {
+                  bool timed, bool capturing = false, bool copy_inputs = true, bool use_px = false) {
     const DevCfg& dc = h->dc;
     char* ws = h->dev;
     if (noise_mode != MPPI_NOISE_PHILOX && noise_mode != MPPI_NOISE_INJECTED)
@@ -235,7 +240,8 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
     if (copy_inputs && !h->zero_copy)
         CU(h, cudaMemcpyAsync(ws + h->ws.off_in, h->host, h->in_bytes, cudaMemcpyHostToDevice, s));
     if (timed) CU(h, cudaEventRecord(h->tev[0], s));
-    mppi_prepare_sm100a<<<dc.n_env, 32, 0, s>>>(dc, dio, ref, step_blocks, zc);
+    mppi_prepare_sm100a<<<dc.n_env, 32, 0, s>>>(dc, dio, ref, step_blocks, zc,
+                                                (unsigned long long*)(ws + h->ws.off_seq));
     if (timed) CU(h, cudaEventRecord(h->tev[1], s));
     {
         dim3 grid(dc.g_roll, dc.n_env);
@@ -266,7 +272,7 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
         const size_t sm = (size_t)(kWsumThreads / 32) * ((dc.T + 1) / 2) * sizeof(float4);
         mppi_softmin_wsum_philox_sm100a<<<dim3(g, dc.n_env), kWsumThreads, sm, s>>>(
             dc, step_ctr, S, bmin, w, (double*)(ws + h->ws.off_eta_fused), v_part,
-            (unsigned int*)(ws + h->ws.off_tickets), rho, partial_dev);
+            (unsigned int*)(ws + h->ws.off_tickets), rho, partial_dev, use_px ? h->px : PeerExchange{});
         if (timed) { CU(h, cudaEventRecord(h->tev[3], s)); CU(h, cudaEventRecord(h->tev[4], s)); }
         h->launches += 3;
     } else {
@@ -278,7 +284,8 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
         else
             mppi_wsum_injected_sm100a<float2><<<grid, kWsumThreads, kWsumThreads * sizeof(float2), s>>>(dc, w, eps_dev, v_part);
         if (timed) CU(h, cudaEventRecord(h->tev[4], s));
-        mppi_reduce_sm100a<<<dc.n_env, kReduceThreads, 0, s>>>(dc, dc.g_wsum, rho, eta_part, v_part, partial_dev);
+        mppi_reduce_sm100a<<<dc.n_env, kReduceThreads, 0, s>>>(dc, dc.g_wsum, rho, eta_part, v_part, partial_dev,
+                                                               use_px ? h->px : PeerExchange{});
         h->launches += 5;
     }
     if (timed) CU(h, cudaEventRecord(h->tev[5], s));
@@ -288,9 +295,11 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
 }
 
 int enqueue_combine(MppiHandle* h, const double* gathered_dev, int world, cudaStream_t s, bool timed,
-                    bool record_done = true, bool copy_outputs = true) {
+                    bool record_done = true, bool copy_outputs = true, bool use_px = false) {
     if (world < 1 || world > 64) return fail(h, MPPI_ERR_INVALID, "%s", "world must be in [1, 64]");
-    mppi_finalize_sm100a<<<h->dc.n_env, 256, 0, s>>>(h->dc, copy_outputs ? h->dio : h->dio_dev, gathered_dev, world);
+    mppi_finalize_sm100a<<<h->dc.n_env, 256, 0, s>>>(h->dc, copy_outputs ? h->dio : h->dio_dev, gathered_dev, world,
+                                                     use_px ? h->px : PeerExchange{},
+                                                     (int*)(h->dev + h->ws.off_seq + sizeof(unsigned long long)));
     if (timed) CU(h, cudaEventRecord(h->tev[6], s));
     CU(h, cudaGetLastError());
     if (copy_outputs && !h->zero_copy) CU(h, cudaMemcpyAsync(h->host + h->out_off, h->dev + h->ws.off_out, h->out_bytes, cudaMemcpyDeviceToHost, s));
@@ -418,7 +427,10 @@ int mppi_create(const MppiConfig* c, void* workspace, size_t workspace_bytes, vo
             cudaGetLastError();
         }
     }
-    if (cudaMemset(h->dev + h->ws.off_tickets, 0, sizeof(unsigned int) * c->n_env) != cudaSuccess) {
+    h->px.world = 0;
+    h->px.seq = (const unsigned long long*)(h->dev + h->ws.off_seq);
+    if (cudaMemset(h->dev + h->ws.off_seq, 0, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(h->dev + h->ws.off_tickets, 0, sizeof(unsigned int) * c->n_env) != cudaSuccess) {
         snprintf(g_create_error, sizeof(g_create_error), "cudaMemset(tickets) failed");
         delete h;
         return MPPI_ERR_CUDA;
@@ -441,6 +453,7 @@ void mppi_destroy(MppiHandle* h) {
     const_forget(h);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->tick_exec) cudaGraphExecDestroy(h->tick_exec);
+    if (h->sharded_exec) cudaGraphExecDestroy(h->sharded_exec);
     if (h->done) cudaEventDestroy(h->done);
     if (h->const_ev) cudaEventDestroy(h->const_ev);
     for (int i = 0; i <= kNumTimers; ++i)
@@ -544,6 +557,72 @@ int mppi_step(MppiHandle* h, int32_t noise_mode, const float* eps_dev, void* str
     rc = enqueue_combine(h, partial, 1, s, h->timing);
     h->timing_pending = h->timing && rc == MPPI_OK;
     return rc;
+}
+
+size_t mppi_exchange_bytes(const MppiConfig* c, int32_t world) {
+    const char* why = nullptr;
+    if (!valid_cfg(c, &why) || world < 1 || world > kMaxPeers) { fail(nullptr, MPPI_ERR_INVALID, "%s", why ? why : "world must be 1..16"); return 0; }
+    const size_t slot = (size_t)world * c->n_env * (2 + 2 * c->T) * sizeof(double);
+    return align_up(2 * slot, 256) + align_up(2 * (size_t)world * c->n_env * sizeof(unsigned long long), 256);
+}
+
+int mppi_set_peer_exchange(MppiHandle* h, int32_t rank, int32_t world, void* const* peer_bufs) {
+    if (!h) return MPPI_ERR_INVALID;
+    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || !peer_bufs)
+        return fail(h, MPPI_ERR_INVALID, "%s", "peer exchange needs 1 <= world <= 16, 0 <= rank < world and the peer buffer table");
+    for (int r = 0; r < world; ++r)
+        if (!peer_bufs[r] || ((uintptr_t)peer_bufs[r] & 15)) return fail(h, MPPI_ERR_INVALID, "%s", "null or misaligned peer buffer");
+    h->px.rank = rank; h->px.world = world;
+    for (int r = 0; r < kMaxPeers; ++r) h->px.buf[r] = r < world ? (char*)peer_bufs[r] : nullptr;
+    h->px.slot_bytes = (size_t)world * h->cfg.n_env * (2 + 2 * h->cfg.T) * sizeof(double);
+    h->px.flags_off = align_up(2 * h->px.slot_bytes, 256);
+    if (h->sharded_exec) { cudaGraphExecDestroy(h->sharded_exec); h->sharded_exec = nullptr; }
+    return MPPI_OK;
+}
+
+int mppi_step_sharded(MppiHandle* h, int32_t noise_mode, const float* eps_dev, void* stream) {
+    if (!h) return MPPI_ERR_INVALID;
+    if (h->px.world < 1) return fail(h, MPPI_ERR_INVALID, "%s", "mppi_set_peer_exchange() has not been called");
+    cudaStream_t s = (cudaStream_t)stream;
+    double* partial = (double*)(h->dev + h->ws.off_partial);
+    const double* local_slots = (const double*)h->px.buf[h->px.rank];
+    const bool use_graph = (h->cfg.flags & MPPI_FLAG_DEVICE_GRAPH) && noise_mode == MPPI_NOISE_PHILOX && s != nullptr;
+    h->timing_pending = false;
+    if (use_graph) {
+        if (!h->sharded_exec || h->sharded_stream != stream) {
+            if (h->sharded_exec) { cudaGraphExecDestroy(h->sharded_exec); h->sharded_exec = nullptr; }
+            const uint64_t before = h->launches;
+            cudaGraph_t g = nullptr;
+            CU(h, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            int rc = enqueue_local(h, noise_mode, nullptr, partial, s, false, true, true, /*use_px=*/true);
+            if (rc == MPPI_OK) rc = enqueue_combine(h, local_slots, h->px.world, s, false, false, true, true);
+            cudaError_t ce = cudaStreamEndCapture(s, &g);
+            if (rc != MPPI_OK) { if (g) cudaGraphDestroy(g); return rc; }
+            CU(h, ce);
+            CU(h, cudaGraphInstantiate(&h->sharded_exec, g, 0));
+            cudaGraphDestroy(g);
+            h->sharded_kernels = h->launches - before;
+            h->launches = before;
+            h->sharded_stream = stream;
+        }
+        if (h->const_window) { int rc = const_acquire(h, s); if (rc != MPPI_OK) return rc; }
+        CU(h, cudaGraphLaunch(h->sharded_exec, s));
+        if (h->const_window) { int rc = const_release(h, s); if (rc != MPPI_OK) return rc; }
+        CU(h, cudaEventRecord(h->done, s));
+        h->launches += h->sharded_kernels;
+        h->have_step = true;
+        return MPPI_OK;
+    }
+    int rc = enqueue_local(h, noise_mode, eps_dev, partial, s, false, false, true, /*use_px=*/true);
+    if (rc != MPPI_OK) return rc;
+    return enqueue_combine(h, local_slots, h->px.world, s, false, true, true, true);
+}
+
+int mppi_exchange_status(MppiHandle* h) {
+    if (!h) return MPPI_ERR_INVALID;
+    int st = 0;
+    CU(h, cudaMemcpy(&st, h->dev + h->ws.off_seq + sizeof(unsigned long long), sizeof(int), cudaMemcpyDeviceToHost));
+    return st;
 }
 
 int mppi_closed_loop(MppiHandle* h, int32_t n_steps, double plant_dt, double* log_dev, int32_t* stop_dev,

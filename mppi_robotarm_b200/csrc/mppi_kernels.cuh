@@ -100,6 +100,50 @@ __host__ __device__ __forceinline__ StepBlockView view_step_block(void* base) {
     return v;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Peer-memory exchange of the sharded step (replaces the NCCL all-gather): every rank owns an
+// exchange buffer that all ranks of the node have mapped over NVLink.  Layout of one buffer:
+//   double slot[2][world][n_env][2 + 2T]   partial triples, double-buffered by step parity
+//   uint64 flag[2][world][n_env]           sequence number of the step whose triple is in the slot
+// The last block of the weight-sum kernel PUTS this rank's triple into slot[parity][rank] of every
+// peer (plain stores to peer addresses), fences system-wide and raises the flags; the finalize
+// kernel of each rank waits for its `world` flags and then reads only local memory.  Double
+// buffering is enough: a rank can only be one step ahead of a peer, because its finalize waits
+// for that peer's flag of the same step.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 16;
+struct PeerExchange {
+    int rank, world;              // world == 0: exchange disabled
+    char* buf[kMaxPeers];         // exchange buffer of rank r as mapped on THIS GPU (buf[rank] is local)
+    size_t slot_bytes;            // world * n_env * (2 + 2T) * 8
+    size_t flags_off;             // 2 * slot_bytes rounded up to 256
+    const unsigned long long* seq;   // step sequence number of this handle (device memory, set by prepare)
+};
+__device__ __forceinline__ double* px_slot(const PeerExchange& px, int on_rank, int parity, int from_rank, int n_env,
+                                           int e, int n) {
+    return (double*)(px.buf[on_rank] + (size_t)parity * px.slot_bytes) + ((size_t)from_rank * n_env + e) * n;
+}
+__device__ __forceinline__ unsigned long long* px_flag(const PeerExchange& px, int on_rank, int parity, int from_rank,
+                                                       int n_env, int e) {
+    return (unsigned long long*)(px.buf[on_rank] + px.flags_off) + ((size_t)parity * px.world + from_rank) * n_env + e;
+}
+// called by all threads of the block that just wrote `triple` (this rank's partial of environment e)
+__device__ __forceinline__ void px_put(const PeerExchange& px, const double* triple, int n_env, int e, int n) {
+    __syncthreads();                                            // the triple is complete
+    const unsigned long long seq = *px.seq;
+    const int par = (int)(seq & 1ull);
+    for (int r = 0; r < px.world; ++r) {
+        double* dst = px_slot(px, r, par, px.rank, n_env, e, n);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldcg(triple + i);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < px.world) {
+        volatile unsigned long long* f = px_flag(px, threadIdx.x, par, px.rank, n_env, e);
+        *f = seq;
+    }
+}
+
 // input block on the device (mirror of the caller's pinned block, see MppiIoLayout)
 struct DevIo {
     const double* x0;        // [n_env][4]
@@ -127,8 +171,10 @@ __device__ __forceinline__ void out_store(const DevIo& io, TT* dev_ptr, TT v) {
 // 1. prepare: one warp per environment
 // ================================================================================================
 __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, const double* __restrict__ ref,
-                                                          char* __restrict__ step_blocks, bool pull_inputs) {
+                                                          char* __restrict__ step_blocks, bool pull_inputs,
+                                                          unsigned long long* __restrict__ seq) {
     const int e = blockIdx.x, lane = threadIdx.x;
+    if (e == 0 && lane == 0) *seq += 1ull;        // step sequence number, read by every later kernel of the step
     if (io.host_in != nullptr && pull_inputs) {
         // zero-copy: this environment's inputs come straight from the caller's pinned block; they are
         // also written to the device mirror, which every later kernel of the step reads
@@ -509,7 +555,7 @@ mppi_softmin_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ct
                                 const float* __restrict__ block_min, float* __restrict__ w,
                                 double* __restrict__ eta_part, float* __restrict__ v_part,
                                 unsigned int* __restrict__ tickets, float* __restrict__ rho_out,
-                                double* __restrict__ partial) {
+                                double* __restrict__ partial, PeerExchange px) {
     extern __shared__ __align__(16) unsigned char smem_wsum[];
     float4* sh = (float4*)smem_wsum;                          // [warps][pairs]
     __shared__ float redf[kWsumThreads / 32];
@@ -615,6 +661,7 @@ mppi_softmin_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ct
         for (int b = 0; b < G; ++b) a += (double)__ldcg(src + (size_t)b * 2 * cfg.T);
         out[2 + c] = a;
     }
+    if (px.world > 0) px_put(px, out, cfg.n_env, e, 2 + 2 * cfg.T);   // fused exchange: triple -> every peer
 }
 
 // ================================================================================================
@@ -625,7 +672,7 @@ constexpr int kReduceThreads = 1024;
 
 __global__ void __launch_bounds__(kReduceThreads)
 mppi_reduce_sm100a(DevCfg cfg, int n_wsum_blocks, const float* __restrict__ rho, const double* __restrict__ eta_part,
-                   const float* __restrict__ v_part, double* __restrict__ partial) {
+                   const float* __restrict__ v_part, double* __restrict__ partial, PeerExchange px) {
     __shared__ double red[kReduceThreads / 32];
     __shared__ double colsum[kReduceThreads];
     const int e = blockIdx.x, tid = threadIdx.x;
@@ -657,6 +704,7 @@ mppi_reduce_sm100a(DevCfg cfg, int n_wsum_blocks, const float* __restrict__ rho,
         for (int i = 1; i < n_slice; ++i) t += colsum[i * C + tid];
         out[2 + tid] = t;
     }
+    if (px.world > 0) px_put(px, out, cfg.n_env, e, 2 + 2 * cfg.T);
 }
 
 // ================================================================================================
@@ -670,12 +718,30 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {          // scipy 're
 }
 
 __global__ void __launch_bounds__(256)
-mppi_finalize_sm100a(DevCfg cfg, DevIo io, const double* __restrict__ gathered, int world) {
+mppi_finalize_sm100a(DevCfg cfg, DevIo io, const double* gathered, int world, PeerExchange px,
+                     int* __restrict__ px_status) {
     __shared__ double raw[2 * MPPI_MAX_T_INTERNAL];
     __shared__ double unew[2 * MPPI_MAX_T_INTERNAL];
     __shared__ double scale[64];
     __shared__ double eta_s;
     const int e = blockIdx.x, tid = threadIdx.x, T = cfg.T;
+    if (px.world > 0) {
+        // wait until every rank's triple of THIS step has landed in the local exchange buffer
+        const unsigned long long seq = *px.seq;
+        const int par = (int)(seq & 1ull);
+        if (tid < px.world) {
+            volatile const unsigned long long* f = px_flag(px, px.rank, par, tid, cfg.n_env, e);
+            const long long t0 = clock64();
+            while (*f < seq) {
+                if (clock64() - t0 > 6000000000ll) { atomicExch(px_status, 1); break; }   // ~3 s: a peer died
+                __nanosleep(64);
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        gathered = (const double*)(px.buf[px.rank] + (size_t)par * px.slot_bytes);
+        world = px.world;
+    }
     const size_t stride_rank = (size_t)cfg.n_env * (2 + 2 * T);
     const double* g0 = gathered + (size_t)e * (2 + 2 * T);
     if (tid == 0) {

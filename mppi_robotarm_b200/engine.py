@@ -47,7 +47,7 @@ class MppiEngine:
     def __init__(self, *, K, T, delta_t, param_lambda, param_gamma, sigma, stage_cost_weight,
                  terminal_cost_weight, arm_params, ref_path, param_exploration=0.0, cost_l1=1.0, cost_l2=1.0,
                  n_env=1, seed=0, device=None, optimal_traj=True, use_graph=True, smoother="median",
-                 shard: ShardSpec | None = None, process_group=None, max_ref_rows=None):
+                 shard: ShardSpec | None = None, process_group=None, max_ref_rows=None, exchange="nccl"):
         import torch
         self.torch = torch
         self.lib = _cabi.load()
@@ -132,7 +132,37 @@ class MppiEngine:
         self._gathered = None
         self._dist_graph = None
         self.use_graph = bool(use_graph)
+        self._symm = None
+        if exchange not in ("nccl", "p2p"):
+            raise ValueError("exchange must be 'nccl' or 'p2p'")
+        self.exchange = exchange if self.shard.world > 1 else "nccl"
         self.set_ref_path(ref)
+        if self.exchange == "p2p":
+            self._setup_peer_exchange()
+
+    def _setup_peer_exchange(self):
+        """Map one exchange buffer per rank into every rank's address space (torch symmetric memory over
+        NVLink) and hand the table of peer addresses to the library: the kernels then exchange the
+        shard partials themselves (mppi_step_sharded) — no NCCL call in the control step."""
+        torch = self.torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        world, rank = self.shard.world, self.shard.rank
+        nbytes = int(self.lib.mppi_exchange_bytes(C.byref(self.cfg), world))
+        if nbytes == 0:
+            raise ValueError("libmppi_b200: " + _cabi.last_error())
+        group = self.group if self.group is not None else dist.group.WORLD
+        with torch.cuda.device(self.device):
+            buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, group)
+            torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)                    # every buffer is zeroed before anyone may write to it
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        assert len(ptrs) == world and ptrs[rank] == buf.data_ptr()
+        table = (C.c_void_p * world)(*ptrs)
+        _cabi.check(self.lib.mppi_set_peer_exchange(self.handle, rank, world, table), self.handle, "mppi_set_peer_exchange")
+        self._symm = (buf, hdl)
 
     # ------------------------------------------------------------------------------------------
     def close(self):
@@ -144,6 +174,7 @@ class MppiEngine:
             self._gathered = self._partial = self._gathered_keepalive = None
             self.lib.mppi_destroy(self.handle)
             self.handle = None
+            self._symm = None
 
     def __del__(self):
         try:
@@ -212,6 +243,9 @@ class MppiEngine:
         once into a torch.cuda.CUDAGraph and replayed: one launch per control step instead of ten."""
         torch = self.torch
         import torch.distributed as dist
+        if self.exchange == "p2p":
+            _cabi.check(self.lib.mppi_step_sharded(self.handle, mode, eps_ptr, s), self.handle, "mppi_step_sharded")
+            return
         if self.use_graph and mode == _cabi.NOISE_PHILOX:
             if self._dist_graph is None:
                 self._sharded_eager(mode, eps_ptr, dist)          # NCCL must have run once eagerly
@@ -261,6 +295,8 @@ class MppiEngine:
 
     def wait(self):
         _cabi.check(self.lib.mppi_wait(self.handle), self.handle, "mppi_wait")
+        if self.exchange == "p2p" and self.lib.mppi_exchange_status(self.handle) != 0:
+            raise RuntimeError("peer exchange timed out: a rank did not deliver its partial within ~3 s")
 
     def closed_loop(self, x0, u_prev, prev_idx, n_steps, plant_dt):
         """n_steps ticks of the run.py loop entirely on the device (Philox noise, FP64 plant).

@@ -26,8 +26,9 @@ def main():
     K, T = 50001, 40                                            # not divisible by the world size
     kw = cases.run_py_kwargs(ref, K, T, param_lambda=3000.0)
     results = {}
-    for label, graph in (("eager", False), ("graph", True)):
-        c = MPPIControllerForPathTracking(**kw, seed=77, verbose=False, distributed=True, use_graph=graph)
+    for label, graph, exch in (("eager", False, "nccl"), ("graph", True, "nccl"), ("p2p", True, "p2p"),
+                               ("p2p_eager", False, "p2p")):
+        c = MPPIControllerForPathTracking(**kw, seed=77, verbose=False, distributed=True, use_graph=graph, exchange=exch)
         x = np.array(cases.X0)
         seq = []
         for _ in range(4):
@@ -41,9 +42,10 @@ def main():
         for other in allu:
             assert torch.equal(other, allu[0]), "ranks diverged"
         c.close()
-    for a, b in zip(results["eager"], results["graph"]):
-        for xa, xb in zip(a[:3], b[:3]):
-            np.testing.assert_array_equal(xa, xb)
+    for other in ("graph", "p2p", "p2p_eager"):           # same partials, same combine: bit-identical
+        for a, b in zip(results["eager"], results[other]):
+            for xa, xb in zip(a[:3], b[:3]):
+                np.testing.assert_array_equal(xa, xb)
     if rank == 0:
         single = MPPIControllerForPathTracking(**kw, seed=77, verbose=False, device=torch.cuda.current_device())
         x = np.array(cases.X0)

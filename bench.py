@@ -316,9 +316,27 @@ def main():
         torch.cuda.synchronize()
 
     ref = synthetic_ref_path()
-    ctrl = MPPIControllerForPathTracking(**run_py_kwargs(ref, K_TOTAL, T_HORIZON), noise="philox", seed=1234,
-                                         verbose=False, distributed=distributed, use_graph=True)
-    eng = ctrl._engine()
+    # sharded run: partial triples are exchanged by the kernels themselves over NVLink peer memory
+    # ("p2p"); BENCH_EXCHANGE=nccl selects the NCCL all-gather path instead.  If the peer mapping cannot be
+    # set up on this box the NCCL path is used (both are GPU paths; the choice is recorded in `config`).
+    exchange = os.environ.get("BENCH_EXCHANGE", "p2p") if distributed else "nccl"
+
+    def make_ctrl(exch):
+        c = MPPIControllerForPathTracking(**run_py_kwargs(ref, K_TOTAL, T_HORIZON), noise="philox", seed=1234,
+                                          verbose=False, distributed=distributed, use_graph=True, exchange=exch)
+        return c, c._engine()
+    try:
+        ctrl, eng = make_ctrl(exchange)
+        ok = 1
+    except Exception as ex:                             # noqa: BLE001
+        print(f"[bench] rank {rank}: p2p exchange unavailable ({type(ex).__name__}: {ex})", file=sys.stderr)
+        ok = 0
+    if distributed:
+        flag = torch.tensor([ok], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:                       # any rank failed: everyone falls back together
+            exchange = "nccl"
+            ctrl, eng = make_ctrl(exchange)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     u_nom = ctrl.u_prev.copy()
 
@@ -395,7 +413,8 @@ def main():
     line = {"metric": "mppi_sample_steps_per_s", "value": value, "unit": "sample-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world), "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            "config": dict(workload_config(world), exchange=(exchange if distributed else "none")),
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "ms_per_step_stats_rank0": {"min": min(per_step), "median": float(np.median(per_step)), "max": max(per_step)}}
 
     if rank == 0:

@@ -146,6 +146,17 @@ int mppi_wait(MppiHandle* h);
 int mppi_closed_loop(MppiHandle* h, int32_t n_steps, double plant_dt, double* log_dev, int32_t* stop_dev,
                      void* stream);
 
+/* Sharded step with the exchange fused into the kernels (no NCCL call): every rank owns an exchange
+ * buffer of mppi_exchange_bytes() bytes, ZERO-INITIALISED, that all ranks of the node have mapped over
+ * NVLink (peer / symmetric memory).  peer_bufs[r] = address of rank r's buffer as mapped on THIS GPU.
+ * The last block of the weight-sum kernel stores this shard's (rho_g, eta_g, V_g) into every peer's
+ * buffer and raises a flag; the finalize kernel of each rank waits for its `world` flags (with a ~3 s
+ * timeout, reported by mppi_exchange_status() != 0) and combines.  mppi_step_sharded() = the whole step. */
+size_t mppi_exchange_bytes(const MppiConfig* cfg, int32_t world);
+int mppi_set_peer_exchange(MppiHandle* h, int32_t rank, int32_t world, void* const* peer_bufs);
+int mppi_step_sharded(MppiHandle* h, int32_t noise_mode, const float* eps_dev, void* stream);
+int mppi_exchange_status(MppiHandle* h);
+
 /* Caller-side CUDA-graph capture of the sharded step (mppi_step_local + the caller's collective +
  * mppi_step_combine on one capturing stream): while capture mode is on, the library enqueues only
  * capturable work (no event records).  Each replay of the caller's graph is bracketed by

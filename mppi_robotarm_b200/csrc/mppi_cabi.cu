@@ -473,6 +473,7 @@ int mppi_set_ref_path(MppiHandle* h, const double* ref, int32_t n_rows) {
     h->dc.n_ref_rows = n_rows;
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
     if (h->tick_exec) { cudaGraphExecDestroy(h->tick_exec); h->tick_exec = nullptr; }
+    if (h->sharded_exec) { cudaGraphExecDestroy(h->sharded_exec); h->sharded_exec = nullptr; }
     return MPPI_OK;
 }
 

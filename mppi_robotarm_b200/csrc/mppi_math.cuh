@@ -143,8 +143,9 @@ MPPI_HD void arm_step(ArmState& st, const ArmF& A, float v1, float v2) {
     // state error stays ~1 ulp instead of growing like sqrt(T) ulp over the horizon
     kahan_(st.d1, st.kd1, fma_(n1, idt, -st.kd1));
     kahan_(st.d2, st.kd2, fma_(n2, idt, -st.kd2));
-    kahan_(st.q1, st.kq1, fma_(-st.kd1, A.dt, fma_(st.d1, A.dt, -st.kq1)));
-    kahan_(st.q2, st.kq2, fma_(-st.kd2, A.dt, fma_(st.d2, A.dt, -st.kq2)));
+    // (the rate's own compensation term times dt, ~1e-8 * dt, is far below one ulp of q and is dropped)
+    kahan_(st.q1, st.kq1, fma_(st.d1, A.dt, -st.kq1));
+    kahan_(st.q2, st.kq2, fma_(st.d2, A.dt, -st.kq2));
 #else
     st.d1 = fma_(n1, idt, st.d1);
     st.d2 = fma_(n2, idt, st.d2);

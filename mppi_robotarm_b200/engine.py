@@ -188,6 +188,7 @@ class MppiEngine:
             raise ValueError(f"reference path has {ref.shape[0]} rows; this engine was sized for {self.cfg.max_ref_rows} "
                              "(pass max_ref_rows= at construction)")
         self.torch.cuda.synchronize(self.device)
+        self._dist_graph = None          # captured graphs carry the old row count in their kernel arguments
         self.n_ref_rows = ref.shape[0]
         _cabi.check(self.lib.mppi_set_ref_path(self.handle, ref.ctypes.data, ref.shape[0]), self.handle,
                     "mppi_set_ref_path")

@@ -198,3 +198,50 @@ def test_full_size_config4_properties(paths):
     np.testing.assert_array_equal(eng2.out_u_new[0], u_new)
     assert bool((eng2.last_costs()[0][0] == S).all())
     eng2.close()
+
+
+@pytest.mark.parametrize("K,T", [(200, 1), (200, 2), (64, 255), (64, 256), (1, 30), (33, 9)])
+def test_extreme_horizons_and_tiny_sample_counts(paths, K, T):
+    """Edges of the supported shape range (T = 1 .. MPPI_MAX_T, K = 1) against the oracle."""
+    case = dict(name="edge", file="xydq_circle.txt", K=K, T=T, ctor=dict(param_lambda=3.0e4))
+    ctrl, kw = H.make_controller(case, paths)
+    eps = mo.injected_noise(5, K, T, kw["sigma"])
+    H.inject(ctrl, eps)
+    u0, useq, opt, _ = H.quiet_step(ctrl, cases.X0)
+    c = mo.OracleMPPI(**kw)
+    o = mo.step_vectorized(c, cases.X0, eps.astype(np.float64))
+    eng = ctrl._engine()
+    S = eng.last_costs()[0][0].cpu().numpy().astype(np.float64)
+    assert H.rel_err(S, o["S"]) <= 5e-6                      # long horizons accumulate a little more rounding
+    assert H.rel_err(eng.out_u_new[0], o["u_new"]) <= TOL_U
+    np.testing.assert_allclose(opt, o["optimal_traj"], rtol=0, atol=1e-4 if T > 100 else TOL_TRAJ)
+    assert H.rel_err(ctrl.u_prev, c.u_prev) <= TOL_U
+    np.testing.assert_allclose(u0, o["u0"], rtol=0, atol=TOL_U * np.max(np.abs(o["u_new"])))
+    # the same shapes in Philox mode run and stay finite
+    ph, _ = H.make_controller(case, paths)
+    ph.noise = "philox"
+    out = H.quiet_step(ph, cases.X0)
+    assert np.all(np.isfinite(out[1]))
+    ctrl.close(); ph.close()
+
+
+def test_grid_stride_path_with_more_samples_than_the_grid_covers(paths):
+    """K = 9,000,000 (> 32768 CTAs x 256 samples): the rollout kernel's grid-stride loop, T = 2."""
+    import torch
+    from mppi_robotarm_b200 import MppiEngine
+    from mppi_robotarm_b200.arm_params import SYS_PARAMS
+    K, T = 9_000_000, 2
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    eng = MppiEngine(K=K, T=T, delta_t=0.006, param_lambda=1.0e4, param_gamma=200.0, sigma=np.eye(2) * 20.0,
+                     stage_cost_weight=[0.5, 0.5, 5, 5], terminal_cost_weight=[5, 5, 50, 50],
+                     arm_params=SYS_PARAMS(), ref_path=ref, seed=3, optimal_traj=False)
+    eng.step(cases.X0, np.tile([10.0, -2.0], (T, 1)), 0, None)
+    S, w = (t[0] for t in eng.last_costs())
+    assert bool(torch.isfinite(S).all()) and float(S.min()) == eng.out_rho[0]
+    np.testing.assert_allclose(eng.out_eta[0], float(w.double().sum()), rtol=1e-6)
+    # spot-check the tail of the sample range (handled by the last loop iteration) against the oracle
+    eps_tail = eng.philox_noise(step=0)[0, -2000:].cpu().numpy().astype(np.float64)
+    kw = cases.run_py_kwargs(ref, K, T)
+    S64 = mo.rollout_costs(mo.OracleMPPI(**kw), np.array(cases.X0), eps_tail, prev_idx=int(eng.out_new_idx[0]))
+    assert H.rel_err(S[-2000:].cpu().numpy().astype(np.float64), S64) <= TOL_S
+    eng.close()

@@ -47,3 +47,30 @@ def test_plant_twin_matches_reference_utils():
         a = utils.Arm_Dynamic(q, dq, u)
         b = mo.arm_accel(q[0], q[1], dq[0], dq[1], u[0], u[1], mo.default_arm_params())
         np.testing.assert_allclose(a, b, rtol=1e-13, atol=1e-13)
+
+
+def test_reference_run_py_drives_our_control_module_unchanged(tmp_path, monkeypatch):
+    """The reference's own run.py, byte for byte, with THIS repo's control.py / utils.py / sys_params.py
+    ahead of it on sys.path (and a no-op matplotlib): it must import, load its data file, construct the
+    controller with its keywords and reach the first calc_control_input call.  Without a GPU that call
+    raises NativeLibraryError (no CPU fallback) — which is the point where the drop-in boundary ends; on a
+    GPU box the same loop is covered by tests/test_gpu_features.py."""
+    import os
+    import runpy
+    import shutil
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU-side check of the drop-in boundary")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shutil.copy(os.path.join(rh.REFERENCE_DIR, "xydq_circle.txt"), tmp_path / "xydq_circle.txt")
+    monkeypatch.chdir(tmp_path)
+    rh._install_stubs()
+    for name in ("control", "utils", "sys_params"):
+        monkeypatch.delitem(sys.modules, name, raising=False)
+    monkeypatch.syspath_prepend(root)
+    from mppi_robotarm_b200 import _cabi
+    with pytest.raises(_cabi.NativeLibraryError):
+        runpy.run_path(os.path.join(rh.REFERENCE_DIR, "run.py"), run_name="__main__")
+    import control
+    assert control.MPPIControllerForPathTracking.__module__ == "mppi_robotarm_b200.controller"

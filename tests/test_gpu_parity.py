@@ -241,7 +241,7 @@ def test_grid_stride_path_with_more_samples_than_the_grid_covers(paths):
     np.testing.assert_allclose(eng.out_eta[0], float(w.double().sum()), rtol=1e-6)
     # spot-check the tail of the sample range (handled by the last loop iteration) against the oracle
     eps_tail = eng.philox_noise(step=0)[0, -2000:].cpu().numpy().astype(np.float64)
-    kw = cases.run_py_kwargs(ref, K, T)
+    kw = cases.run_py_kwargs(ref, K, T, param_lambda=1.0e4)          # gamma = 1e4 * (1 - 0.98) = 200, as above
     S64 = mo.rollout_costs(mo.OracleMPPI(**kw), np.array(cases.X0), eps_tail, prev_idx=int(eng.out_new_idx[0]))
     assert H.rel_err(S[-2000:].cpu().numpy().astype(np.float64), S64) <= TOL_S
     eng.close()

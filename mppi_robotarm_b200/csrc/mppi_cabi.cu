@@ -214,9 +214,20 @@ void const_forget(MppiHandle* h) {
     if (o.h == h) { cudaEventSynchronize(o.ev); o.h = nullptr; }
 }
 
+// How one step is enqueued.
+struct StepOpts {
+    bool timed = false;        // record the per-kernel timing events
+    bool capturing = false;    // inside a stream capture: no event records, no cross-handle waits
+    bool host_io = true;       // read inputs from / deliver outputs to the caller's pinned block
+                               // (false: device mirror only — the ticks of the device closed loop)
+    bool use_px = false;       // exchange the partial triple through peer memory (sharded step)
+    bool record_done = true;   // record the completion event after the step
+};
+
 // enqueue everything up to this shard's partial triple
 int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* partial_dev, cudaStream_t s,
-                  bool timed, bool capturing = false, bool copy_inputs = true, bool use_px = false) {
+                  const StepOpts& o) {
+    const bool timed = o.timed, capturing = o.capturing, copy_inputs = o.host_io, use_px = o.use_px;
     const DevCfg& dc = h->dc;
     char* ws = h->dev;
     if (noise_mode != MPPI_NOISE_PHILOX && noise_mode != MPPI_NOISE_INJECTED)
@@ -294,8 +305,8 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
     return MPPI_OK;
 }
 
-int enqueue_combine(MppiHandle* h, const double* gathered_dev, int world, cudaStream_t s, bool timed,
-                    bool record_done = true, bool copy_outputs = true, bool use_px = false) {
+int enqueue_combine(MppiHandle* h, const double* gathered_dev, int world, cudaStream_t s, const StepOpts& o) {
+    const bool timed = o.timed, record_done = o.record_done && !o.capturing, copy_outputs = o.host_io, use_px = o.use_px;
     if (world < 1 || world > 64) return fail(h, MPPI_ERR_INVALID, "%s", "world must be in [1, 64]");
     mppi_finalize_sm100a<<<h->dc.n_env, 256, 0, s>>>(h->dc, copy_outputs ? h->dio : h->dio_dev, gathered_dev, world,
                                                      use_px ? h->px : PeerExchange{},
@@ -482,7 +493,8 @@ int mppi_step_local(MppiHandle* h, int32_t noise_mode, const float* eps_dev, dou
     if (!partial_dev) return fail(h, MPPI_ERR_INVALID, "%s", "null partial_dev");
     h->timing_pending = false;
     const uint64_t before = h->launches;
-    int rc = enqueue_local(h, noise_mode, eps_dev, partial_dev, (cudaStream_t)stream, false, h->capture_mode);
+    StepOpts o; o.capturing = h->capture_mode;
+    int rc = enqueue_local(h, noise_mode, eps_dev, partial_dev, (cudaStream_t)stream, o);
     if (h->capture_mode) { h->capture_kernels += h->launches - before; h->launches = before; }
     return rc;
 }
@@ -491,7 +503,8 @@ int mppi_step_combine(MppiHandle* h, const double* gathered_dev, int32_t world, 
     if (!h) return MPPI_ERR_INVALID;
     if (!gathered_dev) return fail(h, MPPI_ERR_INVALID, "%s", "null gathered_dev");
     const uint64_t before = h->launches;
-    int rc = enqueue_combine(h, gathered_dev, world, (cudaStream_t)stream, false, !h->capture_mode);
+    StepOpts o; o.capturing = h->capture_mode;
+    int rc = enqueue_combine(h, gathered_dev, world, (cudaStream_t)stream, o);
     if (h->capture_mode) { h->capture_kernels += h->launches - before; h->launches = before; }
     return rc;
 }
@@ -534,8 +547,9 @@ int mppi_step(MppiHandle* h, int32_t noise_mode, const float* eps_dev, void* str
             const uint64_t before = h->launches;
             cudaGraph_t g = nullptr;
             CU(h, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            int rc = enqueue_local(h, noise_mode, nullptr, partial, s, false, /*capturing=*/true);
-            if (rc == MPPI_OK) rc = enqueue_combine(h, partial, 1, s, false, /*record_done=*/false);
+            StepOpts o; o.capturing = true;
+            int rc = enqueue_local(h, noise_mode, nullptr, partial, s, o);
+            if (rc == MPPI_OK) rc = enqueue_combine(h, partial, 1, s, o);
             cudaError_t ce = cudaStreamEndCapture(s, &g);
             if (rc != MPPI_OK) { if (g) cudaGraphDestroy(g); return rc; }
             CU(h, ce);
@@ -553,9 +567,10 @@ int mppi_step(MppiHandle* h, int32_t noise_mode, const float* eps_dev, void* str
         h->timing_pending = false;
         return MPPI_OK;
     }
-    int rc = enqueue_local(h, noise_mode, eps_dev, partial, s, h->timing);
+    StepOpts o; o.timed = h->timing;
+    int rc = enqueue_local(h, noise_mode, eps_dev, partial, s, o);
     if (rc != MPPI_OK) return rc;
-    rc = enqueue_combine(h, partial, 1, s, h->timing);
+    rc = enqueue_combine(h, partial, 1, s, o);
     h->timing_pending = h->timing && rc == MPPI_OK;
     return rc;
 }
@@ -595,8 +610,9 @@ int mppi_step_sharded(MppiHandle* h, int32_t noise_mode, const float* eps_dev, v
             const uint64_t before = h->launches;
             cudaGraph_t g = nullptr;
             CU(h, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            int rc = enqueue_local(h, noise_mode, nullptr, partial, s, false, true, true, /*use_px=*/true);
-            if (rc == MPPI_OK) rc = enqueue_combine(h, local_slots, h->px.world, s, false, false, true, true);
+            StepOpts o; o.capturing = true; o.use_px = true;
+            int rc = enqueue_local(h, noise_mode, nullptr, partial, s, o);
+            if (rc == MPPI_OK) rc = enqueue_combine(h, local_slots, h->px.world, s, o);
             cudaError_t ce = cudaStreamEndCapture(s, &g);
             if (rc != MPPI_OK) { if (g) cudaGraphDestroy(g); return rc; }
             CU(h, ce);
@@ -614,9 +630,10 @@ int mppi_step_sharded(MppiHandle* h, int32_t noise_mode, const float* eps_dev, v
         h->have_step = true;
         return MPPI_OK;
     }
-    int rc = enqueue_local(h, noise_mode, eps_dev, partial, s, false, false, true, /*use_px=*/true);
+    StepOpts o; o.use_px = true;
+    int rc = enqueue_local(h, noise_mode, eps_dev, partial, s, o);
     if (rc != MPPI_OK) return rc;
-    return enqueue_combine(h, local_slots, h->px.world, s, false, true, true, true);
+    return enqueue_combine(h, local_slots, h->px.world, s, o);
 }
 
 int mppi_exchange_status(MppiHandle* h) {
@@ -650,8 +667,9 @@ int mppi_closed_loop(MppiHandle* h, int32_t n_steps, double plant_dt, double* lo
         const uint64_t before = h->launches;
         cudaGraph_t g = nullptr;
         CU(h, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        int rc = enqueue_local(h, MPPI_NOISE_PHILOX, nullptr, partial, s, false, true, /*copy_inputs=*/false);
-        if (rc == MPPI_OK) rc = enqueue_combine(h, partial, 1, s, false, false, /*copy_outputs=*/false);
+        StepOpts o; o.capturing = true; o.host_io = false;
+        int rc = enqueue_local(h, MPPI_NOISE_PHILOX, nullptr, partial, s, o);
+        if (rc == MPPI_OK) rc = enqueue_combine(h, partial, 1, s, o);
         if (rc == MPPI_OK) {
             mppi_plant_sm100a<<<h->dc.n_env, 32, 0, s>>>(h->dc, h->dio, ws + h->ws.off_step_blocks, lp_dev);
             h->launches += 1;

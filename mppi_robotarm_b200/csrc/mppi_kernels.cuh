@@ -3,7 +3,8 @@
 //   mppi_prepare_sm100a    waypoint update in FP64 + step-block tables       control.py:75, 200-232
 //   mppi_rollout_sm100a    K fused rollouts, costs only                       control.py:84-109
 //   mppi_softmin_sm100a    min / exp / partial normaliser                     control.py:297-314
-//   mppi_wsum_*_sm100a     weighted noise sum, K x (T*2) reduction            control.py:115-118
+//   mppi_wsum_injected_sm100a   weighted noise sum, K x (T*2) reduction       control.py:115-118
+//   mppi_softmin_wsum_philox_sm100a  the two above + reduce fused (Philox)      control.py:297-314, 115-118
 //   mppi_reduce_sm100a     this GPU's partial (rho_g, eta_g, V_g)             (sharding)
 //   mppi_finalize_sm100a   combine, median filter, update, optimal rollout    control.py:122-134
 //   mppi_sampled_traj_sm100a  trajectories of all samples                     control.py:137-145
@@ -483,69 +484,13 @@ mppi_wsum_injected_sm100a(DevCfg cfg, const float* __restrict__ w, const float* 
     }
 }
 
-// ================================================================================================
-// 4b. weighted noise sum, Philox noise: eps is regenerated (bit-identical to the rollout kernel's
-//     draw: same noise_pair() on the same counters) only for samples with a non-zero weight.  A
-//     warp scans 32 weights at a time; for each non-zero one its lanes split the T/2 Philox calls.
-// ================================================================================================
-constexpr int kPairSlots = MPPI_MAX_T_INTERNAL / 2 / 32;      // Philox calls per lane and sample
-
-__global__ void __launch_bounds__(kWsumThreads)
-mppi_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const float* __restrict__ w,
-                        float* __restrict__ v_part) {
-    extern __shared__ __align__(16) unsigned char smem_wsum[];
-    float4* sh = (float4*)smem_wsum;                               // [warps][pairs]
-    const int e = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_pairs = (cfg.T + 1) >> 1;
-    NoiseCfg nc = cfg.noise; nc.step = (uint32_t)(*step_ctr);
-    const float* we = w + (size_t)e * cfg.K_local;
-    float4 acc[kPairSlots];
-#pragma unroll
-    for (int i = 0; i < kPairSlots; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int warps_total = gridDim.x * (kWsumThreads / 32);
-    for (int k0 = (blockIdx.x * (kWsumThreads / 32) + warp) * 32; k0 < cfg.K_local; k0 += warps_total * 32) {
-        const int k = k0 + lane;
-        const float wk = k < cfg.K_local ? we[k] : 0.0f;
-        unsigned mask = __ballot_sync(0xffffffffu, wk != 0.0f);
-        while (mask) {
-            const int b = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float wb = __shfl_sync(0xffffffffu, wk, b);
-            const uint32_t kg = (uint32_t)(cfg.k_offset + k0 + b);
-#pragma unroll
-            for (int i = 0; i < kPairSlots; ++i) {
-                const int pr = lane + 32 * i;
-                if (pr < n_pairs) {
-                    float a0, a1, b0, b1;
-                    noise_pair(nc, (uint32_t)e, kg, (uint32_t)pr, a0, a1, b0, b1);
-                    acc[i].x = fmaf(wb, a0, acc[i].x); acc[i].y = fmaf(wb, a1, acc[i].y);
-                    acc[i].z = fmaf(wb, b0, acc[i].z); acc[i].w = fmaf(wb, b1, acc[i].w);
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < kPairSlots; ++i) {
-        const int pr = lane + 32 * i;
-        if (pr < n_pairs) sh[warp * n_pairs + pr] = acc[i];
-    }
-    __syncthreads();
-    for (int pr = tid; pr < n_pairs; pr += kWsumThreads) {
-        float4 s = sh[pr];
-        for (int wv = 1; wv < kWsumThreads / 32; ++wv) {
-            const float4 v = sh[wv * n_pairs + pr];
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-        }
-        float* dst = v_part + ((size_t)e * cfg.g_wsum + blockIdx.x) * 2 * cfg.T + 4 * pr;
-        dst[0] = s.x; dst[1] = s.y;
-        if (2 * pr + 1 < cfg.T) { dst[2] = s.z; dst[3] = s.w; }
-    }
-}
+constexpr int kPairSlots = MPPI_MAX_T_INTERNAL / 2 / 32;      // Philox calls per lane and sample (weight-sum kernel)
 
 // ================================================================================================
-// 4c. Philox mode, fused: soft-min weights + weighted noise sum + this GPU's partial triple in ONE
+// 4b. Philox mode, fused: soft-min weights + weighted noise sum + this GPU's partial triple in ONE
 //     launch (three launches less per control step, which is what bounds the 1 kHz loop and the
-//     8-GPU strong-scaling run).  Same arithmetic and summation order as kernels 3, 4b and 5: every
+//     8-GPU strong-scaling run).  Same arithmetic as kernels 3, 4a and 5 with eps regenerated
+//     (bit-identical to the rollout kernel's draw: same noise_pair() on the same counters): every
 //     block derives rho from the rollout's block minima, weights its slice of samples, regenerates
 //     eps for the non-zero weights, writes its partials; the block that arrives last (atomic ticket)
 //     adds the partials of all blocks in block order, so the result does not depend on arrival order.

@@ -329,75 +329,8 @@ MPPI_HD int nearest_candidate(const Win& win, float xl, float yl) {
     return (int)id[0];
 }
 
-// Variant of the search that keeps the ALU pipe (half rate on sm_100) free: the minimum VALUE comes
-// from an FMNMX3 tree, then every candidate is mapped on the FMA pipe to h_j = (d_j - m)*HUGE + j,
-// which equals j exactly where d_j == m and is >= 2^40 elsewhere, and a second FMNMX3 tree returns the
-// smallest such j — the same first-arg-min, ties included (d_j - m is exact or large by Sterbenz).
 template <class Win>
-MPPI_HD int nearest_candidate_fma(const Win& win, float xl, float yl) {
-    float d[kWindow];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int j = 0; j < kWindow; ++j) d[j] = fma_(win.a(j), xl, fma_(win.b(j), yl, win.c(j)));
-    float m[10];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int i = 0; i < 10; ++i) m[i] = min3_(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
-    const float best = fminf(min3_(min3_(m[0], m[1], m[2]), min3_(m[3], m[4], m[5]), min3_(m[6], m[7], m[8])), m[9]);
-    float h[kWindow];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int j = 0; j < kWindow; ++j) h[j] = fma_(sub_(d[j], best), 1.0e30f, (float)j);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int i = 0; i < 10; ++i) m[i] = min3_(h[3 * i], h[3 * i + 1], h[3 * i + 2]);
-    const float hj = fminf(min3_(min3_(m[0], m[1], m[2]), min3_(m[3], m[4], m[5]), min3_(m[6], m[7], m[8])), m[9]);
-    return (int)hj;
-}
-
-// Tournament whose index selects run on the FMA pipe: value = FMNMX, lt = FSET (1.0 / 0.0),
-// index = idxA + lt * (idxB - idxA) evaluated exactly on small integers held as floats.
-template <class Win>
-MPPI_HD int nearest_candidate_arith(const Win& win, float xl, float yl) {
-    float d[kWindowPad], id[kWindowPad];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int j = 0; j < kWindow; ++j) { d[j] = fma_(win.a(j), xl, fma_(win.b(j), yl, win.c(j))); id[j] = (float)j; }
-    d[30] = kSentinel; d[31] = kSentinel; id[30] = 30.f; id[31] = 31.f;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int w = 1; w < kWindowPad; w *= 2) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int j = 0; j + w < kWindowPad; j += 2 * w) {
-            const float lt = d[j + w] < d[j] ? 1.0f : 0.0f;
-            d[j] = fminf(d[j + w], d[j]);
-            id[j] = fma_(lt, sub_(id[j + w], id[j]), id[j]);
-        }
-    }
-    return (int)id[0];
-}
-
-#ifndef MPPI_SEARCH
-#define MPPI_SEARCH 0
-#endif
-template <class Win>
-MPPI_HD int nearest_wp(const Win& win, float xl, float yl) {
-#if MPPI_SEARCH == 1
-    return nearest_candidate_fma(win, xl, yl);
-#elif MPPI_SEARCH == 2
-    return nearest_candidate_arith(win, xl, yl);
-#else
-    return nearest_candidate(win, xl, yl);
-#endif
-}
+MPPI_HD int nearest_wp(const Win& win, float xl, float yl) { return nearest_candidate(win, xl, yl); }
 
 // NS samples advance in lockstep inside one thread: they share the window registers, the per-step
 // constants and the loop overhead, and give the scheduler NS independent instruction streams.

@@ -131,7 +131,7 @@ void carve(const MppiConfig* c, int sm, Workspace* w) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     w->off_ref = take((size_t)c->max_ref_rows * 4 * sizeof(double));
-    w->off_step_blocks = take(E * (64 + 1024 + 16 * T));
+    w->off_step_blocks = take(E * (kStepBlockFixed + 16 * T));
     MppiIoLayout io; mppi_io_layout(c, &io);
     w->off_in = take(io.off_new_idx);                 // inputs occupy [0, off_new_idx)
     w->off_out = take(io.bytes - io.off_new_idx);
@@ -181,7 +181,7 @@ void fill_dev_cfg(MppiHandle* h) {
     d.noise.L11 = (float)c.sigma_chol[0]; d.noise.L21 = (float)c.sigma_chol[2]; d.noise.L22 = (float)c.sigma_chol[3];
     d.K_local = c.K_local; d.K_total = c.K_total; d.k_offset = c.k_offset; d.T = c.T; d.n_env = c.n_env;
     d.n_exploit = c.n_exploit; d.n_ref_rows = 0; d.flags = c.flags;
-    d.step_block_bytes = 64 + 1024 + 16 * c.T;
+    d.step_block_bytes = kStepBlockFixed + 16 * c.T;
     grid_sizes(&c, h->sm_count, &d.g_roll, &d.g_soft, &d.g_wsum);
     d.gamma = c.param_gamma; d.lambda = c.param_lambda; d.inv_lambda = 1.0 / c.param_lambda;
     for (int i = 0; i < 4; ++i) d.sig_inv[i] = c.sigma_inv[i];
@@ -260,7 +260,8 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
         if (h->const_window) {
             // single environment, large K: stage this step's window coefficients in the constant bank
             if (!capturing) { int rc = const_acquire(h, s); if (rc != MPPI_OK) return rc; }
-            CU(h, cudaMemcpyToSymbolAsync(c_window, step_blocks + 64, sizeof(WinEntry) * kWindowPad, 0,
+            // (window + rows + pair table are adjacent in the step block and in the constant bank: one copy)
+            CU(h, cudaMemcpyToSymbolAsync(c_window, step_blocks + 64, kStepBlockFixed - 64, 0,
                                           cudaMemcpyDeviceToDevice, s));
         }
 #define MPPI_LAUNCH_ROLL(NOISE, CW, NS_) \

@@ -295,6 +295,23 @@ struct WinRegs {
 // Exact FP32 comparisons on d_j - |p'|^2 = c_j + a_j x' + b_j y', as a tournament tree of depth 5;
 // `<` is strict and the right operand always carries the larger index, so ties keep the first
 // candidate like list.index(min(d)) does.
+// d[j] = c_j + a_j x' + b_j y' for the 30 candidates; a window policy may provide its own
+// `distances` (the constant-bank policy of the kernels uses packed FFMA2 there)
+template <class Win>
+MPPI_HD auto window_distances(const Win& win, float xl, float yl, float (&d)[kWindowPad], int)
+    -> decltype(win.distances(xl, yl, d), void()) { win.distances(xl, yl, d); }
+template <class Win>
+MPPI_HD void window_distances(const Win& win, float xl, float yl, float (&d)[kWindowPad], long) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < kWindow; ++j) d[j] = fma_(win.a(j), xl, fma_(win.b(j), yl, win.c(j)));
+}
+template <class Win>
+MPPI_HD void window_distances(const Win& win, float xl, float yl, float (&d)[kWindowPad]) {
+    window_distances(win, xl, yl, d, 0);
+}
+
 template <class Win>
 MPPI_HD int nearest_candidate(const Win& win, float xl, float yl) {
     float d[kWindowPad];
@@ -302,7 +319,7 @@ MPPI_HD int nearest_candidate(const Win& win, float xl, float yl) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int j = 0; j < kWindow; ++j) d[j] = fma_(win.a(j), xl, fma_(win.b(j), yl, win.c(j)));
+    window_distances(win, xl, yl, d);
     d[30] = kSentinel; d[31] = kSentinel;
     // level 1: adjacent pairs; the index is 2i + [d(2i+1) < d(2i)]
 #if defined(__CUDA_ARCH__)

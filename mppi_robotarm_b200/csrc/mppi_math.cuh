@@ -316,9 +316,6 @@ template <class Win>
 MPPI_HD int nearest_candidate(const Win& win, float xl, float yl) {
     float d[kWindowPad];
     float id[kWindowPad / 2];            // indices as small exact floats
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
     window_distances(win, xl, yl, d);
     d[30] = kSentinel; d[31] = kSentinel;
     // level 1: adjacent pairs; the index is 2i + [d(2i+1) < d(2i)]

@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 K_TOTAL = 1 << 20
 T_HORIZON = 100
 FLOPS_PER_SAMPLE_STEP = 254.0          # 70 + 6*30 + 4
-NCU_ROLLOUT_DRAM_BYTES = 22272         # dram__bytes_read+write of the rollout kernel, one ncu --set full capture
+NCU_ROLLOUT_DRAM_BYTES = 21504         # dram__bytes_read+write of the rollout kernel, one ncu --set full capture
 NCU_WSUM_DRAM_BYTES = 843073280 + 3861504   # same for mppi_wsum_injected_sm100a (algorithmic: K*T*8 = 838,860,800)
 LAT_K, LAT_T = 16384, 50               # BASELINE.json configs[2]
 
@@ -428,8 +428,8 @@ def main():
             ach = FLOPS_PER_SAMPLE_STEP * eng.K_local * T_HORIZON / (roll_us * 1e-6) / 1e12
             line["roofline"] = {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                                 "traffic": NCU_ROLLOUT_DRAM_BYTES,
-                                "traffic_source": "ncu --set full, profiles/r1c_rollout_ncu_summary.txt "
-                                                  "(dram read 22,272 B + write 0 B per launch at K=2^20, T=100)",
+                                "traffic_source": "ncu --set full, profiles/r1d_rollout_ncu_summary.txt "
+                                                  "(dram read 21,504 B + write 0 B per launch at K=2^20, T=100)",
                                 "kernel": "mppi_rollout_sm100a<philox>",
                                 "kernel_us": roll_us, "peak_source": "mppi_probe_fp32 FMA chain, this GPU, this run",
                                 "mufu_peak_gops": mufu.value / 1e9,

@@ -65,5 +65,18 @@ class BatchedMPPIController:
         opt = eng.out_opt_traj.copy() if self._want_opt else None
         return u[:, 0].copy(), u, opt
 
+    def run_closed_loop(self, observed_x, n_steps: int, plant_dt: float):
+        """n_steps ticks of the run.py loop (controller + FP64 plant of utils.py:14-29) for all environments
+        on the device, no host round trip per tick.  Returns (log, stop): log float64 [n_steps, n_env, 8] =
+        (q1, q2, dq1, dq2, u1, u2, waypoint index, rho) after each tick; stop int32 [n_env] = first tick at
+        which an environment reached the end of the path (it is frozen from there), >= n_steps if never."""
+        eng = self.engine
+        x = np.asarray(observed_x, dtype=np.float64).reshape(self.n_env, 4)
+        log, stop = eng.closed_loop(x, self.u_prev, self.prev_waypoints_idx, n_steps, plant_dt)
+        self.u_prev[...] = eng.in_u_prev
+        self.prev_waypoints_idx = eng.in_prev_idx.astype(np.int64)
+        self.finished |= stop < n_steps
+        return log, stop
+
     def close(self):
         self.engine.close()

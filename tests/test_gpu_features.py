@@ -443,3 +443,37 @@ def test_reassigning_ref_path_is_followed(paths):
     o = mo.step_vectorized(mo.OracleMPPI(**{**kw, "ref_path": shifted}), cases.X0, eps.astype(np.float64))
     assert H.rel_err(c._engine().out_u_new[0], o["u_new"]) <= TOL_U
     c.close()
+
+
+def test_batched_device_closed_loop_equals_single_environment_loops(paths):
+    """mppi_closed_loop with n_env > 1: every environment evolves exactly like a batched controller
+    stepped from the host with the same plant (same Philox streams: same seed, env index, step)."""
+    from mppi_robotarm_b200.batched import BatchedMPPIController
+    from utils import Arm_Dynamic
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    traj1 = paths["trajectory1"]
+    B, K, T, n, dt = 4, 256, 20, 60, 0.003
+    rows = [0, 400, 1000, 1600]
+    X0 = np.array([[traj1[r, 0], traj1[r, 1], 0.0, 0.0] for r in rows])
+    kw = cases.run_py_kwargs(ref, K, T)
+    dev = BatchedMPPIController(B, **kw, seed=9)
+    host = BatchedMPPIController(B, **kw, seed=9)
+    for c in (dev, host):
+        c.prev_waypoints_idx = np.array(rows)
+    log, stop = dev.run_closed_loop(X0, n, dt)
+    assert log.shape == (n, B, 8) and np.all(stop >= n)
+    X = X0.copy()
+    for t in range(n):
+        u0, _, _ = host.calc_control_input(X)
+        for b in range(B):
+            q, dq = X[b, 0:2], X[b, 2:4]
+            dq = dq + dt * Arm_Dynamic(q, dq, u0[b])
+            q = q + dt * dq
+            X[b] = np.concatenate([q, dq])
+        if t < 20:
+            np.testing.assert_allclose(log[t, :, 0:4], X, rtol=0, atol=1e-9)
+            np.testing.assert_allclose(log[t, :, 4:6], u0, rtol=0, atol=1e-7)
+            np.testing.assert_array_equal(log[t, :, 6].astype(np.int64), host.prev_waypoints_idx)
+    assert np.max(np.abs(log[-1, :, 0:4] - X)) <= 0.3
+    np.testing.assert_array_equal(dev.prev_waypoints_idx >= np.array(rows), True)
+    dev.close(); host.close()

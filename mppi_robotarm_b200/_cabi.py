@@ -94,6 +94,13 @@ def load() -> C.CDLL:
     if _lib is not None:
         return _lib
     path = library_path()
+    if not os.path.isfile(path) and "MPPI_B200_LIB" not in os.environ:
+        try:                                   # fresh checkout: compile the CUDA library once (nvcc, a few seconds)
+            _build.build_library()
+        except Exception as ex:                # noqa: BLE001
+            raise NativeLibraryError(
+                f"{path} not found and building it failed ({ex}). Build it with `python -m mppi_robotarm_b200.build` "
+                "(needs nvcc; the library is sm_100a CUDA and there is no CPU fallback).") from ex
     if not os.path.isfile(path):
         raise NativeLibraryError(
             f"{path} not found. Build it with `python -m mppi_robotarm_b200.build` (needs nvcc; the "

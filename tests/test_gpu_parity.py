@@ -28,6 +28,11 @@ def _compare_step(ctrl, g, s, kw, out, label):
     assert [int(g[f"prev_idx.{s}"][0]), ctrl.prev_waypoints_idx] == list(g[f"prev_idx.{s}"]), label
     S = eng.last_costs()[0][0].cpu().numpy().astype(np.float64)
     assert H.rel_err(S, g[f"S.{s}"]) <= TOL_S, (label, "S", H.rel_err(S, g[f"S.{s}"]))
+    # normalised weights (control.py:297-314); a cost error dS moves a weight by ~dS/lambda relative
+    wt = eng.last_costs()[1][0].cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(wt / wt.sum(), g[f"w.{s}"], rtol=0, atol=2e-2 * 100.0 / float(ctrl.param_lambda) + 1e-6,
+                               err_msg=label)
+    assert int(np.argmax(wt)) == int(np.argmax(g[f"w.{s}"])), label
     scale_u = np.max(np.abs(g[f"u_new.{s}"]))
     assert np.max(np.abs(ctrl.last["w_eps_raw"] - g[f"w_eps_raw.{s}"])) <= TOL_U * scale_u, (label, "w_eps_raw")
     assert np.max(np.abs(ctrl.last["w_eps_filt"] - g[f"w_eps_filt.{s}"])) <= TOL_U * scale_u, (label, "w_eps_filt")

@@ -566,30 +566,42 @@ mppi_softmin_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ct
     for (int i = 0; i < kPairSlots; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     double eta = 0.0;
     const int warps_total = gridDim.x * (kWsumThreads / 32);
-    for (int k0 = (blockIdx.x * (kWsumThreads / 32) + warp) * 32; k0 < cfg.K_local; k0 += warps_total * 32) {
-        const int k = k0 + lane;
-        float wk = 0.0f;
-        if (k < cfg.K_local) {
-            const float s = Se[k];
-            const float x = expf((s - rho) * nil);
-            wk = finite_(s) ? x : 0.0f;
-            we[k] = wk;
-            eta += (double)wk;
-        }
-        unsigned mask = __ballot_sync(0xffffffffu, wk != 0.0f);
-        while (mask) {
-            const int b = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float wb = __shfl_sync(0xffffffffu, wk, b);
-            const uint32_t kg = (uint32_t)(cfg.k_offset + k0 + b);
+    const int chunk_stride = warps_total * 32;
+    constexpr int kAhead = 4;                                 // cost loads in flight per lane (the scan is latency bound)
+    for (int kb = (blockIdx.x * (kWsumThreads / 32) + warp) * 32; kb < cfg.K_local; kb += kAhead * chunk_stride) {
+        float sv[kAhead];
 #pragma unroll
-            for (int i = 0; i < kPairSlots; ++i) {
-                const int pr = lane + 32 * i;
-                if (pr < n_pairs) {
-                    float a0, a1, b0, b1;
-                    noise_pair(nc, (uint32_t)e, kg, (uint32_t)pr, a0, a1, b0, b1);
-                    acc[i].x = fmaf(wb, a0, acc[i].x); acc[i].y = fmaf(wb, a1, acc[i].y);
-                    acc[i].z = fmaf(wb, b0, acc[i].z); acc[i].w = fmaf(wb, b1, acc[i].w);
+        for (int u = 0; u < kAhead; ++u) {
+            const int k = kb + u * chunk_stride + lane;
+            sv[u] = k < cfg.K_local ? Se[k] : INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < kAhead; ++u) {
+            const int k0 = kb + u * chunk_stride;
+            if (k0 >= cfg.K_local) break;
+            const int k = k0 + lane;
+            float wk = 0.0f;
+            if (k < cfg.K_local) {
+                const float x = expf((sv[u] - rho) * nil);
+                wk = finite_(sv[u]) ? x : 0.0f;
+                we[k] = wk;
+                eta += (double)wk;
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, wk != 0.0f);
+            while (mask) {
+                const int b = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float wb = __shfl_sync(0xffffffffu, wk, b);
+                const uint32_t kg = (uint32_t)(cfg.k_offset + k0 + b);
+#pragma unroll
+                for (int i = 0; i < kPairSlots; ++i) {
+                    const int pr = lane + 32 * i;
+                    if (pr < n_pairs) {
+                        float a0, a1, b0, b1;
+                        noise_pair(nc, (uint32_t)e, kg, (uint32_t)pr, a0, a1, b0, b1);
+                        acc[i].x = fmaf(wb, a0, acc[i].x); acc[i].y = fmaf(wb, a1, acc[i].y);
+                        acc[i].z = fmaf(wb, b0, acc[i].z); acc[i].w = fmaf(wb, b1, acc[i].w);
+                    }
                 }
             }
         }

@@ -712,6 +712,7 @@ mppi_finalize_sm100a(DevCfg cfg, DevIo io, const double* gathered, int world, Pe
                      int* __restrict__ px_status) {
     __shared__ double raw[2 * MPPI_MAX_T_INTERNAL];
     __shared__ double unew[2 * MPPI_MAX_T_INTERNAL];
+    __shared__ __align__(16) float tr[8 * MPPI_MAX_T_INTERNAL];    // optimal trajectory: (value, compensation) per state and step
     __shared__ double scale[64];
     __shared__ double eta_s;
     const int e = blockIdx.x, tid = threadIdx.x, T = cfg.T;
@@ -796,20 +797,26 @@ mppi_finalize_sm100a(DevCfg cfg, DevIo io, const double* gathered, int world, Pe
         out_store(io, io.u_new + (size_t)e * 2 * T + c, u);
     }
     __syncthreads();
-    // control.py:129-134: x <- F(x, u[t-1]) for t = 0..T-1 (t = 0 wraps to the last control, Q3)
+    // control.py:129-134: x <- F(x, u[t-1]) for t = 0..T-1 (t = 0 wraps to the last control, Q3).
+    // The recurrence is serial: one thread runs it and parks (value, compensation) pairs in shared
+    // memory; all threads then convert and store the trajectory (keeps global / PCIe stores off the chain).
     if (cfg.flags & 1) {
         if (tid == 0) {
             const double* x0 = io.x0 + 4 * e;
             ArmState st; arm_init(st, (float)x0[0], (float)x0[1], (float)x0[2], (float)x0[3]);
-            double* o = io.opt_traj + (size_t)e * 4 * T;
             for (int t = 0; t < T; ++t) {
                 const int tc = t == 0 ? T - 1 : t - 1;
                 arm_step(st, cfg.arm, (float)unew[2 * tc], (float)unew[2 * tc + 1]);
-                out_store(io, o + 4 * t + 0, (double)st.q1 - (double)st.kq1);
-                out_store(io, o + 4 * t + 1, (double)st.q2 - (double)st.kq2);
-                out_store(io, o + 4 * t + 2, (double)st.d1 - (double)st.kd1);
-                out_store(io, o + 4 * t + 3, (double)st.d2 - (double)st.kd2);
+                float4* o = (float4*)(tr + 8 * t);
+                o[0] = make_float4(st.q1, st.q2, st.d1, st.d2);
+                o[1] = make_float4(st.kq1, st.kq2, st.kd1, st.kd2);
             }
+        }
+        __syncthreads();
+        double* o = io.opt_traj + (size_t)e * 4 * T;
+        for (int c = tid; c < 4 * T; c += blockDim.x) {
+            const int t = c >> 2, k = c & 3;
+            out_store(io, o + c, (double)tr[8 * t + k] - (double)tr[8 * t + 4 + k]);
         }
     } else {
         for (int c = tid; c < 4 * T; c += blockDim.x) out_store(io, io.opt_traj + (size_t)e * 4 * T + c, 0.0);

@@ -301,7 +301,10 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
     if (timed) CU(h, cudaEventRecord(h->tev[2], s));
     if (noise_mode == MPPI_NOISE_PHILOX) {
         // fused: soft-min weights + weighted sum + this GPU's partial triple
+        // 4096 samples per block for large K; small K is latency bound: up to 64 blocks of >= 512 samples
         int g = (dc.K_local + 4095) / 4096;
+        const int g_small = (dc.K_local + 511) / 512 < 64 ? (dc.K_local + 511) / 512 : 64;
+        if (g < g_small) g = g_small;
         if (g > dc.g_wsum) g = dc.g_wsum;
         const size_t sm = (size_t)(kWsumThreads / 32) * ((dc.T + 1) / 2) * sizeof(float4);
         mppi_softmin_wsum_philox_sm100a<<<dim3(g, dc.n_env), kWsumThreads, sm, s>>>(

@@ -173,56 +173,81 @@ __device__ __forceinline__ void out_store(const DevIo& io, TT* dev_ptr, TT v) {
 // ================================================================================================
 // 1. prepare: one warp per environment
 // ================================================================================================
+// One warp per environment.  The kernel is a chain of memory latencies, so every load is issued as
+// early as its address is known: (1) all inputs at once — from the caller's pinned block over PCIe
+// (zero-copy) or from the device mirror; (2) the 60 reference rows the new window can touch, while the
+// FP64 forward kinematics run; the rows of the final window are then picked by shuffles, not reloaded.
 __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, const double* __restrict__ ref,
                                                           char* __restrict__ step_blocks, bool pull_inputs,
                                                           unsigned long long* __restrict__ seq) {
-    const int e = blockIdx.x, lane = threadIdx.x;
+    const int e = blockIdx.x, lane = threadIdx.x, T = cfg.T;
     if (e == 0 && lane == 0) *seq += 1ull;        // step sequence number, read by every later kernel of the step
-    if (io.host_in != nullptr && pull_inputs) {
-        // zero-copy: this environment's inputs come straight from the caller's pinned block; they are
-        // also written to the device mirror, which every later kernel of the step reads
-        const double* hx = (const double*)((const char*)io.x0 - io.in_delta) + 4 * e;
-        const double* hu = (const double*)((const char*)io.u_prev - io.in_delta) + (size_t)e * cfg.T * 2;
-        double* dx = const_cast<double*>(io.x0) + 4 * e;
-        double* du = const_cast<double*>(io.u_prev) + (size_t)e * cfg.T * 2;
-        // issue every PCIe read before using any of them: one round trip instead of several
-        constexpr int kSlots = (2 * MPPI_MAX_T_INTERNAL + 31) / 32;
-        double vu[kSlots];
+    const bool zc = io.host_in != nullptr && pull_inputs;
+    const ptrdiff_t back = zc ? io.in_delta : 0;  // zero-copy: read the pinned block instead of the mirror
+    const double* sx = (const double*)((const char*)(io.x0 + 4 * e) - back);
+    const double2* su = (const double2*)((const char*)(io.u_prev + (size_t)e * T * 2) - back);
+    const int32_t* sp = (const int32_t*)((const char*)(io.prev_idx + e) - back);
+    // ---- (1) inputs --------------------------------------------------------------------------------
+    constexpr int kTS = (MPPI_MAX_T_INTERNAL + 31) / 32;
+    double2 uu[kTS];
 #pragma unroll
-        for (int i = 0; i < kSlots; ++i) { const int c = lane + 32 * i; vu[i] = c < 2 * cfg.T ? hu[c] : 0.0; }
-        const double vx = lane < 4 ? hx[lane] : 0.0;
-        const int32_t pidx = lane == 4 ? *(const int32_t*)((const char*)(io.prev_idx + e) - io.in_delta) : 0;
-        const uint64_t stp = (lane == 5 && e == 0) ? *(const uint64_t*)((const char*)io.step - io.in_delta) : 0;
-#pragma unroll
-        for (int i = 0; i < kSlots; ++i) { const int c = lane + 32 * i; if (c < 2 * cfg.T) du[c] = vu[i]; }
-        if (lane < 4) dx[lane] = vx;
-        if (lane == 4) const_cast<int32_t*>(io.prev_idx)[e] = pidx;
-        if (lane == 5 && e == 0) *const_cast<uint64_t*>(io.step) = stp;
-        __syncwarp();
-    }
-    const double* x0 = io.x0 + 4 * e;
+    for (int i = 0; i < kTS; ++i) { const int t = lane + 32 * i; uu[i] = t < T ? su[t] : make_double2(0.0, 0.0); }
+    const double q1 = sx[0], q2 = sx[1], dq1 = sx[2], dq2 = sx[3];
+    int p = *sp;
+    const uint64_t stp = (zc && lane == 0 && e == 0) ? *(const uint64_t*)((const char*)io.step - back) : 0;
     const int n = cfg.n_ref_rows;
-    int p = io.prev_idx[e];
     p = max(0, min(p, n - 1));
+    // ---- (2) reference rows p .. p+63 (clamped), two per lane --------------------------------------
+    const double4* ref4 = (const double4*)ref;
+    const double4 r_lo = ref4[min(p + lane, n - 1)];
+    const double4 r_hi = ref4[min(p + 32 + lane, n - 1)];
+    if (zc) {                                     // fill the device mirror every later kernel reads
+        double* dx = const_cast<double*>(io.x0) + 4 * e;
+        double2* du = (double2*)(const_cast<double*>(io.u_prev) + (size_t)e * T * 2);
+        if (lane == 0) {
+            dx[0] = q1; dx[1] = q2; dx[2] = dq1; dx[3] = dq2;
+            const_cast<int32_t*>(io.prev_idx)[e] = *sp;
+            if (e == 0) *const_cast<uint64_t*>(io.step) = stp;
+        }
+#pragma unroll
+        for (int i = 0; i < kTS; ++i) { const int t = lane + 32 * i; if (t < T) du[t] = uu[i]; }
+    }
     // control.py:206-215 in FP64: end-effector, distances to the forward window, first arg-min
-    const double q1 = x0[0], q2 = x0[1];
     const double x = cfg.cost_l1 * cos(q1) + cfg.cost_l2 * cos(q1 + q2);
     const double y = cfg.cost_l1 * sin(q1) + cfg.cost_l2 * sin(q1 + q2);
     double d = 1.0e300;
     int j = lane;
-    if (lane < kWindow && p + lane < n) d = waypoint_d(ref, p + lane, x, y);
+    if (lane < kWindow && p + lane < n) {
+        const double dx_ = x - r_lo.x, dy_ = y - r_lo.y;
+        d = (dx_ * dx_ + dy_ * dy_) * 100;                   // control.py:210-212
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double d2 = __shfl_xor_sync(0xffffffffu, d, o);
         const int j2 = __shfl_xor_sync(0xffffffffu, j, o);
         if (d2 < d || (d2 == d && j2 < j)) { d = d2; j = j2; }
     }
+    const int p_old = p;
     p += j;                                                  // control.py:230
+    // row p + lane of the path = preloaded row (j + lane) relative to p_old
+    const int src = j + lane;                                // 0 .. 60
+    const bool from_hi = src >= 32;
+    double4 row;
+    {
+        const int sl = src & 31;
+        const double ax = __shfl_sync(0xffffffffu, r_lo.x, sl), bx = __shfl_sync(0xffffffffu, r_hi.x, sl);
+        const double ay = __shfl_sync(0xffffffffu, r_lo.y, sl), by = __shfl_sync(0xffffffffu, r_hi.y, sl);
+        const double az = __shfl_sync(0xffffffffu, r_lo.z, sl), bz = __shfl_sync(0xffffffffu, r_hi.z, sl);
+        const double aw = __shfl_sync(0xffffffffu, r_lo.w, sl), bw = __shfl_sync(0xffffffffu, r_hi.w, sl);
+        row = from_hi ? make_double4(bx, by, bz, bw) : make_double4(ax, ay, az, aw);
+    }
+    const double ox = __shfl_sync(0xffffffffu, row.x, 0), oy = __shfl_sync(0xffffffffu, row.y, 0);   // row p
+    (void)p_old;
     StepBlockView sb = view_step_block(step_blocks + (size_t)e * cfg.step_block_bytes);
     if (lane == 0) {
         StepHeader h;
-        h.q1 = (float)x0[0]; h.q2 = (float)x0[1]; h.d1 = (float)x0[2]; h.d2 = (float)x0[3];
-        h.ox = (float)ref[4 * p]; h.oy = (float)ref[4 * p + 1];
+        h.q1 = (float)q1; h.q2 = (float)q2; h.d1 = (float)dq1; h.d2 = (float)dq2;
+        h.ox = (float)ox; h.oy = (float)oy;
         h.win_start = p; h.n_valid = min(kWindow, n - p);
         h.status = (p >= n - 1) ? 1 : 0;                     // control.py:76
         for (int i = 0; i < 7; ++i) h.pad[i] = 0;
@@ -230,8 +255,16 @@ __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, 
         out_store(io, io.new_idx + e, p);
     }
     {
+        // window row `lane` in coordinates local to row p (make_window_row on the preloaded rows)
         WinEntry w; RefRow r;
-        make_window_row(ref, n, p, lane, w, r);
+        if (lane < kWindow && p + lane < n) {
+            const double rx = row.x - ox, ry = row.y - oy;
+            w.a = (float)(-2.0 * rx); w.b = (float)(-2.0 * ry); w.c = (float)(rx * rx + ry * ry); w.pad = 0.f;
+            r.rx = (float)rx; r.ry = (float)ry; r.rd1 = (float)row.z; r.rd2 = (float)row.w;
+        } else {                   // beyond the end of the path (control.py:208-209) or table padding
+            w.a = 0.f; w.b = 0.f; w.c = kSentinel; w.pad = 0.f;
+            r.rx = 0.f; r.ry = 0.f; r.rd1 = 0.f; r.rd2 = 0.f;
+        }
         // the rollouts subtract the FP32 origin from the FP32 end-effector; rows are relative to
         // the FP64 origin — the difference (<= 6e-8) is common to all candidates of a lookup
         sb.win[lane] = w; sb.rows[lane] = r;
@@ -239,10 +272,14 @@ __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, 
         const float a1 = __shfl_down_sync(0xffffffffu, w.a, 1), b1 = __shfl_down_sync(0xffffffffu, w.b, 1);
         if ((lane & 1) == 0) sb.pairs[lane >> 1] = make_float4(w.a, a1, w.b, b1);
     }
-    const double* u = io.u_prev + (size_t)e * cfg.T * 2;
-    for (int t = lane; t < cfg.T; t += 32) {
-        StepCtl c; make_step_ctl(u + 2 * t, cfg.gamma, cfg.sig_inv, c);
-        sb.ctl[t] = c;
+#pragma unroll
+    for (int i = 0; i < kTS; ++i) {
+        const int t = lane + 32 * i;
+        if (t < T) {
+            const double ut[2] = { uu[i].x, uu[i].y };
+            StepCtl c; make_step_ctl(ut, cfg.gamma, cfg.sig_inv, c);
+            sb.ctl[t] = c;
+        }
     }
 }
 

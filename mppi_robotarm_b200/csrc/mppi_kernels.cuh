@@ -213,8 +213,11 @@ __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, 
         for (int i = 0; i < kTS; ++i) { const int t = lane + 32 * i; if (t < T) du[t] = uu[i]; }
     }
     // control.py:206-215 in FP64: end-effector, distances to the forward window, first arg-min
-    const double x = cfg.cost_l1 * cos(q1) + cfg.cost_l2 * cos(q1 + q2);
-    const double y = cfg.cost_l1 * sin(q1) + cfg.cost_l2 * sin(q1 + q2);
+    double s1, c1, s12, c12;
+    sincos(q1, &s1, &c1);
+    sincos(q1 + q2, &s12, &c12);
+    const double x = cfg.cost_l1 * c1 + cfg.cost_l2 * c12;
+    const double y = cfg.cost_l1 * s1 + cfg.cost_l2 * s12;
     double d = 1.0e300;
     int j = lane;
     if (lane < kWindow && p + lane < n) {

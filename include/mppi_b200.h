@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MPPI_ABI_VERSION 1
+#define MPPI_ABI_VERSION 2
 
 enum {
     MPPI_OK = 0,
@@ -51,7 +51,11 @@ enum {
     MPPI_FLAG_OPTIMAL_TRAJ = 1, /* control.py:129-134: roll the updated sequence out             */
     MPPI_FLAG_DEVICE_GRAPH = 2, /* replay the step as one CUDA graph (Philox mode only)          */
     MPPI_FLAG_SMOOTH_AVERAGE = 4, /* smooth the update with control.py:329-344 instead of the median filter (needs T >= 10) */
-    MPPI_FLAG_SMOOTH_NONE = 8   /* no smoothing of the weighted noise sum                        */
+    MPPI_FLAG_SMOOTH_NONE = 8,  /* no smoothing of the weighted noise sum                        */
+    MPPI_FLAG_FULL_SEARCH = 16, /* control.py:208-215: always run the 30-candidate search (switches off the
+                                   certified end-of-window shortcut; results are bit-identical either way) */
+    MPPI_FLAG_DYNAMICS_F1 = 32, /* roll out with control.py:265-295 (_F1, feedback-linearised) instead of _F */
+    MPPI_FLAG_SEARCH_STATS = 64 /* count certified / total warp-lookups of the rollouts (mppi_search_stats) */
 };
 
 /* Hyper-parameters: control.py:21-65 + sys_params.py:3-10, fixed for the life of a handle. */
@@ -182,6 +186,10 @@ int mppi_sampled_trajectories_subset(MppiHandle* h, int32_t noise_mode, const fl
 int mppi_philox_noise(MppiHandle* h, uint64_t step, float* eps_dev, void* stream);
 /* Number of kernels launched by this handle so far (graph replays count their kernel nodes). */
 uint64_t mppi_launch_count(const MppiHandle* h);
+/* Nearest-waypoint lookups of the rollouts (control.py:200-215 via _c / _phi) since the last reset, counted
+ * per warp (32 samples): out2[0] = lookups answered by the certified end-of-window shortcut, out2[1] = all
+ * lookups.  Needs MPPI_FLAG_SEARCH_STATS; synchronises the device. */
+int mppi_search_stats(MppiHandle* h, uint64_t* out2, int32_t reset);
 /* Mean device time of each kernel family over the steps run with timing enabled, in microseconds:
  * out[0..5] = prepare, rollout, softmin, weighted-sum, reduce, finalize.  Returns #timed steps. */
 int mppi_set_timing(MppiHandle* h, int32_t enable);

@@ -10,7 +10,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_T = 256
 
 NOISE_PHILOX = 0
@@ -19,6 +19,9 @@ FLAG_OPTIMAL_TRAJ = 1
 FLAG_DEVICE_GRAPH = 2
 FLAG_SMOOTH_AVERAGE = 4
 FLAG_SMOOTH_NONE = 8
+FLAG_FULL_SEARCH = 16
+FLAG_DYNAMICS_F1 = 32
+FLAG_SEARCH_STATS = 64
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_WORKSPACE = 0, -1, -2, -3, -4
 
@@ -71,6 +74,7 @@ SYMBOLS = {
                                                    C.c_void_p, C.c_void_p]),
     "mppi_philox_noise": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "mppi_launch_count": (C.c_uint64, [C.c_void_p]),
+    "mppi_search_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int32]),
     "mppi_set_timing": (C.c_int, [C.c_void_p, C.c_int32]),
     "mppi_get_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int32]),
     "mppi_probe_fp32": (C.c_int, [C.c_int32, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -17,7 +17,8 @@ class BatchedMPPIController:
     def __init__(self, n_env: int, *, delta_t, ref_path, horizon_step_T, number_of_samples_K,
                  param_exploration=0.0, param_lambda=50.0, param_alpha=1.0, sigma=None,
                  stage_cost_weight=None, terminal_cost_weight=None, visualize_optimal_traj=False,
-                 seed=0, device=None, use_graph=True, env_offset=0):
+                 seed=0, device=None, use_graph=True, env_offset=0, search="certified", search_stats=False,
+                 dynamics="F"):
         self.n_env = int(n_env)
         self.T, self.K = int(horizon_step_T), int(number_of_samples_K)
         self.param_lambda, self.param_alpha = param_lambda, param_alpha
@@ -35,7 +36,8 @@ class BatchedMPPIController:
             sigma=self.Sigma, stage_cost_weight=stage_cost_weight, terminal_cost_weight=terminal_cost_weight,
             arm_params=_arm_params(), ref_path=ref_path, param_exploration=param_exploration, n_env=self.n_env,
             seed=int(seed) + 0x9E3779B97F4A7C15 * int(env_offset), device=device,
-            optimal_traj=bool(visualize_optimal_traj), use_graph=use_graph)
+            optimal_traj=bool(visualize_optimal_traj), use_graph=use_graph, search=search,
+            search_stats=search_stats, dynamics=dynamics)
 
     def calc_control_input(self, observed_x, eps=None, strict=False):
         """observed_x [n_env, 4] -> (u0 [n_env, 2], u_seq [n_env, T, 2], optimal_traj [n_env, T, 4] or None

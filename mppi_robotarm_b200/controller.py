@@ -52,6 +52,9 @@ class MPPIControllerForPathTracking:
             exchange: str = "nccl",     # sharded runs: "nccl" all-gather or "p2p" (fused peer-memory exchange)
             sampled_traj_top_n=None,    # with visualze_sampled_trajs: return only the n best, best first
             smoother: str = "median",  # "median" (control.py:122), "average" (control.py:329-344) or "none"
+            dynamics: str = "F",        # rollout model: "F" (control.py:234-263) or "F1" (control.py:265-295)
+            search: str = "certified",  # nearest-waypoint lookups: "certified" shortcut or always "full" (same results)
+            search_stats: bool = False,  # count how many lookups the shortcut answered (engine.search_stats())
     ) -> None:
         # same attributes as control.py:37-65
         self.dim_x = 4
@@ -86,6 +89,9 @@ class MPPIControllerForPathTracking:
         self._exchange = exchange
         self.sampled_traj_top_n = sampled_traj_top_n
         self.smoother = smoother
+        self.dynamics = dynamics
+        self._search = search
+        self._search_stats = search_stats
         self._engine_obj = None
         self._engine_ref_path = None
         self.last = {}               # intermediates of the last step (rho, eta, raw / filtered update)
@@ -107,7 +113,8 @@ class MPPIControllerForPathTracking:
                 cost_l1=self.l1, cost_l2=self.l2, n_env=1, seed=self.seed, device=self._device,
                 optimal_traj=bool(self.visualize_optimal_traj), use_graph=self._use_graph,
                 smoother=self.smoother, shard=self._shard(), process_group=self._group,
-                exchange=self._exchange)
+                exchange=self._exchange, search=self._search, search_stats=self._search_stats,
+                dynamics=self.dynamics)
             self._engine_ref_path = self.ref_path
         elif self.ref_path is not self._engine_ref_path:
             # the reference reads self.ref_path on every call (control.py:208); follow a re-assignment

@@ -25,7 +25,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct Workspace {
     size_t bytes;
     size_t off_ref, off_step_blocks, off_in, off_out, off_S, off_w, off_block_min, off_eta_part,
-        off_rho, off_v_part, off_partial, off_loop, off_eta_fused, off_tickets, off_seq;
+        off_rho, off_v_part, off_partial, off_loop, off_eta_fused, off_tickets, off_seq, off_stats;
 };
 
 }  // namespace
@@ -168,6 +168,7 @@ void carve(const MppiConfig* c, int sm, Workspace* w) {
     w->off_eta_fused = take(E * g_wsum * sizeof(double));
     w->off_tickets = take(E * sizeof(unsigned int));
     w->off_seq = take(2 * sizeof(unsigned long long));       // [0] step sequence number, [1] exchange status
+    w->off_stats = take(2 * sizeof(unsigned long long));     // [0] certified warp-lookups, [1] warp-lookups
     w->bytes = off;
 }
 
@@ -287,7 +288,8 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
                                           cudaMemcpyDeviceToDevice, s));
         }
 #define MPPI_LAUNCH_ROLL(NOISE, CW, NS_) \
-        mppi_rollout_sm100a<NOISE, CW, NS_><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, ph ? nullptr : eps_dev, S, bmin)
+        mppi_rollout_sm100a<NOISE, CW, NS_><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, ph ? nullptr : eps_dev, S, bmin, \
+                                                                                     (unsigned long long*)(ws + h->ws.off_stats))
         if (h->const_window) {
             if (h->ns == 2) { if (ph) MPPI_LAUNCH_ROLL(0, true, 2); else MPPI_LAUNCH_ROLL(1, true, 2); }
             else { if (ph) MPPI_LAUNCH_ROLL(0, true, 1); else MPPI_LAUNCH_ROLL(1, true, 1); }
@@ -465,6 +467,7 @@ int mppi_create(const MppiConfig* c, void* workspace, size_t workspace_bytes, vo
     h->px.world = 0;
     h->px.seq = (const unsigned long long*)(h->dev + h->ws.off_seq);
     if (cudaMemset(h->dev + h->ws.off_seq, 0, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(h->dev + h->ws.off_stats, 0, 2 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(h->dev + h->ws.off_tickets, 0, sizeof(unsigned int) * c->n_env) != cudaSuccess) {
         snprintf(g_create_error, sizeof(g_create_error), "cudaMemset(tickets) failed");
         delete h;
@@ -780,6 +783,19 @@ int mppi_philox_noise(MppiHandle* h, uint64_t step, float* eps_dev, void* stream
 }
 
 uint64_t mppi_launch_count(const MppiHandle* h) { return h ? h->launches : 0; }
+
+int mppi_search_stats(MppiHandle* h, uint64_t* out2, int32_t reset) {
+    if (!h || !out2) return MPPI_ERR_INVALID;
+    if (!(h->cfg.flags & MPPI_FLAG_SEARCH_STATS))
+        return fail(h, MPPI_ERR_INVALID, "%s", "the handle was created without MPPI_FLAG_SEARCH_STATS");
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaDeviceSynchronize());
+    unsigned long long v[2] = { 0, 0 };
+    CU(h, cudaMemcpy(v, h->dev + h->ws.off_stats, sizeof(v), cudaMemcpyDeviceToHost));
+    out2[0] = v[0]; out2[1] = v[1];
+    if (reset) CU(h, cudaMemset(h->dev + h->ws.off_stats, 0, sizeof(v)));
+    return MPPI_OK;
+}
 
 int mppi_set_timing(MppiHandle* h, int32_t enable) {
     if (!h) return MPPI_ERR_INVALID;

@@ -89,9 +89,9 @@ struct LoopParams {
 };
 
 struct StepBlockView {          // pointers into one environment's step block (global or shared)
-    StepHeader* hd; WinEntry* win; RefRow* rows; float4* pairs; StepCtl* ctl;
+    StepHeader* hd; WinEntry* win; RefRow* rows; float4* pairs; EndCert* cert; StepCtl* ctl;
 };
-constexpr int kStepBlockFixed = 64 + 32 * kWindowPad + 16 * (kWindowPad / 2);   // header + win + rows + pairs
+constexpr int kStepBlockFixed = 64 + 32 * kWindowPad + 16 * (kWindowPad / 2) + 64;   // header + win + rows + pairs + certificate
 __host__ __device__ __forceinline__ StepBlockView view_step_block(void* base) {
     char* b = (char*)base;
     StepBlockView v;
@@ -99,6 +99,7 @@ __host__ __device__ __forceinline__ StepBlockView view_step_block(void* base) {
     v.win = (WinEntry*)(b + 64);
     v.rows = (RefRow*)(b + 64 + 16 * kWindowPad);
     v.pairs = (float4*)(b + 64 + 32 * kWindowPad);          // (a_2i, a_2i+1, b_2i, b_2i+1): operands of packed FFMA2
+    v.cert = (EndCert*)(b + 64 + 32 * kWindowPad + 16 * (kWindowPad / 2));   // end-of-window certificate
     v.ctl = (StepCtl*)(b + kStepBlockFixed);
     return v;
 }
@@ -168,6 +169,55 @@ template <class TT>
 __device__ __forceinline__ void out_store(const DevIo& io, TT* dev_ptr, TT v) {
     *dev_ptr = v;
     if (io.out_delta != 0) *(TT*)((char*)dev_ptr + io.out_delta) = v;
+}
+
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// make_wedge() of mppi_math.cuh with one lane per window row (rx, ry = this lane's local row, valid for
+// lane < n).  Every lane returns the same coefficients.
+__device__ __forceinline__ void warp_wedge(double rx, double ry, int lane, int n, int target, double margin, double dom,
+                                           float (&ox)[2], float (&oy)[2], float (&ok)[2]) {
+    cert_disable(ox, oy, ok);
+    if (n < 2) return;                                        // (uniform)
+    const int other = target == 0 ? n - 1 : 0;
+    const double tx = __shfl_sync(0xffffffffu, rx, target), ty = __shfl_sync(0xffffffffu, ry, target);
+    double n0x = tx - __shfl_sync(0xffffffffu, rx, other), n0y = ty - __shfl_sync(0xffffffffu, ry, other);
+    const double n0 = sqrt(n0x * n0x + n0y * n0y);
+    if (!(n0 > 0.0)) return;
+    n0x /= n0; n0y /= n0;
+    const bool mine = lane < n && lane != target;
+    const double gx = tx - rx, gy = ty - ry;
+    const double along = gx * n0x + gy * n0y, across = n0x * gy - n0y * gx;
+    const bool bad = mine && (!(along > 0.05 * fabs(across)) || !(along > 0.0));
+    if (__any_sync(0xffffffffu, bad)) return;
+    const double sl = mine ? across / along : 0.0;
+    double smin = warp_min_d(mine ? sl : 1e300), smax = warp_max_d(mine ? sl : -1e300);
+    smin -= 1e-7 * (1.0 + smin * smin); smax += 1e-7 * (1.0 + smax * smax);
+    double mx[2], my[2];
+    const double s2[2] = { smin, smax };
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double vx = n0x - s2[i] * n0y, vy = n0y + s2[i] * n0x, vn = sqrt(vx * vx + vy * vy);
+        mx[i] = vx / vn; my[i] = vy / vn;
+    }
+    double bx = mx[0] + mx[1], by = my[0] + my[1];
+    const double bn = sqrt(bx * bx + by * by);
+    if (!(bn > 1e-3)) return;
+    bx /= bn; by /= bn;
+    const double g2 = gx * gx + gy * gy, ng = bx * gx + by * gy;
+    if (__any_sync(0xffffffffu, mine && !(ng > 0.0))) return;
+    const double tau = warp_max_d(mine ? fmax((margin - g2) / (2.0 * ng), 0.0) : 0.0);
+    if (!(tau <= kCertMaxTau)) return;
+    cert_finish(tx + tau * bx, ty + tau * by, mx, my, dom, ox, oy, ok);
 }
 
 // ================================================================================================
@@ -271,6 +321,27 @@ __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, 
         // the rollouts subtract the FP32 origin from the FP32 end-effector; rows are relative to
         // the FP64 origin — the difference (<= 6e-8) is common to all candidates of a lookup
         sb.win[lane] = w; sb.rows[lane] = r;
+        {   // end-of-window certificate (make_end_cert of mppi_math.cuh, one lane per row)
+            const int nv = min(kWindow, n - p);
+            const bool valid = lane < nv;
+            const double rx = valid ? row.x - ox : 0.0, ry = valid ? row.y - oy : 0.0;
+            const double aox = fabs(ox), aoy = fabs(oy);
+            const double dom = 1.01 * (cfg.cost_l1 + cfg.cost_l2) + fmax(aox, aoy) + 0.01;
+            EndCert c;
+            c.dom = (float)dom; c.last = nv - 1; c.pad[0] = c.pad[1] = 0;
+            cert_disable(c.lx, c.ly, c.lk); cert_disable(c.fx, c.fy, c.fk);
+            if (!(cfg.flags & 16)) {                          // MPPI_FLAG_FULL_SEARCH switches the shortcut off
+                if (nv == 1) { c.fk[0] = c.fk[1] = 1.0f; }
+                else if (nv >= 2) {
+                    const double amax = warp_max_d(2.0 * fabs(rx)), bmax = warp_max_d(2.0 * fabs(ry));
+                    const double cmax = warp_max_d(rx * rx + ry * ry);
+                    const double margin = cert_margin(amax, bmax, cmax, 1.0001 * dom);
+                    warp_wedge(rx, ry, lane, nv, nv - 1, margin, 1.0001 * dom, c.lx, c.ly, c.lk);
+                    warp_wedge(rx, ry, lane, nv, 0, margin, 1.0001 * dom, c.fx, c.fy, c.fk);
+                }
+            }
+            if (lane == 0) *sb.cert = c;
+        }
         // the same a/b coefficients once more, laid out as candidate pairs
         const float a1 = __shfl_down_sync(0xffffffffu, w.a, 1), b1 = __shfl_down_sync(0xffffffffu, w.b, 1);
         if ((lane & 1) == 0) sb.pairs[lane >> 1] = make_float4(w.a, a1, w.b, b1);
@@ -318,6 +389,7 @@ struct ConstWindow {                 // same layout as bytes [64, kStepBlockFixe
     WinEntry win[kWindowPad];
     RefRow rows[kWindowPad];         // (not read from here: the winning row is fetched from shared memory)
     float4 pairs[kWindowPad / 2];
+    EndCert cert;                    // read as immediate constant operands by the certificate test
 };
 __constant__ ConstWindow c_window;
 #ifndef MPPI_FFMA2_SEARCH
@@ -365,10 +437,16 @@ struct WinConst {
 #define MPPI_ROLL_MIN_BLOCKS_CONST 4
 #endif
 
+template <bool CW>
+__device__ __forceinline__ const EndCert& cert_of(const StepBlockView& sb) {
+    if constexpr (CW) return c_window.cert; else return *sb.cert;
+}
+
 template <int NOISE, bool CONSTWIN, int kNS>
 __global__ void __launch_bounds__(kRollThreads, CONSTWIN ? MPPI_ROLL_MIN_BLOCKS_CONST : (kNS == 1 ? 3 : 2))
 mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const char* __restrict__ step_blocks,
-                    const float* __restrict__ eps, float* __restrict__ S_out, float* __restrict__ block_min) {
+                    const float* __restrict__ eps, float* __restrict__ S_out, float* __restrict__ block_min,
+                    unsigned long long* __restrict__ search_stats) {
     extern __shared__ __align__(128) unsigned char smem_roll[];
     unsigned char* smem = smem_roll;
     __shared__ uint64_t bar;
@@ -385,13 +463,20 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
     const StepHeader hd = *sb.hd;
     typename std::conditional<CONSTWIN, WinConst, WinRegs>::type win;
     win.load(sb.win);
+    // the certificate test reads its coefficients as constant-bank operands (single environment) or
+    // from the staged step block
+    const EndCert& cert = cert_of<CONSTWIN>(sb);
+    int hits = 0, lookups = 0;
 
     float tmin = INFINITY;
     const int T = cfg.T;
-    // thread handles samples kl0 + s*kRollThreads (s < NS): consecutive lanes -> consecutive samples
-    for (int kl0 = blockIdx.x * (kRollThreads * kNS) + tid; kl0 < cfg.K_local; kl0 += gridDim.x * kRollThreads * kNS) {
+    // thread handles samples kl0 + s*kRollThreads (s < NS): consecutive lanes -> consecutive samples.
+    // The trip count is decided per WARP (its first lane), because the lookups vote across the warp.
+    for (int kw0 = blockIdx.x * (kRollThreads * kNS) + (tid & ~31); kw0 < cfg.K_local; kw0 += gridDim.x * kRollThreads * kNS) {
+        const int kl0 = kw0 + (tid & 31);
         float um[kNS], S[kNS];
         int kl[kNS];
+        lookups += kNS * T;
 #pragma unroll
         for (int s = 0; s < kNS; ++s) {
             // a padding sample past the end recomputes the last one (its result is not stored)
@@ -405,12 +490,12 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
                 nz[s].nc = cfg.noise; nz[s].nc.step = (uint32_t)(*step_ctr); nz[s].env = (uint32_t)e;
                 nz[s].k = (uint32_t)(cfg.k_offset + kl[s]);
             }
-            rollout_cost_n<kNS>(hd, cfg.arm, cfg.cost, win, sb.rows, sb.ctl, T, um, nz, S);
+            rollout_cost_n<kNS>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
         } else {
             InjectedNoise nz[kNS];
 #pragma unroll
             for (int s = 0; s < kNS; ++s) nz[s].row = (const float2*)eps + ((size_t)e * cfg.K_local + kl[s]) * T;
-            rollout_cost_n<kNS>(hd, cfg.arm, cfg.cost, win, sb.rows, sb.ctl, T, um, nz, S);
+            rollout_cost_n<kNS>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
         }
 #pragma unroll
         for (int s = 0; s < kNS; ++s) {
@@ -422,6 +507,10 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
     }
     tmin = warp_min(tmin);
     if ((tid & 31) == 0) red[tid >> 5] = tmin;
+    if ((cfg.flags & 64) && (tid & 31) == 0) {              // MPPI_FLAG_SEARCH_STATS: warp-lookups certified / done
+        atomicAdd(search_stats, (unsigned long long)hits);
+        atomicAdd(search_stats + 1, (unsigned long long)lookups);
+    }
     __syncthreads();
     if (tid == 0) {
         float m = red[0];

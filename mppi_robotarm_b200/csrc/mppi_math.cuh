@@ -276,6 +276,130 @@ struct StepHeader {            // first 64 bytes of a step block (one per enviro
 };
 static_assert(sizeof(StepHeader) == 64, "header is 64 bytes");
 
+// ---- end-of-window certificate ------------------------------------------------------------------
+// The window (control.py:208-209) is fixed for the whole horizon while the rollouts move along the
+// path at about one waypoint per step, so after ~10-20 horizon steps every sample of a warp lies
+// beyond the last window row (or, for an arm that falls back, before the first) and the 30-candidate
+// search can only return that row.  The prepare kernel derives, in FP64, two half-planes whose
+// intersection (a wedge) lies inside the Voronoi cell of the last row — and two for row 0 — with a
+// margin that covers every FP32 rounding of the search AND of the test itself: if
+//     mx_i x' + my_i y' + k_i >= 0  (i = 0, 1)   and   |x'|, |y'| <= dom
+// then the full FP32 search is guaranteed to return that row, so it is skipped when a whole warp is
+// certified.  Results are bit-identical with and without the shortcut (tests: emulation + GPU).
+// Derivation: with g_j = r_L - r_j,  d_j - d_L = |g_j|^2 + 2 g_j.(p - r_L).  All g_j lie in the cone
+// spanned by the two extreme directions m_0, m_1; for p = z + s with s.m_0 >= 0 and s.m_1 >= 0 every
+// s.g_j >= 0, hence d_j - d_L >= |g_j|^2 + 2 tau n.g_j at the apex z = r_L + tau n, and tau is chosen
+// so that this is >= the rounding margin for every j.
+struct EndCert {               // 64 bytes of a step block
+    float lx[2], ly[2], lk[2]; // wedge inside the cell of the last valid row
+    float fx[2], fy[2], fk[2]; // wedge inside the cell of row 0
+    float dom;                 // the margins hold for |x'|, |y'| <= dom
+    int32_t last;              // index of the last valid row (n_valid - 1)
+    int32_t pad[2];
+};
+static_assert(sizeof(EndCert) == 64, "certificate block is 64 bytes");
+
+// Certificate test for (x', y'): wl >= 0 certifies the last row, wf >= 0 certifies row 0 (the two
+// wedges are disjoint), both only inside the domain the margins were derived for.
+struct CertTest { float wl, wf; bool in_dom; };
+MPPI_HD CertTest cert_test(const EndCert& c, float xl, float yl) {
+    CertTest t;
+    t.wl = fminf(fma_(c.lx[0], xl, fma_(c.ly[0], yl, c.lk[0])), fma_(c.lx[1], xl, fma_(c.ly[1], yl, c.lk[1])));
+    t.wf = fminf(fma_(c.fx[0], xl, fma_(c.fy[0], yl, c.fk[0])), fma_(c.fx[1], xl, fma_(c.fy[1], yl, c.fk[1])));
+    t.in_dom = fmaxf(fabsf(xl), fabsf(yl)) <= c.dom;               // false for NaN
+    return t;
+}
+MPPI_HD bool cert_ok(const CertTest& t) { return t.in_dom && fmaxf(t.wl, t.wf) >= 0.0f; }
+MPPI_HD int cert_row(const EndCert& c, const CertTest& t) { return t.wl >= 0.0f ? c.last : 0; }
+// index the search is certain to return for (x', y'), or -1 when nothing is certified
+MPPI_HD int cert_pick(const EndCert& c, float xl, float yl) {
+    const CertTest t = cert_test(c, xl, yl);
+    return cert_ok(t) ? cert_row(c, t) : -1;
+}
+
+MPPI_HD void cert_disable(float (&mx)[2], float (&my)[2], float (&k)[2]) {
+    mx[0] = mx[1] = 0.f; my[0] = my[1] = 0.f; k[0] = k[1] = -INFINITY;
+}
+
+// One wedge: rows[j] = (x, y) of window row j in local coordinates (FP64), n rows valid, `target`
+// = 0 or n-1.  amax/bmax/cmax bound |a_j|, |b_j|, c_j of the FP32 table.  Serial form (host tests and
+// the reference for the warp-parallel version in the prepare kernel).
+constexpr double kCertU = 5.9604644775390625e-08;      // 2^-24
+constexpr double kCertMaxTau = 0.25;                   // give up when the apex would be > 25 cm past the row
+MPPI_HD double cert_margin(double amax, double bmax, double cmax, double dom) {
+    // |D_j - d_j| <= 3u(|a x| + |b y| + c) for D = fma(a, x, fma(b, y, c)) with rounded a, b, c; the
+    // test needs d_j - d_t > 2 * that; factor 2 of slack on top
+    return 16.0 * kCertU * (amax * dom + bmax * dom + cmax);
+}
+MPPI_HD void cert_finish(double zx, double zy, const double (&mx)[2], const double (&my)[2], double dom,
+                         float (&ox)[2], float (&oy)[2], float (&ok)[2]) {
+    for (int i = 0; i < 2; ++i) {
+        const double k = -(mx[i] * zx + my[i] * zy);
+        // the FP32 value of mx x + my y + k differs from the exact one by <= 3u(|x| + |y| + |k|)
+        const double delta = 8.0 * kCertU * (2.0 * dom + fabs(k)) + 1e-30;
+        ox[i] = (float)mx[i]; oy[i] = (float)my[i]; ok[i] = (float)(k - delta);
+    }
+}
+MPPI_HD void make_wedge(const double (*rows)[2], int n, int target, double margin, double dom,
+                        float (&ox)[2], float (&oy)[2], float (&ok)[2]) {
+    cert_disable(ox, oy, ok);
+    if (n < 2) return;
+    const int other = target == 0 ? n - 1 : 0;
+    double n0x = rows[target][0] - rows[other][0], n0y = rows[target][1] - rows[other][1];
+    const double n0 = sqrt(n0x * n0x + n0y * n0y);
+    if (!(n0 > 0.0)) return;
+    n0x /= n0; n0y /= n0;
+    double smin = 1e300, smax = -1e300;
+    for (int j = 0; j < n; ++j) {
+        if (j == target) continue;
+        const double gx = rows[target][0] - rows[j][0], gy = rows[target][1] - rows[j][1];
+        const double along = gx * n0x + gy * n0y, across = n0x * gy - n0y * gx;
+        if (!(along > 0.05 * fabs(across)) || !(along > 0.0)) return;   // direction spread too wide (or duplicate rows)
+        const double s = across / along;
+        smin = s < smin ? s : smin; smax = s > smax ? s : smax;
+    }
+    smin -= 1e-7 * (1.0 + smin * smin); smax += 1e-7 * (1.0 + smax * smax);     // widen the cone by ~1e-7 rad
+    double mx[2], my[2];
+    const double s2[2] = { smin, smax };
+    for (int i = 0; i < 2; ++i) {
+        const double vx = n0x - s2[i] * n0y, vy = n0y + s2[i] * n0x, vn = sqrt(vx * vx + vy * vy);
+        mx[i] = vx / vn; my[i] = vy / vn;
+    }
+    double bx = mx[0] + mx[1], by = my[0] + my[1];
+    const double bn = sqrt(bx * bx + by * by);
+    if (!(bn > 1e-3)) return;
+    bx /= bn; by /= bn;
+    double tau = 0.0;
+    for (int j = 0; j < n; ++j) {
+        if (j == target) continue;
+        const double gx = rows[target][0] - rows[j][0], gy = rows[target][1] - rows[j][1];
+        const double g2 = gx * gx + gy * gy, ng = bx * gx + by * gy;
+        if (!(ng > 0.0)) return;
+        const double t = (margin - g2) / (2.0 * ng);
+        tau = t > tau ? t : tau;
+    }
+    if (!(tau <= kCertMaxTau)) return;
+    cert_finish(rows[target][0] + tau * bx, rows[target][1] + tau * by, mx, my, dom, ox, oy, ok);
+}
+// rows: the n_valid local rows (FP64); reach = L1 + L2 of the cost-side kinematics; (ox, oy) = window origin
+MPPI_HD void make_end_cert(const double (*rows)[2], int n_valid, double reach, double ox, double oy,
+                           bool enabled, EndCert& c) {
+    const double aox = fabs(ox), aoy = fabs(oy);
+    const double dom = 1.01 * reach + (aox > aoy ? aox : aoy) + 0.01;
+    c.dom = (float)dom; c.last = n_valid - 1; c.pad[0] = c.pad[1] = 0;
+    cert_disable(c.lx, c.ly, c.lk); cert_disable(c.fx, c.fy, c.fk);
+    if (!enabled || n_valid < 1) return;
+    if (n_valid == 1) { c.fk[0] = c.fk[1] = 1.0f; return; }       // a one-row window: the search can only return row 0
+    double amax = 0, bmax = 0, cmax = 0;
+    for (int j = 0; j < n_valid; ++j) {
+        const double a = 2.0 * fabs(rows[j][0]), b = 2.0 * fabs(rows[j][1]), cc = rows[j][0] * rows[j][0] + rows[j][1] * rows[j][1];
+        amax = a > amax ? a : amax; bmax = b > bmax ? b : bmax; cmax = cc > cmax ? cc : cmax;
+    }
+    const double margin = cert_margin(amax, bmax, cmax, 1.0001 * dom);
+    make_wedge(rows, n_valid, n_valid - 1, margin, 1.0001 * dom, c.lx, c.ly, c.lk);
+    make_wedge(rows, n_valid, 0, margin, 1.0001 * dom, c.fx, c.fy, c.fk);
+}
+
 // Where the 30 x (a, b, c) window coefficients live.  WinRegs: per-thread registers (any number of
 // environments).  The kernels add WinConst: the constant bank, read as immediate FFMA operands.
 struct WinRegs {
@@ -346,12 +470,25 @@ MPPI_HD int nearest_candidate(const Win& win, float xl, float yl) {
 template <class Win>
 MPPI_HD int nearest_wp(const Win& win, float xl, float yl) { return nearest_candidate(win, xl, yl); }
 
+// The lookup of the rollouts: the certified row when the whole warp is certified (one vote, no
+// divergence), else the full search.  `hits` counts the skipped searches (per warp on the device).
+template <class Win>
+MPPI_HD int nearest_wp(const Win& win, const EndCert& cert, float xl, float yl, int& hits) {
+    const CertTest t = cert_test(cert, xl, yl);
+#if defined(__CUDA_ARCH__)
+    if (__all_sync(0xffffffffu, cert_ok(t))) { ++hits; return cert_row(cert, t); }
+#else
+    if (cert_ok(t)) { ++hits; return cert_row(cert, t); }
+#endif
+    return nearest_candidate(win, xl, yl);
+}
+
 // NS samples advance in lockstep inside one thread: they share the window registers, the per-step
 // constants and the loop overhead, and give the scheduler NS independent instruction streams.
 template <int NS, class Win, class Noise>
 MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
-                            const Win& win, const RefRow* rows, const StepCtl* ctl,
-                            int T, const float (&um)[NS], Noise (&noise)[NS], float (&S_out)[NS]) {
+                            const Win& win, const EndCert& cert, const RefRow* rows, const StepCtl* ctl,
+                            int T, const float (&um)[NS], Noise (&noise)[NS], float (&S_out)[NS], int& hits) {
     ArmState st[NS];
     float S[NS], kS[NS], ex[NS], ey[NS], e1[NS], e2[NS];
 #if defined(__CUDA_ARCH__)
@@ -383,7 +520,7 @@ MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
 #endif
         for (int s = 0; s < NS; ++s) {
             fk_local(st[s], A, hd.ox, hd.oy, xl[s], yl[s]);
-            j[s] = nearest_wp(win, xl[s], yl[s]);
+            j[s] = nearest_wp(win, cert, xl[s], yl[s], hits);
         }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -410,12 +547,12 @@ MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
 
 template <class Win, class Noise>
 MPPI_HD float rollout_cost(const StepHeader& hd, const ArmF& A, const CostW& W,
-                           const Win& win, const RefRow* rows, const StepCtl* ctl,
-                           int T, float um, Noise& noise) {
+                           const Win& win, const EndCert& cert, const RefRow* rows, const StepCtl* ctl,
+                           int T, float um, Noise& noise, int& hits) {
     const float ums[1] = { um };
     float out[1];
     Noise (&nz)[1] = reinterpret_cast<Noise (&)[1]>(noise);
-    rollout_cost_n<1>(hd, A, W, win, rows, ctl, T, ums, nz, out);
+    rollout_cost_n<1>(hd, A, W, win, cert, rows, ctl, T, ums, nz, out, hits);
     return out[0];
 }
 

@@ -47,7 +47,8 @@ class MppiEngine:
     def __init__(self, *, K, T, delta_t, param_lambda, param_gamma, sigma, stage_cost_weight,
                  terminal_cost_weight, arm_params, ref_path, param_exploration=0.0, cost_l1=1.0, cost_l2=1.0,
                  n_env=1, seed=0, device=None, optimal_traj=True, use_graph=True, smoother="median",
-                 shard: ShardSpec | None = None, process_group=None, max_ref_rows=None, exchange="nccl"):
+                 shard: ShardSpec | None = None, process_group=None, max_ref_rows=None, exchange="nccl",
+                 search="certified", search_stats=False, dynamics="F"):
         import torch
         self.torch = torch
         self.lib = _cabi.load()
@@ -79,8 +80,15 @@ class MppiEngine:
             raise ValueError("smoother must be 'median', 'average' or 'none'")
         if smoother == "average" and self.T < 10:
             raise ValueError("the moving-average smoother needs horizon_step_T >= 10 (np.convolve 'same', control.py:338)")
+        if search not in ("certified", "full"):
+            raise ValueError("search must be 'certified' (end-of-window shortcut, bit-identical results) or 'full'")
+        if dynamics not in ("F", "F1"):
+            raise ValueError("dynamics must be 'F' (control.py:234-263) or 'F1' (control.py:265-295)")
         cfg.flags = ((_cabi.FLAG_OPTIMAL_TRAJ if optimal_traj else 0) | (_cabi.FLAG_DEVICE_GRAPH if use_graph else 0)
-                     | {"median": 0, "average": _cabi.FLAG_SMOOTH_AVERAGE, "none": _cabi.FLAG_SMOOTH_NONE}[smoother])
+                     | {"median": 0, "average": _cabi.FLAG_SMOOTH_AVERAGE, "none": _cabi.FLAG_SMOOTH_NONE}[smoother]
+                     | (_cabi.FLAG_FULL_SEARCH if search == "full" else 0)
+                     | (_cabi.FLAG_SEARCH_STATS if search_stats else 0)
+                     | (_cabi.FLAG_DYNAMICS_F1 if dynamics == "F1" else 0))
         cfg.max_ref_rows = int(max_ref_rows or ref.shape[0])
         cfg.delta_t, cfg.param_lambda, cfg.param_gamma = float(delta_t), float(param_lambda), float(param_gamma)
         cfg.sigma_chol[:] = chol.reshape(-1).tolist()
@@ -372,6 +380,15 @@ class MppiEngine:
                     self.handle, "mppi_philox_noise")
         self.stream.synchronize()
         return out
+
+    def search_stats(self, reset=True) -> dict:
+        """Nearest-waypoint lookups of the rollouts since the last reset, per warp of 32 samples:
+        how many the certified end-of-window shortcut answered, and how many there were
+        (engine built with search_stats=True)."""
+        buf = (C.c_uint64 * 2)()
+        _cabi.check(self.lib.mppi_search_stats(self.handle, buf, 1 if reset else 0), self.handle, "mppi_search_stats")
+        return {"certified": int(buf[0]), "lookups": int(buf[1]),
+                "fraction": (buf[0] / buf[1]) if buf[1] else 0.0}
 
     def launch_count(self) -> int:
         return int(self.lib.mppi_launch_count(self.handle))

@@ -3,6 +3,7 @@
 // to study FP32-vs-FP64 parity without a GPU; never loaded by the product package.
 #include "../../mppi_robotarm_b200/csrc/mppi_math.cuh"
 #include <cmath>
+#include <cstring>
 #include <vector>
 using namespace mppi;
 
@@ -17,7 +18,7 @@ extern "C" {
 int emul_rollout_costs(const double* ref, int n_rows, int prev_idx, const double* x0, const double* u_prev,
                        int K, int T, int n_exploit, double dt, double gamma, const double* sig_inv,
                        const double* ws, const double* wt, const double* arm, double cl1, double cl2,
-                       const float* eps, float* S_out) {
+                       const float* eps, float* S_out, int use_cert, long long* hits_out) {
     // waypoint update, FP64 (control.py:75, 200-232)
     double x = cl1 * cos(x0[0]) + cl2 * cos(x0[0] + x0[1]);
     double y = cl1 * sin(x0[0]) + cl2 * sin(x0[0] + x0[1]);
@@ -33,6 +34,15 @@ int emul_rollout_costs(const double* ref, int n_rows, int prev_idx, const double
     WinRegs win; RefRow rows[kWindowPad]; WinEntry tab[kWindowPad];
     for (int j = 0; j < kWindowPad; ++j) make_window_row(ref, n_rows, p, j, tab[j], rows[j]);
     win.load(tab);
+    // end-of-window certificate, as the prepare kernel builds it (serial form)
+    double lrows[kWindow][2];
+    int n_valid = 0;
+    for (int j = 0; j < kWindow && p + j < n_rows; ++j, ++n_valid) {
+        lrows[j][0] = ref[4 * (p + j)] - ref[4 * p]; lrows[j][1] = ref[4 * (p + j) + 1] - ref[4 * p + 1];
+    }
+    EndCert cert;
+    make_end_cert(lrows, n_valid, cl1 + cl2, ref[4 * p], ref[4 * p + 1], use_cert != 0, cert);
+    long long hits_total = 0;
     std::vector<StepCtl> ctl(T);
     for (int t = 0; t < T; ++t) make_step_ctl(u_prev + 2 * t, gamma, sig_inv, ctl[t]);
     const double m1 = arm[0], m2 = arm[1], l1 = arm[2], l2 = arm[3], lc1 = arm[4], lc2 = arm[5], g = arm[6];
@@ -47,9 +57,33 @@ int emul_rollout_costs(const double* ref, int n_rows, int prev_idx, const double
              (float)(wt[0] * 1e4), (float)(wt[1] * 1e4), (float)(wt[2] * 1e4), (float)(wt[3] * 1e4) };
     for (int k = 0; k < K; ++k) {
         EpsArray n{ eps + (size_t)k * T * 2, T };
-        S_out[k] = rollout_cost(hd, A, W, win, rows, ctl.data(), T, k < n_exploit ? 1.f : 0.f, n);
+        int hits = 0;
+        S_out[k] = rollout_cost(hd, A, W, win, cert, rows, ctl.data(), T, k < n_exploit ? 1.f : 0.f, n, hits);
+        hits_total += hits;
     }
+    if (hits_out) *hits_out = hits_total;
     return p;
+}
+
+// Soundness probe of the end-of-window certificate: for n queries (x', y') in the local coordinates
+// of the window starting at row p, pick[i] = certified row or -1, full[i] = result of the FP32 search.
+void emul_cert_probe(const double* ref, int n_rows, int p, double reach, const float* xy, int n, int* pick, int* full,
+                     float* cert_out) {
+    WinRegs win; RefRow rows[kWindowPad]; WinEntry tab[kWindowPad];
+    for (int j = 0; j < kWindowPad; ++j) make_window_row(ref, n_rows, p, j, tab[j], rows[j]);
+    win.load(tab);
+    double lrows[kWindow][2];
+    int n_valid = 0;
+    for (int j = 0; j < kWindow && p + j < n_rows; ++j, ++n_valid) {
+        lrows[j][0] = ref[4 * (p + j)] - ref[4 * p]; lrows[j][1] = ref[4 * (p + j) + 1] - ref[4 * p + 1];
+    }
+    EndCert cert;
+    make_end_cert(lrows, n_valid, reach, ref[4 * p], ref[4 * p + 1], true, cert);
+    if (cert_out) memcpy(cert_out, &cert, sizeof(cert));
+    for (int i = 0; i < n; ++i) {
+        pick[i] = cert_pick(cert, xy[2 * i], xy[2 * i + 1]);
+        full[i] = nearest_candidate(win, xy[2 * i], xy[2 * i + 1]);
+    }
 }
 
 void emul_sincos(const float* x, int n, float* s, float* c) { for (int i = 0; i < n; ++i) sincos_(x[i], s[i], c[i]); }

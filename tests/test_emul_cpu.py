@@ -34,7 +34,7 @@ def fp(a):
     return a.ctypes.data_as(C.POINTER(C.c_float))
 
 
-def emul_costs(lib, c, x0, eps32, prev_idx, u=None):
+def emul_costs(lib, c, x0, eps32, prev_idx, u=None, use_cert=True, hits=None):
     ref = np.ascontiguousarray(c.ref_path)
     u = np.ascontiguousarray(c.u_prev if u is None else u)
     K, T = eps32.shape[:2]
@@ -42,11 +42,14 @@ def emul_costs(lib, c, x0, eps32, prev_idx, u=None):
     arm = np.array([c.arm[k] for k in ("m1", "m2", "l1", "l2", "lc1", "lc2", "g")], dtype=np.float64)
     sinv = np.ascontiguousarray(np.linalg.inv(c.sigma))
     x0 = np.ascontiguousarray(np.asarray(x0, dtype=np.float64))
+    h = C.c_longlong(0)
     p = lib.emul_rollout_costs(dp(ref), ref.shape[0], prev_idx, dp(x0), dp(u), K, T,
                                mo.exploit_count(K, c.param_exploration), C.c_double(c.delta_t),
                                C.c_double(c.param_gamma), dp(sinv), dp(np.ascontiguousarray(c.stage_cost_weight)),
                                dp(np.ascontiguousarray(c.terminal_cost_weight)), dp(arm), C.c_double(c.cost_l1),
-                               C.c_double(c.cost_l2), fp(np.ascontiguousarray(eps32)), fp(S))
+                               C.c_double(c.cost_l2), fp(np.ascontiguousarray(eps32)), fp(S), int(use_cert), C.byref(h))
+    if hits is not None:
+        hits.append(h.value)
     return S, p
 
 
@@ -109,3 +112,82 @@ def test_host_noise_moments(emul):
     flat = eps.reshape(-1, 2).astype(np.float64)
     assert np.all(np.abs(flat.mean(0)) < 0.05)
     np.testing.assert_allclose(np.cov(flat.T), [[20.0, 6.0], [6.0, 10.0]], atol=0.25)
+
+
+# ---------------------------------------------------------------------------------------------
+# certified end-of-window shortcut of the nearest-waypoint lookups (mppi_math.cuh: EndCert)
+# ---------------------------------------------------------------------------------------------
+def _probe(emul, ref, p, xy):
+    n = xy.shape[0]
+    pick, full = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    cert = np.zeros(16, np.float32)
+    xy = np.ascontiguousarray(xy.astype(np.float32))
+    emul.emul_cert_probe(dp(ref), ref.shape[0], int(p), C.c_double(2.0), fp(xy), n,
+                         pick.ctypes.data_as(C.POINTER(C.c_int)), full.ctypes.data_as(C.POINTER(C.c_int)), fp(cert))
+    return pick, full, cert
+
+
+def test_certificate_never_disagrees_with_the_full_search(emul, paths):
+    """Whenever the certificate names a row, the exact FP32 30-candidate search returns the same row:
+    random queries from 10 um to 2 m around windows of all four reference files (noisy recorded paths
+    included), windows truncated by the end of the path, and queries placed on the wedge boundaries."""
+    rng = np.random.default_rng(5)
+    certified = 0
+    for name in ("xydq_circle", "xydq", "trajectory", "trajectory1"):
+        ref = np.ascontiguousarray(paths[name][:, 0:4], dtype=np.float64)
+        n = ref.shape[0]
+        for p in list(rng.integers(0, n - 31, 12)) + [n - 31, n - 30, n - 12, n - 3, n - 2, n - 1, 0]:
+            nv = min(30, n - int(p))
+            N = 6000
+            base = ref[int(p) + rng.integers(0, nv, N), 0:2] - ref[int(p), 0:2]
+            q = base + rng.standard_normal((N, 2)) * (10.0 ** rng.uniform(-5, 0.3, N))[:, None]
+            pick, full, cert = _probe(emul, ref, p, q)
+            m = pick >= 0
+            assert np.array_equal(pick[m], full[m]), (name, int(p))
+            certified += int(m.sum())
+            for off in (0, 6):                       # queries around the apex and along the edges of each wedge
+                mx, my, k = (cert[off + 2 * i:off + 2 * i + 2].astype(np.float64) for i in range(3))
+                A = np.array([[mx[0], my[0]], [mx[1], my[1]]])
+                if not np.all(np.isfinite(k)) or abs(np.linalg.det(A)) < 1e-9:
+                    continue
+                z = np.linalg.solve(A, -k)
+                t = (10.0 ** rng.uniform(-7, 0.5, N) * rng.choice([-1, 1], N))[:, None]
+                which = rng.integers(0, 3, N)[:, None]
+                q = (z[None, :] + rng.standard_normal((N, 2)) * (10.0 ** rng.uniform(-9, -5, N))[:, None]
+                     + np.where(which == 0, t * np.array([-my[0], mx[0]]), 0.0)
+                     + np.where(which == 1, t * np.array([-my[1], mx[1]]), 0.0))
+                pick, full, _ = _probe(emul, ref, p, q)
+                m = pick >= 0
+                assert np.array_equal(pick[m], full[m]), (name, int(p), off)
+                certified += int(m.sum())
+    assert certified > 500000        # the test exercised the certificate, not only its refusals
+
+
+def test_certified_rollout_costs_are_bit_identical(emul, paths):
+    """Rollout costs with the shortcut on and off are the same floats, and on a tracking state most
+    lookups of a long horizon are certified (the window ends ~15 steps ahead of the arm)."""
+    with np.load(cases.HERE + "/closed_loop_c1.npz") as z:
+        cl = {k: z[k] for k in z.files}
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    for s, T in ((100, 30), (500, 100), (1000, 64), (1499, 40)):
+        K = 256
+        kw = cases.run_py_kwargs(ref, K, T)
+        c = mo.OracleMPPI(**kw)
+        prev = cl["u_new"][s - 1]
+        u = np.concatenate([prev[1:], np.repeat(prev[-1:], max(T - 29, 1), axis=0)], axis=0)[:T]
+        eps = mo.injected_noise(1000 + s, K, T, kw["sigma"])
+        hits = []
+        S_on, p_on = emul_costs(emul, c, cl["state"][s], eps, int(cl["prev_idx"][s, 0]), u=u, use_cert=True, hits=hits)
+        S_off, p_off = emul_costs(emul, c, cl["state"][s], eps, int(cl["prev_idx"][s, 0]), u=u, use_cert=False, hits=hits)
+        assert p_on == p_off and np.array_equal(S_on, S_off)
+        assert hits[1] == 0
+        if T >= 64:
+            assert hits[0] > 0.6 * K * T, (s, T, hits)
+    # a window cut short by the end of the path, and the arm at rest at the start of the path
+    for x0, p, T in ((cases.X0, 0, 50), (paths["trajectory1"][1987, 0:2].tolist() + [0.01, 0.01], 1985, 20)):
+        kw = cases.run_py_kwargs(ref, 128, T)
+        c = mo.OracleMPPI(**kw)
+        eps = mo.injected_noise(3, 128, T, kw["sigma"])
+        S_on, _ = emul_costs(emul, c, x0, eps, p, use_cert=True)
+        S_off, _ = emul_costs(emul, c, x0, eps, p, use_cert=False)
+        assert np.array_equal(S_on, S_off)

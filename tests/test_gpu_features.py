@@ -477,3 +477,73 @@ def test_batched_device_closed_loop_equals_single_environment_loops(paths):
     assert np.max(np.abs(log[-1, :, 0:4] - X)) <= 0.3
     np.testing.assert_array_equal(dev.prev_waypoints_idx >= np.array(rows), True)
     dev.close(); host.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# certified end-of-window shortcut of the nearest-waypoint lookups (search="certified", the default)
+# ---------------------------------------------------------------------------------------------
+def _tracking_state(cl, s, T):
+    prev = cl["u_new"][s - 1]
+    u = np.concatenate([prev[1:], np.repeat(prev[-1:], max(T - 29, 1), axis=0)], axis=0)[:T]
+    return cl["state"][s], u, int(cl["prev_idx"][s, 0])
+
+
+@pytest.mark.parametrize("K,T,s,noise", [
+    (32768, 100, 500, "philox"),       # constant-bank window, 2 samples per thread
+    (32768, 100, 1000, "injected"),    # same kernel family, noise read from HBM
+    (1000, 30, 100, "injected"),       # register window, partial last warp (1000 = 31 warps + 8 lanes)
+    (4096, 50, 1499, "philox"),
+    (64, 20, -1, "injected"),          # window truncated by the end of the path
+    (16384, 50, 0, "philox"),          # arm at rest at the start of the path: every sample falls behind row 0
+])
+def test_certified_search_is_bit_identical_to_the_full_search(paths, K, T, s, noise):
+    with np.load(cases.HERE + "/closed_loop_c1.npz") as z:
+        cl = {k: z[k] for k in z.files}
+    if s > 0:
+        x0, u, p = _tracking_state(cl, s, T)
+    elif s == 0:
+        x0, u, p = cases.X0, _u0(T), 0
+    else:
+        x0, u, p = paths["trajectory1"][1987, 0:2].tolist() + [0.01, 0.01], _u0(T), 1985
+    out = {}
+    for mode in ("certified", "full"):
+        eng = _engine(paths, K, T, search=mode, search_stats=True)
+        eps = eng.philox_noise(step=0) if noise == "injected" else None
+        eng.step(x0, u, p, eps)
+        S, w = (t[0].cpu().numpy().copy() for t in eng.last_costs())
+        out[mode] = (S, w, eng.out_u_new[0].copy(), eng.out_opt_traj[0].copy(), int(eng.out_new_idx[0]),
+                     eng.search_stats())
+        eng.close()
+    a, b = out["certified"], out["full"]
+    for i in range(4):
+        assert np.array_equal(a[i], b[i]), f"output {i} differs between search modes"
+    assert a[4] == b[4]
+    assert b[5]["certified"] == 0 and b[5]["lookups"] == a[5]["lookups"] > 0
+    if T >= 50:
+        assert a[5]["fraction"] > 0.6, a[5]      # most of a long horizon lies beyond the 30-row window
+
+
+def test_certified_search_batched_environments(paths):
+    """n_env > 1: every environment has its own window and certificate (step block in shared memory)."""
+    from mppi_robotarm_b200 import BatchedMPPIController
+    with np.load(cases.HERE + "/closed_loop_c1.npz") as z:
+        cl = {k: z[k] for k in z.files}
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    T, K, steps = 64, 512, (0, 100, 500, 1000, 1499)
+    kw = cases.run_py_kwargs(ref, K, T)
+    kw.pop("visualize_optimal_traj", None); kw.pop("visualze_sampled_trajs", None)
+    res = {}
+    for mode in ("certified", "full"):
+        b = BatchedMPPIController(len(steps), **kw, seed=4, search=mode, search_stats=True)
+        xs, us, ps = [], [], []
+        for s in steps:
+            x0, u, p = _tracking_state(cl, s, T) if s else (cases.X0, _u0(T), 0)
+            xs.append(x0); us.append(u); ps.append(p)
+        b.u_prev[...] = np.array(us)
+        b.prev_waypoints_idx[...] = ps
+        b.calc_control_input(np.array(xs))
+        res[mode] = (b.engine.last_costs()[0].cpu().numpy().copy(), b.engine.out_u_new.copy(), b.engine.search_stats())
+        b.close()
+    assert np.array_equal(res["certified"][0], res["full"][0])
+    assert np.array_equal(res["certified"][1], res["full"][1])
+    assert res["certified"][2]["fraction"] > 0.5 and res["full"][2]["certified"] == 0

@@ -173,6 +173,10 @@ int mppi_replay_end(MppiHandle* h, void* stream);
 /* Per-sample costs S (control.py:91-109) and un-normalised weights exp(-(S-rho_g)/lambda)
  * (control.py:297-314) of the last step: device float32 [n_env][K_local] each. */
 int mppi_last_costs(MppiHandle* h, const float** S_dev, const float** w_dev);
+/* The tables the prepare kernel built for environment `env` in the last step (tests / debugging), device
+ * memory: 64 B header (state, window origin and start) | 32 x 16 B window coefficients | 32 x 16 B reference
+ * rows | 16 x 16 B coefficient pairs | 64 B end-of-window certificate | T x 16 B step controls. */
+int mppi_step_block(MppiHandle* h, int32_t env, const void** dev_ptr, size_t* bytes);
 /* control.py:137-145 — trajectories of all samples under v[k, t-1] (index wrap included), for the
  * state / sequence / window of the last step.  traj_dev: float32 [n_env][K_local][T][4]. */
 int mppi_sampled_trajectories(MppiHandle* h, int32_t noise_mode, const float* eps_dev,

@@ -69,6 +69,7 @@ SYMBOLS = {
     "mppi_replay_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mppi_replay_end": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mppi_last_costs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "mppi_step_block": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "mppi_sampled_trajectories": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mppi_sampled_trajectories_subset": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                                    C.c_void_p, C.c_void_p]),

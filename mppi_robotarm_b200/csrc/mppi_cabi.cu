@@ -746,6 +746,15 @@ int mppi_last_costs(MppiHandle* h, const float** S_dev, const float** w_dev) {
     return MPPI_OK;
 }
 
+int mppi_step_block(MppiHandle* h, int32_t env, const void** dev_ptr, size_t* bytes) {
+    if (!h || !dev_ptr || !bytes) return MPPI_ERR_INVALID;
+    if (!h->have_step) return fail(h, MPPI_ERR_INVALID, "%s", "no step has run yet");
+    if (env < 0 || env >= h->cfg.n_env) return fail(h, MPPI_ERR_INVALID, "%s", "environment index out of range");
+    *dev_ptr = h->dev + h->ws.off_step_blocks + (size_t)env * h->dc.step_block_bytes;
+    *bytes = (size_t)h->dc.step_block_bytes;
+    return MPPI_OK;
+}
+
 int mppi_sampled_trajectories_subset(MppiHandle* h, int32_t noise_mode, const float* eps_dev, const int32_t* subset_dev,
                                      int32_t n_subset, float* traj_dev, void* stream) {
     if (!h) return MPPI_ERR_INVALID;

@@ -182,42 +182,82 @@ __device__ __forceinline__ double warp_min_d(double v) {
     return v;
 }
 
-// make_wedge() of mppi_math.cuh with one lane per window row (rx, ry = this lane's local row, valid for
-// lane < n).  Every lane returns the same coefficients.
-__device__ __forceinline__ void warp_wedge(double rx, double ry, int lane, int n, int target, double margin, double dom,
-                                           float (&ox)[2], float (&oy)[2], float (&ok)[2]) {
-    cert_disable(ox, oy, ok);
-    if (n < 2) return;                                        // (uniform)
-    const int other = target == 0 ? n - 1 : 0;
-    const double tx = __shfl_sync(0xffffffffu, rx, target), ty = __shfl_sync(0xffffffffu, ry, target);
-    double n0x = tx - __shfl_sync(0xffffffffu, rx, other), n0y = ty - __shfl_sync(0xffffffffu, ry, other);
-    const double n0 = sqrt(n0x * n0x + n0y * n0y);
-    if (!(n0 > 0.0)) return;
-    n0x /= n0; n0y /= n0;
-    const bool mine = lane < n && lane != target;
-    const double gx = tx - rx, gy = ty - ry;
-    const double along = gx * n0x + gy * n0y, across = n0x * gy - n0y * gx;
-    const bool bad = mine && (!(along > 0.05 * fabs(across)) || !(along > 0.0));
-    if (__any_sync(0xffffffffu, bad)) return;
-    const double sl = mine ? across / along : 0.0;
-    double smin = warp_min_d(mine ? sl : 1e300), smax = warp_max_d(mine ? sl : -1e300);
-    smin -= 1e-7 * (1.0 + smin * smin); smax += 1e-7 * (1.0 + smax * smax);
-    double mx[2], my[2];
-    const double s2[2] = { smin, smax };
+// FP64 reciprocal / reciprocal square root from the FP32 MUFU seed + two Newton steps (~1e-14 relative):
+// the wedge construction is a chain of divisions and square roots on the latency path of every control
+// step, and its results only feed quantities that carry >= 1e-7 of deliberate slack.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r = (double)__frcp_rn((float)x);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return fma(r, fma(-x, r, 1.0), r);
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double r = (double)rsqrtf((float)x);
+    r = r * fma(-0.5 * x * r, r, 1.5);
+    return r * fma(-0.5 * x * r, r, 1.5);
+}
+
+// make_wedge() of mppi_math.cuh for BOTH targets at once (w = 0: last row, w = 1: row 0; the two
+// dependency chains interleave), one lane per window row: (rx, ry) = this lane's local row, valid for
+// lane < n, n >= 2.  Every lane returns the same coefficients.
+__device__ __forceinline__ void warp_wedges(double rx, double ry, int lane, int n, double margin, double dom, EndCert& c) {
+    const int target[2] = { n - 1, 0 };
+    double tx[2], ty[2], n0x[2], n0y[2], gx[2], gy[2], sl[2];
+    bool ok[2], mine[2];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const double vx = n0x - s2[i] * n0y, vy = n0y + s2[i] * n0x, vn = sqrt(vx * vx + vy * vy);
-        mx[i] = vx / vn; my[i] = vy / vn;
+    for (int w = 0; w < 2; ++w) {
+        tx[w] = __shfl_sync(0xffffffffu, rx, target[w]); ty[w] = __shfl_sync(0xffffffffu, ry, target[w]);
     }
-    double bx = mx[0] + mx[1], by = my[0] + my[1];
-    const double bn = sqrt(bx * bx + by * by);
-    if (!(bn > 1e-3)) return;
-    bx /= bn; by /= bn;
-    const double g2 = gx * gx + gy * gy, ng = bx * gx + by * gy;
-    if (__any_sync(0xffffffffu, mine && !(ng > 0.0))) return;
-    const double tau = warp_max_d(mine ? fmax((margin - g2) / (2.0 * ng), 0.0) : 0.0);
-    if (!(tau <= kCertMaxTau)) return;
-    cert_finish(tx + tau * bx, ty + tau * by, mx, my, dom, ox, oy, ok);
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        n0x[w] = tx[w] - tx[1 - w]; n0y[w] = ty[w] - ty[1 - w];          // target minus the other end (not normalised:
+        mine[w] = lane < n && lane != target[w];                         //  the slopes below are ratios)
+        gx[w] = tx[w] - rx; gy[w] = ty[w] - ry;
+        const double along = gx[w] * n0x[w] + gy[w] * n0y[w], across = n0x[w] * gy[w] - n0y[w] * gx[w];
+        const bool bad = mine[w] && (!(along > 0.05 * fabs(across)) || !(along > 0.0));
+        ok[w] = !__any_sync(0xffffffffu, bad) && (n0x[w] * n0x[w] + n0y[w] * n0y[w] > 0.0);
+        sl[w] = mine[w] && along > 0.0 ? across * fast_rcp(along) : 0.0;
+    }
+    double smin[2], smax[2];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) { smin[w] = mine[w] ? sl[w] : 1e300; smax[w] = mine[w] ? sl[w] : -1e300; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            smin[w] = fmin(smin[w], __shfl_xor_sync(0xffffffffu, smin[w], o));
+            smax[w] = fmax(smax[w], __shfl_xor_sync(0xffffffffu, smax[w], o));
+        }
+    }
+    double mx[2][2], my[2][2], bx[2], by[2], tau[2];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        smin[w] -= 2e-7 * (1.0 + smin[w] * smin[w]); smax[w] += 2e-7 * (1.0 + smax[w] * smax[w]);   // widen the cone
+        const double s2[2] = { smin[w], smax[w] };
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const double vx = n0x[w] - s2[i] * n0y[w], vy = n0y[w] + s2[i] * n0x[w];
+            const double inv = fast_rsqrt(vx * vx + vy * vy);
+            mx[w][i] = vx * inv; my[w][i] = vy * inv;
+        }
+        bx[w] = mx[w][0] + mx[w][1]; by[w] = my[w][0] + my[w][1];       // bisector, not normalised: z = r_t + tau * b
+        const double bn2 = bx[w] * bx[w] + by[w] * by[w];
+        ok[w] = ok[w] && bn2 > 1e-6;
+        const double g2 = gx[w] * gx[w] + gy[w] * gy[w], ng = bx[w] * gx[w] + by[w] * gy[w];
+        ok[w] = ok[w] && !__any_sync(0xffffffffu, mine[w] && !(ng > 0.0));
+        tau[w] = mine[w] && ng > 0.0 ? fmax(0.5 * (margin - g2) * fast_rcp(ng), 0.0) * 1.000001 : 0.0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int w = 0; w < 2; ++w) tau[w] = fmax(tau[w], __shfl_xor_sync(0xffffffffu, tau[w], o));
+    }
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        const double bn2 = bx[w] * bx[w] + by[w] * by[w];
+        ok[w] = ok[w] && (tau[w] * tau[w] * bn2 <= kCertMaxTau * kCertMaxTau);
+    }
+    if (ok[0]) cert_finish(tx[0] + tau[0] * bx[0], ty[0] + tau[0] * by[0], mx[0], my[0], dom, c.lx, c.ly, c.lk);
+    if (ok[1]) cert_finish(tx[1] + tau[1] * bx[1], ty[1] + tau[1] * by[1], mx[1], my[1], dom, c.fx, c.fy, c.fk);
 }
 
 // ================================================================================================
@@ -333,11 +373,10 @@ __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, 
             if (!(cfg.flags & 16)) {                          // MPPI_FLAG_FULL_SEARCH switches the shortcut off
                 if (nv == 1) { c.fk[0] = c.fk[1] = 1.0f; }
                 else if (nv >= 2) {
-                    const double amax = warp_max_d(2.0 * fabs(rx)), bmax = warp_max_d(2.0 * fabs(ry));
-                    const double cmax = warp_max_d(rx * rx + ry * ry);
-                    const double margin = cert_margin(amax, bmax, cmax, 1.0001 * dom);
-                    warp_wedge(rx, ry, lane, nv, nv - 1, margin, 1.0001 * dom, c.lx, c.ly, c.lk);
-                    warp_wedge(rx, ry, lane, nv, 0, margin, 1.0001 * dom, c.fx, c.fy, c.fk);
+                    const double cmax = warp_max_d(rx * rx + ry * ry);            // > 0 for nv >= 2 unless all rows coincide
+                    const double ab = 2.0000001 * cmax * fast_rsqrt(fmax(cmax, 1e-300));  // |a_j|, |b_j| <= 2 sqrt(cmax)
+                    const double margin = cert_margin(ab, ab, cmax, 1.0001 * dom);
+                    warp_wedges(rx, ry, lane, nv, margin, 1.0001 * dom, c);
                 }
             }
             if (lane == 0) *sb.cert = c;

@@ -290,7 +290,7 @@ static_assert(sizeof(StepHeader) == 64, "header is 64 bytes");
 // spanned by the two extreme directions m_0, m_1; for p = z + s with s.m_0 >= 0 and s.m_1 >= 0 every
 // s.g_j >= 0, hence d_j - d_L >= |g_j|^2 + 2 tau n.g_j at the apex z = r_L + tau n, and tau is chosen
 // so that this is >= the rounding margin for every j.
-struct EndCert {               // 64 bytes of a step block
+struct alignas(16) EndCert {   // 64 bytes of a step block
     float lx[2], ly[2], lk[2]; // wedge inside the cell of the last valid row
     float fx[2], fy[2], fk[2]; // wedge inside the cell of row 0
     float dom;                 // the margins hold for |x'|, |y'| <= dom
@@ -304,8 +304,22 @@ static_assert(sizeof(EndCert) == 64, "certificate block is 64 bytes");
 struct CertTest { float wl, wf; bool in_dom; };
 MPPI_HD CertTest cert_test(const EndCert& c, float xl, float yl) {
     CertTest t;
+#if defined(__CUDA_ARCH__) && !defined(MPPI_CERT_SCALAR)
+    // the two half-planes of a wedge as one packed fma.rn.f32x2 chain (same roundings as the scalar form)
+    const unsigned long long x2 = ((unsigned long long)__float_as_uint(xl) << 32) | __float_as_uint(xl);
+    const unsigned long long y2 = ((unsigned long long)__float_as_uint(yl) << 32) | __float_as_uint(yl);
+    const unsigned long long* q = reinterpret_cast<const unsigned long long*>(&c);   // lx, ly, lk, fx, fy, fk pairs
+    unsigned long long a, b;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(a) : "l"(q[1]), "l"(y2), "l"(q[2]));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(a) : "l"(q[0]), "l"(x2), "l"(a));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(b) : "l"(q[4]), "l"(y2), "l"(q[5]));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(b) : "l"(q[3]), "l"(x2), "l"(b));
+    t.wl = fminf(__uint_as_float((unsigned)a), __uint_as_float((unsigned)(a >> 32)));
+    t.wf = fminf(__uint_as_float((unsigned)b), __uint_as_float((unsigned)(b >> 32)));
+#else
     t.wl = fminf(fma_(c.lx[0], xl, fma_(c.ly[0], yl, c.lk[0])), fma_(c.lx[1], xl, fma_(c.ly[1], yl, c.lk[1])));
     t.wf = fminf(fma_(c.fx[0], xl, fma_(c.fy[0], yl, c.fk[0])), fma_(c.fx[1], xl, fma_(c.fy[1], yl, c.fk[1])));
+#endif
     t.in_dom = fmaxf(fabsf(xl), fabsf(yl)) <= c.dom;               // false for NaN
     return t;
 }
@@ -390,12 +404,13 @@ MPPI_HD void make_end_cert(const double (*rows)[2], int n_valid, double reach, d
     cert_disable(c.lx, c.ly, c.lk); cert_disable(c.fx, c.fy, c.fk);
     if (!enabled || n_valid < 1) return;
     if (n_valid == 1) { c.fk[0] = c.fk[1] = 1.0f; return; }       // a one-row window: the search can only return row 0
-    double amax = 0, bmax = 0, cmax = 0;
+    double cmax = 0;
     for (int j = 0; j < n_valid; ++j) {
-        const double a = 2.0 * fabs(rows[j][0]), b = 2.0 * fabs(rows[j][1]), cc = rows[j][0] * rows[j][0] + rows[j][1] * rows[j][1];
-        amax = a > amax ? a : amax; bmax = b > bmax ? b : bmax; cmax = cc > cmax ? cc : cmax;
+        const double cc = rows[j][0] * rows[j][0] + rows[j][1] * rows[j][1];
+        cmax = cc > cmax ? cc : cmax;
     }
-    const double margin = cert_margin(amax, bmax, cmax, 1.0001 * dom);
+    const double ab = 2.0000001 * sqrt(cmax);                 // |a_j|, |b_j| <= 2 sqrt(cmax)
+    const double margin = cert_margin(ab, ab, cmax, 1.0001 * dom);
     make_wedge(rows, n_valid, n_valid - 1, margin, 1.0001 * dom, c.lx, c.ly, c.lk);
     make_wedge(rows, n_valid, 0, margin, 1.0001 * dom, c.fx, c.fy, c.fk);
 }

@@ -342,6 +342,14 @@ class MppiEngine:
             return self._ws[start:start + 4 * n].view(torch.float32).reshape(self.n_env, self.K_local)
         return as_tensor(ps.value), as_tensor(pw.value)
 
+    def step_block(self, env=0):
+        """Raw bytes (uint8 array) of the tables the prepare kernel built for ``env`` in the last step."""
+        ptr, n = C.c_void_p(), C.c_size_t()
+        _cabi.check(self.lib.mppi_step_block(self.handle, int(env), C.byref(ptr), C.byref(n)), self.handle, "mppi_step_block")
+        self.stream.synchronize()
+        start = ptr.value - self._ws.data_ptr()
+        return self._ws[start:start + n.value].cpu().numpy()
+
     def sampled_trajectories(self):
         """control.py:137-145 for the last step: device tensor [n_env, K_local, T, 4] float32."""
         torch = self.torch

@@ -33,3 +33,18 @@ def pytest_collection_modifyitems(config, items):
 def paths():
     from tests.golden import cases
     return cases.load_paths()
+
+
+@pytest.fixture(scope="session")
+def emul():
+    """tests/emul: mppi_math.cuh compiled for the host (test infrastructure, rebuilt when stale)."""
+    import ctypes as C
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    so, src = os.path.join(here, "emul", "_emul.so"), os.path.join(here, "emul", "emul.cpp")
+    hdr = os.path.join(ROOT, "mppi_robotarm_b200", "csrc", "mppi_math.cuh")
+    if not os.path.isfile(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, src], check=True)
+    lib = C.CDLL(so)
+    lib.emul_rollout_costs.restype = C.c_int
+    return lib

@@ -86,6 +86,21 @@ void emul_cert_probe(const double* ref, int n_rows, int p, double reach, const f
     }
 }
 
+// The same probe for a certificate that was built elsewhere (the prepare kernel on the GPU): cert_in =
+// the 64 certificate bytes of a step block.
+void emul_cert_probe_given(const double* ref, int n_rows, int p, const float* cert_in, const float* xy, int n,
+                           int* pick, int* full) {
+    WinRegs win; RefRow rows[kWindowPad]; WinEntry tab[kWindowPad];
+    for (int j = 0; j < kWindowPad; ++j) make_window_row(ref, n_rows, p, j, tab[j], rows[j]);
+    win.load(tab);
+    EndCert cert;
+    memcpy(&cert, cert_in, sizeof(cert));
+    for (int i = 0; i < n; ++i) {
+        pick[i] = cert_pick(cert, xy[2 * i], xy[2 * i + 1]);
+        full[i] = nearest_candidate(win, xy[2 * i], xy[2 * i + 1]);
+    }
+}
+
 void emul_sincos(const float* x, int n, float* s, float* c) { for (int i = 0; i < n; ++i) sincos_(x[i], s[i], c[i]); }
 
 void emul_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {

@@ -17,15 +17,6 @@ SRC = os.path.join(HERE, "emul", "emul.cpp")
 HDR = os.path.join(os.path.dirname(HERE), "mppi_robotarm_b200", "csrc", "mppi_math.cuh")
 
 
-@pytest.fixture(scope="module")
-def emul():
-    if not os.path.isfile(SO) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
-        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", SO, SRC], check=True)
-    lib = C.CDLL(SO)
-    lib.emul_rollout_costs.restype = C.c_int
-    return lib
-
-
 def dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 

@@ -525,7 +525,7 @@ def test_certified_search_is_bit_identical_to_the_full_search(paths, K, T, s, no
 
 def test_certified_search_batched_environments(paths):
     """n_env > 1: every environment has its own window and certificate (step block in shared memory)."""
-    from mppi_robotarm_b200 import BatchedMPPIController
+    from mppi_robotarm_b200.batched import BatchedMPPIController
     with np.load(cases.HERE + "/closed_loop_c1.npz") as z:
         cl = {k: z[k] for k in z.files}
     ref = cases.ref_path_for(paths, "xydq_circle.txt")
@@ -547,3 +547,59 @@ def test_certified_search_batched_environments(paths):
     assert np.array_equal(res["certified"][0], res["full"][0])
     assert np.array_equal(res["certified"][1], res["full"][1])
     assert res["certified"][2]["fraction"] > 0.5 and res["full"][2]["certified"] == 0
+
+
+def test_device_built_certificates_are_sound(paths, emul):
+    """The certificates the prepare kernel builds (warp-parallel FP64, fast reciprocals) are read back from
+    the step block and probed on the host against the exact FP32 search: no certified query may disagree.
+    They must also be (nearly) the certificates of the serial construction the CPU tests cover."""
+    import ctypes as C
+    rng = np.random.default_rng(11)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))        # noqa: E731
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))          # noqa: E731
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))       # noqa: E731
+    off = 64 + 32 * 32 + 16 * 16
+    n_armed = 0
+    for name in ("xydq_circle", "trajectory1", "xydq"):
+        ref = np.ascontiguousarray(paths[name][:, 0:4], dtype=np.float64)
+        n = ref.shape[0]
+        eng = _engine(paths, 64, 8, ref_path=ref)
+        for p in list(rng.integers(0, n - 31, 10)) + [n - 31, n - 12, n - 3, n - 2]:
+            p = int(p)
+            # an arm state whose end effector sits on waypoint p (so the window starts exactly there)
+            x, y = ref[p, 0], ref[p, 1]
+            q2 = -np.arccos(np.clip((x * x + y * y - 2.0) / 2.0, -1, 1))
+            q1 = np.arctan2(y, x) - np.arctan2(np.sin(q2), 1.0 + np.cos(q2))
+            eng.step([q1, q2, 0.0, 0.0], _u0(8), p, None)
+            blk = eng.step_block(0)
+            start = int(blk[24:28].view(np.int32)[0])
+            cert = blk[off:off + 64].view(np.float32).copy()
+            nv = min(30, n - start)
+            N = 20000
+            base = ref[start + rng.integers(0, nv, N), 0:2] - ref[start, 0:2]
+            q = base + rng.standard_normal((N, 2)) * (10.0 ** rng.uniform(-5, 0.3, N))[:, None]
+            for o in (0, 6):                          # plus queries hugging each wedge's apex and edges
+                mx, my, k = (cert[o + 2 * i:o + 2 * i + 2].astype(np.float64) for i in range(3))
+                A = np.array([[mx[0], my[0]], [mx[1], my[1]]])
+                if not np.all(np.isfinite(k)) or abs(np.linalg.det(A)) < 1e-9:
+                    continue
+                n_armed += 1
+                z = np.linalg.solve(A, -k)
+                t = (10.0 ** rng.uniform(-7, 0.5, N) * rng.choice([-1, 1], N))[:, None]
+                which = rng.integers(0, 3, N)[:, None]
+                q = np.concatenate([q, z[None, :] + rng.standard_normal((N, 2)) * (10.0 ** rng.uniform(-9, -5, N))[:, None]
+                                    + np.where(which == 0, t * np.array([-my[0], mx[0]]), 0.0)
+                                    + np.where(which == 1, t * np.array([-my[1], mx[1]]), 0.0)])
+            xy = np.ascontiguousarray(q.astype(np.float32))
+            pick, full = np.zeros(len(xy), np.int32), np.zeros(len(xy), np.int32)
+            emul.emul_cert_probe_given(dp(ref), n, start, fp(cert), fp(xy), len(xy), ip(pick), ip(full))
+            m = pick >= 0
+            assert np.array_equal(pick[m], full[m]), (name, p)
+            serial = np.zeros(16, np.float32)
+            emul.emul_cert_probe(dp(ref), n, start, C.c_double(2.0), fp(xy), 1, ip(pick), ip(full), fp(serial))
+            fin = np.isfinite(serial[:13]) & np.isfinite(cert[:13])
+            assert np.array_equal(np.isfinite(serial[:13]), np.isfinite(cert[:13])), (name, p)
+            np.testing.assert_allclose(cert[:13][fin], serial[:13][fin], rtol=2e-4, atol=2e-6)
+            assert cert[13:14].view(np.int32)[0] == serial[13:14].view(np.int32)[0] == nv - 1
+        eng.close()
+    assert n_armed > 40

@@ -7,7 +7,7 @@ python bench.py --steps 20 --warmup 3 > gpurun_out/bench_$tag.log 2>&1; echo rc=
 P="python tools/profile_step.py --K 1048576 --T 100 --steps 3"
 $P > gpurun_out/plain_$tag.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:mppi_rollout -s 2 -c 1 -f -o gpurun_out/prof_rollout_$tag $P > gpurun_out/ncu_$tag.log 2>&1
-B="python bench.py --steps 2 --warmup 3 --no-latency --no-cpu --no-injected --no-batched"
+B="python bench.py --steps 2 --warmup 3 --no-latency --no-cpu --no-injected --no-batched --no-search"
 $B > gpurun_out/plain_bench_$tag.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches_$tag.csv $B > gpurun_out/ncu_bench_$tag.log 2>&1
 true

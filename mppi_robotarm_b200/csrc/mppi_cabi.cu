@@ -102,7 +102,8 @@ bool valid_cfg(const MppiConfig* c, const char** why) {
 // samples per thread of the rollout kernel: 2 when there is enough work to fill the GPU that way
 bool pick_const_window(const MppiConfig* c) {
     // constant-bank window: single environment and enough work to pay for the extra copy node
-    return (c->n_env == 1) && ((long long)c->K_local * c->T >= (1ll << 21)) && getenv("MPPI_NO_CONST_WINDOW") == nullptr;
+    return (c->n_env == 1) && ((long long)c->K_local * c->T >= (1ll << 21)) && !(c->flags & MPPI_FLAG_DYNAMICS_F1) &&
+           getenv("MPPI_NO_CONST_WINDOW") == nullptr;
 }
 
 // Samples per thread of the rollout kernel.  Two samples per thread cost ~3 % fewer instructions per
@@ -287,10 +288,15 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
             CU(h, cudaMemcpyToSymbolAsync(c_window, step_blocks + 64, kStepBlockFixed - 64, 0,
                                           cudaMemcpyDeviceToDevice, s));
         }
-#define MPPI_LAUNCH_ROLL(NOISE, CW, NS_) \
-        mppi_rollout_sm100a<NOISE, CW, NS_><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, ph ? nullptr : eps_dev, S, bmin, \
-                                                                                     (unsigned long long*)(ws + h->ws.off_stats))
-        if (h->const_window) {
+#define MPPI_LAUNCH_ROLL_D(NOISE, CW, NS_, DYN) \
+        mppi_rollout_sm100a<NOISE, CW, NS_, DYN><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, ph ? nullptr : eps_dev, S, bmin, \
+                                                                                          (unsigned long long*)(ws + h->ws.off_stats))
+#define MPPI_LAUNCH_ROLL(NOISE, CW, NS_) MPPI_LAUNCH_ROLL_D(NOISE, CW, NS_, 0)
+        if (dc.flags & MPPI_FLAG_DYNAMICS_F1) {
+            // the reference's alternative rollout model: register-window kernels only (pick_const_window is off)
+            if (h->ns == 2) { if (ph) MPPI_LAUNCH_ROLL_D(0, false, 2, 1); else MPPI_LAUNCH_ROLL_D(1, false, 2, 1); }
+            else { if (ph) MPPI_LAUNCH_ROLL_D(0, false, 1, 1); else MPPI_LAUNCH_ROLL_D(1, false, 1, 1); }
+        } else if (h->const_window) {
             if (h->ns == 2) { if (ph) MPPI_LAUNCH_ROLL(0, true, 2); else MPPI_LAUNCH_ROLL(1, true, 2); }
             else { if (ph) MPPI_LAUNCH_ROLL(0, true, 1); else MPPI_LAUNCH_ROLL(1, true, 1); }
             if (!capturing) { int rc = const_release(h, s); if (rc != MPPI_OK) return rc; }
@@ -299,6 +305,7 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
             else { if (ph) MPPI_LAUNCH_ROLL(0, false, 1); else MPPI_LAUNCH_ROLL(1, false, 1); }
         }
 #undef MPPI_LAUNCH_ROLL
+#undef MPPI_LAUNCH_ROLL_D
     }
     if (timed) CU(h, cudaEventRecord(h->tev[2], s));
     if (noise_mode == MPPI_NOISE_PHILOX) {

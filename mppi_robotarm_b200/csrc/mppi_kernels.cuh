@@ -481,7 +481,7 @@ __device__ __forceinline__ const EndCert& cert_of(const StepBlockView& sb) {
     if constexpr (CW) return c_window.cert; else return *sb.cert;
 }
 
-template <int NOISE, bool CONSTWIN, int kNS>
+template <int NOISE, bool CONSTWIN, int kNS, int DYN = 0>
 __global__ void __launch_bounds__(kRollThreads, CONSTWIN ? MPPI_ROLL_MIN_BLOCKS_CONST : (kNS == 1 ? 3 : 2))
 mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const char* __restrict__ step_blocks,
                     const float* __restrict__ eps, float* __restrict__ S_out, float* __restrict__ block_min,
@@ -529,12 +529,12 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
                 nz[s].nc = cfg.noise; nz[s].nc.step = (uint32_t)(*step_ctr); nz[s].env = (uint32_t)e;
                 nz[s].k = (uint32_t)(cfg.k_offset + kl[s]);
             }
-            rollout_cost_n<kNS>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
+            rollout_cost_n<kNS, DYN>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
         } else {
             InjectedNoise nz[kNS];
 #pragma unroll
             for (int s = 0; s < kNS; ++s) nz[s].row = (const float2*)eps + ((size_t)e * cfg.K_local + kl[s]) * T;
-            rollout_cost_n<kNS>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
+            rollout_cost_n<kNS, DYN>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
         }
 #pragma unroll
         for (int s = 0; s < kNS; ++s) {
@@ -974,7 +974,8 @@ mppi_finalize_sm100a(DevCfg cfg, DevIo io, const double* gathered, int world, Pe
             ArmState st; arm_init(st, (float)x0[0], (float)x0[1], (float)x0[2], (float)x0[3]);
             for (int t = 0; t < T; ++t) {
                 const int tc = t == 0 ? T - 1 : t - 1;
-                arm_step(st, cfg.arm, (float)unew[2 * tc], (float)unew[2 * tc + 1]);
+                if (cfg.flags & 32) arm_step<1>(st, cfg.arm, (float)unew[2 * tc], (float)unew[2 * tc + 1]);   // MPPI_FLAG_DYNAMICS_F1
+                else arm_step<0>(st, cfg.arm, (float)unew[2 * tc], (float)unew[2 * tc + 1]);
                 float4* o = (float4*)(tr + 8 * t);
                 o[0] = make_float4(st.q1, st.q2, st.d1, st.d2);
                 o[1] = make_float4(st.kq1, st.kq2, st.kd1, st.kd2);
@@ -1024,7 +1025,8 @@ mppi_sampled_traj_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, cons
             n1 = v.x; n2 = v.y;
         }
         const StepCtl c = sb.ctl[tc];
-        arm_step(st, cfg.arm, fma_(um, c.u1, n1), fma_(um, c.u2, n2));
+        if (cfg.flags & 32) arm_step<1>(st, cfg.arm, fma_(um, c.u1, n1), fma_(um, c.u2, n2));
+        else arm_step<0>(st, cfg.arm, fma_(um, c.u1, n1), fma_(um, c.u2, n2));
         out[t] = make_float4(st.q1, st.q2, st.d1, st.d2);
     }
 }

@@ -121,7 +121,25 @@ MPPI_HD void kahan_(float& acc, float& comp, float y) {
 }
 
 // One integration step (control.py:241-259) under control (v1, v2).
+// DYN = 0: the arm model _F.  DYN = 1: the reference's other rollout model _F1 (control.py:265-295),
+// which forms u = M v + C dq (gravity dropped, control.py:281-284) and solves ddq = M^-1 (u - C dq):
+// ddq = v up to FP64 rounding, so the input is applied as the joint acceleration.
+template <int DYN = 0>
 MPPI_HD void arm_step(ArmState& st, const ArmF& A, float v1, float v2) {
+    if (DYN == 1) {
+#ifndef MPPI_NO_KAHAN
+        kahan_(st.d1, st.kd1, fma_(v1, A.dt, -st.kd1));
+        kahan_(st.d2, st.kd2, fma_(v2, A.dt, -st.kd2));
+        kahan_(st.q1, st.kq1, fma_(st.d1, A.dt, -st.kq1));
+        kahan_(st.q2, st.kq2, fma_(st.d2, A.dt, -st.kq2));
+#else
+        st.d1 = fma_(v1, A.dt, st.d1); st.d2 = fma_(v2, A.dt, st.d2);
+        st.q1 = fma_(st.d1, A.dt, st.q1); st.q2 = fma_(st.d2, A.dt, st.q2);
+#endif
+        sincos_(st.q1, st.s1, st.c1);
+        sincos_(add_(st.q1, st.q2), st.s12, st.c12);
+        return;
+    }
     // cos/sin of q2 = (q1+q2) - q1 by the angle-difference identity
     float c2 = fma_(st.c12, st.c1, mul_(st.s12, st.s1));
     float s2 = fma_(st.s12, st.c1, -mul_(st.c12, st.s1));
@@ -505,7 +523,7 @@ MPPI_HD int nearest_wp(const Win& win, const EndCert& cert, float xl, float yl, 
 
 // NS samples advance in lockstep inside one thread: they share the window registers, the per-step
 // constants and the loop overhead, and give the scheduler NS independent instruction streams.
-template <int NS, class Win, class Noise>
+template <int NS, int DYN = 0, class Win, class Noise>
 MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
                             const Win& win, const EndCert& cert, const RefRow* rows, const StepCtl* ctl,
                             int T, const float (&um)[NS], Noise (&noise)[NS], float (&S_out)[NS], int& hits) {
@@ -534,7 +552,7 @@ MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int s = 0; s < NS; ++s) arm_step(st[s], A, v1[s], v2[s]);
+        for (int s = 0; s < NS; ++s) arm_step<DYN>(st[s], A, v1[s], v2[s]);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -566,14 +584,14 @@ MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
         S_out[s] = add_(S[s], sub_(wsq(W.t0, W.t1, W.t2, W.t3, ex[s], ey[s], e1[s], e2[s]), kS[s]));
 }
 
-template <class Win, class Noise>
+template <int DYN = 0, class Win, class Noise>
 MPPI_HD float rollout_cost(const StepHeader& hd, const ArmF& A, const CostW& W,
                            const Win& win, const EndCert& cert, const RefRow* rows, const StepCtl* ctl,
                            int T, float um, Noise& noise, int& hits) {
     const float ums[1] = { um };
     float out[1];
     Noise (&nz)[1] = reinterpret_cast<Noise (&)[1]>(noise);
-    rollout_cost_n<1>(hd, A, W, win, cert, rows, ctl, T, ums, nz, out, hits);
+    rollout_cost_n<1, DYN>(hd, A, W, win, cert, rows, ctl, T, ums, nz, out, hits);
     return out[0];
 }
 

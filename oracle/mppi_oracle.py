@@ -56,6 +56,7 @@ class OracleMPPI:
     visualize_optimal_traj: bool = True
     visualze_sampled_trajs: bool = False
     smoother: str = "median"          # "median" = control.py:122; "average" = control.py:329-344; "none"
+    dynamics: str = "F"               # "F" = control.py:234-263; "F1" = control.py:265-295 (feedback-linearised)
     arm: dict = field(default_factory=default_arm_params)
     cost_l1: float = 1.0      # control.py:55
     cost_l2: float = 1.0      # control.py:56
@@ -116,9 +117,29 @@ def arm_accel(q1, q2, d1, d2, v1, v2, arm):
     return (M22 * b1 - M12 * b2) / det, (M11 * b2 - M12 * b1) / det
 
 
-def arm_step(q1, q2, d1, d2, v1, v2, arm, dt):
+def arm_accel_f1(q1, q2, d1, d2, v1, v2, arm):
+    """control.py:265-290 (``_F1``): the input is turned into a torque u = M v + C dq + G with G = 0
+    (control.py:281-284) and pushed through the same ddq = M^-1 (u - C dq - G) — i.e. ddq = v up to FP64
+    rounding.  Restated operation by operation so the rounding is the reference's."""
+    m1, m2, l1, l2, lc1, lc2 = (arm[k] for k in ("m1", "m2", "l1", "l2", "lc1", "lc2"))
+    c2 = np.cos(q2)
+    M11 = m1 * lc1 ** 2 + l1 + m2 * (l1 ** 2 + lc2 ** 2 + 2 * l1 * lc2 * c2) + l2
+    M22 = m2 * lc2 ** 2 + l2
+    M12 = m2 * l1 * lc2 * c2 + m2 * lc2 ** 2 + l2
+    h = m2 * l1 * lc2 * np.sin(q2)
+    cd1 = (-h * d2) * d1 + (-h * d1 - h * d2) * d2            # C.dot(dq)
+    cd2 = (h * d1) * d1 + 0.0 * d2
+    u1 = (M11 * v1 + M12 * v2) + cd1 + 0.0
+    u2 = (M12 * v1 + M22 * v2) + cd2 + 0.0
+    b1 = u1 - cd1 - 0.0
+    b2 = u2 - cd2 - 0.0
+    det = M11 * M22 - M12 * M12
+    return (M22 * b1 - M12 * b2) / det, (M11 * b2 - M12 * b1) / det
+
+
+def arm_step(q1, q2, d1, d2, v1, v2, arm, dt, dynamics="F"):
     """control.py:253-259: dq += ddq*dt, then q += (new dq)*dt."""
-    a1, a2 = arm_accel(q1, q2, d1, d2, v1, v2, arm)
+    a1, a2 = (arm_accel if dynamics == "F" else arm_accel_f1)(q1, q2, d1, d2, v1, v2, arm)
     d1 = d1 + a1 * dt
     d2 = d2 + a2 * dt
     return q1 + d1 * dt, q2 + d2 * dt, d1, d2
@@ -210,13 +231,13 @@ def _visual_rollouts(c, x0, u, v):
     if c.visualize_optimal_traj:
         s = tuple(float(a) for a in x0)
         for t in range(T):
-            s = arm_step(*s, u[t - 1, 0], u[t - 1, 1], c.arm, c.delta_t)
+            s = arm_step(*s, u[t - 1, 0], u[t - 1, 1], c.arm, c.delta_t, c.dynamics)
             opt[t] = s
     if c.visualze_sampled_trajs:
         samp = np.zeros((K, T, 4))
         s = tuple(np.full(K, float(a)) for a in x0)
         for t in range(T):
-            s = arm_step(*s, v[:, t - 1, 0], v[:, t - 1, 1], c.arm, c.delta_t)
+            s = arm_step(*s, v[:, t - 1, 0], v[:, t - 1, 1], c.arm, c.delta_t, c.dynamics)
             samp[:, t, :] = np.stack(s, axis=1)
     else:
         samp = np.broadcast_to(0.0, (K, T, 4))      # reference allocates zeros (control.py:137)
@@ -277,7 +298,7 @@ def step_loops(c: OracleMPPI, observed_x, eps) -> dict:
                 v[k, t] = u[t] + eps[k, t]
             else:
                 v[k, t] = eps[k, t]
-            s = arm_step(*s, v[k, t, 0], v[k, t, 1], c.arm, c.delta_t)
+            s = arm_step(*s, v[k, t, 0], v[k, t, 1], c.arm, c.delta_t, c.dynamics)
             S[k] += float(tracking_cost(*s, win, c.stage_cost_weight, c.cost_l1, c.cost_l2)) \
                 + c.param_gamma * u[t] @ sig_inv @ v[k, t]
         S[k] += float(tracking_cost(*s, win, c.terminal_cost_weight, c.cost_l1, c.cost_l2))
@@ -297,7 +318,7 @@ def step_vectorized(c: OracleMPPI, observed_x, eps) -> dict:
     s = tuple(np.full(K, float(a)) for a in x0)
     S = np.zeros(K)
     for t in range(T):
-        s = arm_step(*s, v[:, t, 0], v[:, t, 1], c.arm, c.delta_t)
+        s = arm_step(*s, v[:, t, 0], v[:, t, 1], c.arm, c.delta_t, c.dynamics)
         ctrl = c.param_gamma * ((u[t] @ sig_inv) @ v[:, t, :].T)
         S += tracking_cost(*s, win, c.stage_cost_weight, c.cost_l1, c.cost_l2) + ctrl
     S += tracking_cost(*s, win, c.terminal_cost_weight, c.cost_l1, c.cost_l2)
@@ -318,7 +339,7 @@ def rollout_costs(c: OracleMPPI, x0, eps, prev_idx=None, u=None) -> np.ndarray:
     s = tuple(np.full(K, float(a)) for a in x0)
     S = np.zeros(K)
     for t in range(T):
-        s = arm_step(*s, v[:, t, 0], v[:, t, 1], c.arm, c.delta_t)
+        s = arm_step(*s, v[:, t, 0], v[:, t, 1], c.arm, c.delta_t, c.dynamics)
         S += tracking_cost(*s, win, c.stage_cost_weight, c.cost_l1, c.cost_l2) \
             + c.param_gamma * ((u[t] @ sig_inv) @ v[:, t, :].T)
     S += tracking_cost(*s, win, c.terminal_cost_weight, c.cost_l1, c.cost_l2)

@@ -18,7 +18,7 @@ extern "C" {
 int emul_rollout_costs(const double* ref, int n_rows, int prev_idx, const double* x0, const double* u_prev,
                        int K, int T, int n_exploit, double dt, double gamma, const double* sig_inv,
                        const double* ws, const double* wt, const double* arm, double cl1, double cl2,
-                       const float* eps, float* S_out, int use_cert, long long* hits_out) {
+                       const float* eps, float* S_out, int use_cert, long long* hits_out, int dynamics_f1) {
     // waypoint update, FP64 (control.py:75, 200-232)
     double x = cl1 * cos(x0[0]) + cl2 * cos(x0[0] + x0[1]);
     double y = cl1 * sin(x0[0]) + cl2 * sin(x0[0] + x0[1]);
@@ -58,7 +58,9 @@ int emul_rollout_costs(const double* ref, int n_rows, int prev_idx, const double
     for (int k = 0; k < K; ++k) {
         EpsArray n{ eps + (size_t)k * T * 2, T };
         int hits = 0;
-        S_out[k] = rollout_cost(hd, A, W, win, cert, rows, ctl.data(), T, k < n_exploit ? 1.f : 0.f, n, hits);
+        const float um = k < n_exploit ? 1.f : 0.f;
+        S_out[k] = dynamics_f1 ? rollout_cost<1>(hd, A, W, win, cert, rows, ctl.data(), T, um, n, hits)
+                               : rollout_cost<0>(hd, A, W, win, cert, rows, ctl.data(), T, um, n, hits);
         hits_total += hits;
     }
     if (hits_out) *hits_out = hits_total;

@@ -58,6 +58,11 @@ def single_cases(paths: dict) -> list:
         # the reference's other smoother (control.py:329-344) swapped in for the median filter
         dict(name="avg_filter", file="xydq_circle.txt", K=96, T=30, seed=21, x0=X0, steps=2, smoother="average",
              ctor=dict(param_lambda=4.0e4)),
+        # the reference's other rollout model (_F1, control.py:265-295) swapped in for _F
+        dict(name="f1_dynamics", file="xydq_circle.txt", K=96, T=30, seed=23, x0=X0, steps=2, dynamics="F1",
+             ctor=dict(param_lambda=2.0e4)),
+        dict(name="f1_viz", file="xydq_circle.txt", K=32, T=12, seed=24, x0=X0, dynamics="F1",
+             ctor=dict(visualze_sampled_trajs=True)),
         dict(name="mid_path", file="xydq_circle.txt", K=128, T=30, seed=20, prev_idx=700,
              x0=[0.9, 0.6, 0.3, -0.2],
              u_prev=(np.array([[3.0, 1.0]]) * np.linspace(1, 2, 30)[:, None]).tolist()),

@@ -46,6 +46,9 @@ def run_case(case):
             probe.last["w_eps_filt"] = np.array(out, copy=True)
             return out
         probe.ctrl._moving_median_filter = avg
+    if case.get("dynamics") == "F1":
+        # every rollout of the step calls self._F (control.py:104, 133, 143): route it to the reference's own _F1
+        probe.ctrl._F = probe.ctrl._F1
     if "prev_idx" in case:
         probe.ctrl.prev_waypoints_idx = case["prev_idx"]
     if "u_prev" in case:
@@ -101,7 +104,19 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true", help="skip the K=4096 and closed-loop fixtures")
     ap.add_argument("--closed-loop-steps", type=int, default=1500)
+    ap.add_argument("--only", nargs="*", default=None,
+                    help="(re)generate only these single-step cases and merge them into single_steps.npz")
     a = ap.parse_args()
+    if a.only:
+        wanted = [c for c in cases.single_cases(PATHS) if c["name"] in a.only]
+        with np.load(os.path.join(HERE, "single_steps.npz")) as z:
+            single = {k: z[k] for k in z.files if k.split("/", 1)[0] not in a.only}
+        for c in wanted:
+            name, out = run_case(c)
+            single.update({f"{name}/{k}": v for k, v in out.items()})
+            print("generated", name, flush=True)
+        np.savez_compressed(os.path.join(HERE, "single_steps.npz"), **single)
+        return
 
     np.savez_compressed(os.path.join(HERE, "ref_paths.npz"), **PATHS)
     SINGLE, C2 = cases.single_cases(PATHS), cases.c2_cases()

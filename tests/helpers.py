@@ -14,6 +14,8 @@ def make_controller(case, paths, **extra):
     kw = cases.ctor_kwargs(case, paths)
     if "smoother" in case:
         extra = dict(extra, smoother=case["smoother"])
+    if "dynamics" in case:
+        extra = dict(extra, dynamics=case["dynamics"])
     ctrl = MPPIControllerForPathTracking(**kw, noise="numpy", verbose=False, **extra)
     if "prev_idx" in case:
         ctrl.prev_waypoints_idx = case["prev_idx"]

@@ -38,16 +38,18 @@ def emul_costs(lib, c, x0, eps32, prev_idx, u=None, use_cert=True, hits=None):
                                mo.exploit_count(K, c.param_exploration), C.c_double(c.delta_t),
                                C.c_double(c.param_gamma), dp(sinv), dp(np.ascontiguousarray(c.stage_cost_weight)),
                                dp(np.ascontiguousarray(c.terminal_cost_weight)), dp(arm), C.c_double(c.cost_l1),
-                               C.c_double(c.cost_l2), fp(np.ascontiguousarray(eps32)), fp(S), int(use_cert), C.byref(h))
+                               C.c_double(c.cost_l2), fp(np.ascontiguousarray(eps32)), fp(S), int(use_cert), C.byref(h),
+                               1 if getattr(c, "dynamics", "F") == "F1" else 0)
     if hits is not None:
         hits.append(h.value)
     return S, p
 
 
 def test_fp32_costs_within_stated_tolerance(emul, paths):
-    for case in cases.single_cases(paths)[:6] + cases.c2_cases()[:1]:
+    single = cases.single_cases(paths)
+    for case in single[:6] + [c for c in single if "dynamics" in c] + cases.c2_cases()[:1]:
         kw = cases.ctor_kwargs(case, paths)
-        c = mo.OracleMPPI(**kw)
+        c = mo.OracleMPPI(**kw, dynamics=case.get("dynamics", "F"))
         if "u_prev" in case:
             c.u_prev = np.array(case["u_prev"])
         eps = mo.injected_noise(case["seed"], case["K"], case["T"], kw["sigma"])

@@ -12,7 +12,7 @@ KEYS = ["S", "w", "w_eps_raw", "w_eps_filt", "u_new", "u0", "optimal_traj"]
 
 def _run(case, paths, fn):
     kw = cases.ctor_kwargs(case, paths)
-    c = mo.OracleMPPI(**kw, smoother=case.get("smoother", "median"))
+    c = mo.OracleMPPI(**kw, smoother=case.get("smoother", "median"), dynamics=case.get("dynamics", "F"))
     if "prev_idx" in case:
         c.prev_waypoints_idx = case["prev_idx"]
     if "u_prev" in case:

@@ -461,7 +461,7 @@ struct WinConst {
         for (int i = 0; i < kWindow / 2; ++i) {
             const float4 ab = c_window.pairs[i];
             unsigned long long t, r;
-            asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(t) : "l"(pack2(ab.z, ab.w)), "l"(y2), "l"(pack2(c(2 * i), c(2 * i + 1))));
+            asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(t) : "l"(pack2(ab.z, ab.w)), "l"(y2), "l"(pack2(wc[2 * i], wc[2 * i + 1])));
             asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pack2(ab.x, ab.y)), "l"(x2), "l"(t));
             d[2 * i] = __uint_as_float((unsigned)(r & 0xffffffffull));
             d[2 * i + 1] = __uint_as_float((unsigned)(r >> 32));

@@ -326,17 +326,12 @@ MPPI_HD CertTest cert_test(const EndCert& c, float xl, float yl) {
     // the two half-planes of a wedge as one packed fma.rn.f32x2 chain (same roundings as the scalar form)
     const unsigned long long x2 = ((unsigned long long)__float_as_uint(xl) << 32) | __float_as_uint(xl);
     const unsigned long long y2 = ((unsigned long long)__float_as_uint(yl) << 32) | __float_as_uint(yl);
-    // (three 128-bit reads: from the constant bank they become uniform-register operands of the FFMA2s)
-    const float4* q4 = reinterpret_cast<const float4*>(&c);
-    const float4 q0 = q4[0], q1 = q4[1], q2 = q4[2];              // (lx | ly), (lk | fx), (fy | fk)
-    auto pk = [](float lo, float hi) {
-        return ((unsigned long long)__float_as_uint(hi) << 32) | (unsigned long long)__float_as_uint(lo);
-    };
+    const unsigned long long* q = reinterpret_cast<const unsigned long long*>(&c);   // lx, ly, lk, fx, fy, fk pairs
     unsigned long long a, b;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(a) : "l"(pk(q0.z, q0.w)), "l"(y2), "l"(pk(q1.x, q1.y)));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(a) : "l"(pk(q0.x, q0.y)), "l"(x2), "l"(a));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(b) : "l"(pk(q2.x, q2.y)), "l"(y2), "l"(pk(q2.z, q2.w)));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(b) : "l"(pk(q1.z, q1.w)), "l"(x2), "l"(b));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(a) : "l"(q[1]), "l"(y2), "l"(q[2]));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(a) : "l"(q[0]), "l"(x2), "l"(a));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(b) : "l"(q[4]), "l"(y2), "l"(q[5]));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(b) : "l"(q[3]), "l"(x2), "l"(b));
     t.wl = fminf(__uint_as_float((unsigned)a), __uint_as_float((unsigned)(a >> 32)));
     t.wf = fminf(__uint_as_float((unsigned)b), __uint_as_float((unsigned)(b >> 32)));
 #else
@@ -556,11 +551,10 @@ MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int s = 0; s < NS; ++s) fk_local(st[s], A, hd.ox, hd.oy, xl[s], yl[s]);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int s = 0; s < NS; ++s) j[s] = nearest_wp(win, cert, xl[s], yl[s], hits);
+        for (int s = 0; s < NS; ++s) {
+            fk_local(st[s], A, hd.ox, hd.oy, xl[s], yl[s]);
+            j[s] = nearest_wp(win, cert, xl[s], yl[s], hits);
+        }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif

@@ -50,6 +50,8 @@ def make_cfg(c) -> OracleCfg:
 
 def rollout_costs(c, x0, eps, prev_idx, n_exploit=None):
     """FP64 costs S[K] of the samples eps [K,T,2] for window start prev_idx (already updated)."""
+    if getattr(c, "dynamics", "F") != "F":
+        raise ValueError("mppi_oracle.c restates the default rollout model _F only (use mppi_oracle.py for _F1)")
     eps = np.ascontiguousarray(eps, dtype=np.float64)
     K, T = eps.shape[0], eps.shape[1]
     win = np.ascontiguousarray(c.ref_path[prev_idx:prev_idx + 30, 0:4])

@@ -25,7 +25,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct Workspace {
     size_t bytes;
     size_t off_ref, off_step_blocks, off_in, off_out, off_S, off_w, off_block_min, off_eta_part,
-        off_rho, off_v_part, off_partial, off_loop, off_eta_fused, off_tickets, off_seq, off_stats, off_env_ctl;
+        off_rho, off_v_part, off_partial, off_loop, off_eta_fused, off_tickets, off_seq, off_stats;
 };
 
 }  // namespace
@@ -170,7 +170,6 @@ void carve(const MppiConfig* c, int sm, Workspace* w) {
     w->off_tickets = take(E * sizeof(unsigned int));
     w->off_seq = take(2 * sizeof(unsigned long long));       // [0] step sequence number, [1] exchange status
     w->off_stats = take(2 * sizeof(unsigned long long));     // [0] certified warp-lookups, [1] warp-lookups
-    w->off_env_ctl = take(E * 3 * sizeof(unsigned int));     // per environment: certified, lookups, steps without the test
     w->bytes = off;
 }
 
@@ -205,8 +204,7 @@ void fill_dev_cfg(MppiHandle* h) {
     d.noise.step = 0;
     d.noise.L11 = (float)c.sigma_chol[0]; d.noise.L21 = (float)c.sigma_chol[2]; d.noise.L22 = (float)c.sigma_chol[3];
     d.K_local = c.K_local; d.K_total = c.K_total; d.k_offset = c.k_offset; d.T = c.T; d.n_env = c.n_env;
-    d.n_exploit = c.n_exploit; d.n_ref_rows = 0; d.flags = c.flags & 127;
-    if (getenv("MPPI_NO_ADAPTIVE_CERT") != nullptr) d.flags |= 128;     // internal: evaluate the certificate in every step
+    d.n_exploit = c.n_exploit; d.n_ref_rows = 0; d.flags = c.flags;
     d.step_block_bytes = kStepBlockFixed + 16 * c.T;
     grid_sizes(&c, h->sm_count, &d.g_roll, &d.g_soft, &d.g_wsum);
     d.gamma = c.param_gamma; d.lambda = c.param_lambda; d.inv_lambda = 1.0 / c.param_lambda;
@@ -278,8 +276,7 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
         CU(h, cudaMemcpyAsync(ws + h->ws.off_in, h->host, h->in_bytes, cudaMemcpyHostToDevice, s));
     if (timed) CU(h, cudaEventRecord(h->tev[0], s));
     mppi_prepare_sm100a<<<dc.n_env, 32, 0, s>>>(dc, dio, ref, step_blocks, zc,
-                                                (unsigned long long*)(ws + h->ws.off_seq),
-                                                (unsigned int*)(ws + h->ws.off_env_ctl));
+                                                (unsigned long long*)(ws + h->ws.off_seq));
     if (timed) CU(h, cudaEventRecord(h->tev[1], s));
     {
         dim3 grid(dc.g_roll, dc.n_env);
@@ -293,8 +290,7 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
         }
 #define MPPI_LAUNCH_ROLL_D(NOISE, CW, NS_, DYN) \
         mppi_rollout_sm100a<NOISE, CW, NS_, DYN><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, ph ? nullptr : eps_dev, S, bmin, \
-                                                                                          (unsigned long long*)(ws + h->ws.off_stats), \
-                                                                                          (unsigned int*)(ws + h->ws.off_env_ctl))
+                                                                                          (unsigned long long*)(ws + h->ws.off_stats))
 #define MPPI_LAUNCH_ROLL(NOISE, CW, NS_) MPPI_LAUNCH_ROLL_D(NOISE, CW, NS_, 0)
         if (dc.flags & MPPI_FLAG_DYNAMICS_F1) {
             // the reference's alternative rollout model: register-window kernels only (pick_const_window is off)
@@ -479,7 +475,6 @@ int mppi_create(const MppiConfig* c, void* workspace, size_t workspace_bytes, vo
     h->px.seq = (const unsigned long long*)(h->dev + h->ws.off_seq);
     if (cudaMemset(h->dev + h->ws.off_seq, 0, 2 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(h->dev + h->ws.off_stats, 0, 2 * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMemset(h->dev + h->ws.off_env_ctl, 0, 3 * sizeof(unsigned int) * c->n_env) != cudaSuccess ||
         cudaMemset(h->dev + h->ws.off_tickets, 0, sizeof(unsigned int) * c->n_env) != cudaSuccess) {
         snprintf(g_create_error, sizeof(g_create_error), "cudaMemset(tickets) failed");
         delete h;

@@ -171,8 +171,6 @@ __device__ __forceinline__ void out_store(const DevIo& io, TT* dev_ptr, TT v) {
     if (io.out_delta != 0) *(TT*)((char*)dev_ptr + io.out_delta) = v;
 }
 
-constexpr unsigned int kCertRest = 15u;      // steps an environment runs without the certificate test before the next probe
-
 __device__ __forceinline__ double warp_max_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -271,8 +269,7 @@ __device__ __forceinline__ void warp_wedges(double rx, double ry, int lane, int 
 // FP64 forward kinematics run; the rows of the final window are then picked by shuffles, not reloaded.
 __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, const double* __restrict__ ref,
                                                           char* __restrict__ step_blocks, bool pull_inputs,
-                                                          unsigned long long* __restrict__ seq,
-                                                          unsigned int* __restrict__ env_ctl) {
+                                                          unsigned long long* __restrict__ seq) {
     const int e = blockIdx.x, lane = threadIdx.x, T = cfg.T;
     if (e == 0 && lane == 0) *seq += 1ull;        // step sequence number, read by every later kernel of the step
     const bool zc = io.host_in != nullptr && pull_inputs;
@@ -340,30 +337,13 @@ __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, 
     const double ox = __shfl_sync(0xffffffffu, row.x, 0), oy = __shfl_sync(0xffffffffu, row.y, 0);   // row p
     (void)p_old;
     StepBlockView sb = view_step_block(step_blocks + (size_t)e * cfg.step_block_bytes);
-    // Is the certificate worth evaluating for this environment in this step?  The test costs ~22 issue slots
-    // per lookup and saves the ~114 of the search when a warp is certified: below ~20 % certified lookups it
-    // loses.  The rollout kernel left last step's counts in env_ctl; an environment under the threshold runs
-    // plain searches for kCertRest steps and is then probed again.  (Results do not depend on the choice.)
-    int cert_on = 0;
-    if (lane == 0) {
-        unsigned int* ec = env_ctl + 3 * e;                  // { certified, lookups, steps left without the test }
-        const unsigned int hit = ec[0], all = ec[1], rest = ec[2];
-        ec[0] = 0u; ec[1] = 0u;
-        if (cfg.flags & 16) cert_on = 0;                     // MPPI_FLAG_FULL_SEARCH
-        else if (cfg.flags & 128) cert_on = 1;               // adaptive switch disabled (MPPI_NO_ADAPTIVE_CERT)
-        else if (rest > 0u) { ec[2] = rest - 1u; cert_on = 0; }
-        else if (all > 0u && 5ull * hit < (unsigned long long)all) { ec[2] = kCertRest - 1u; cert_on = 0; }
-        else cert_on = 1;
-    }
-    cert_on = __shfl_sync(0xffffffffu, cert_on, 0);
     if (lane == 0) {
         StepHeader h;
         h.q1 = (float)q1; h.q2 = (float)q2; h.d1 = (float)dq1; h.d2 = (float)dq2;
         h.ox = (float)ox; h.oy = (float)oy;
         h.win_start = p; h.n_valid = min(kWindow, n - p);
         h.status = (p >= n - 1) ? 1 : 0;                     // control.py:76
-        h.cert_on = cert_on;
-        for (int i = 0; i < 6; ++i) h.pad[i] = 0;
+        for (int i = 0; i < 7; ++i) h.pad[i] = 0;
         *sb.hd = h;
         out_store(io, io.new_idx + e, p);
     }
@@ -390,7 +370,7 @@ __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, 
             EndCert c;
             c.dom = (float)dom; c.last = nv - 1; c.pad[0] = c.pad[1] = 0;
             cert_disable(c.lx, c.ly, c.lk); cert_disable(c.fx, c.fy, c.fk);
-            if (cert_on) {
+            if (!(cfg.flags & 16)) {                          // MPPI_FLAG_FULL_SEARCH switches the shortcut off
                 if (nv == 1) { c.fk[0] = c.fk[1] = 1.0f; }
                 else if (nv >= 2) {
                     const double cmax = warp_max_d(rx * rx + ry * ry);            // > 0 for nv >= 2 unless all rows coincide
@@ -505,7 +485,7 @@ template <int NOISE, bool CONSTWIN, int kNS, int DYN = 0>
 __global__ void __launch_bounds__(kRollThreads, CONSTWIN ? MPPI_ROLL_MIN_BLOCKS_CONST : (kNS == 1 ? 3 : 2))
 mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const char* __restrict__ step_blocks,
                     const float* __restrict__ eps, float* __restrict__ S_out, float* __restrict__ block_min,
-                    unsigned long long* __restrict__ search_stats, unsigned int* __restrict__ env_ctl) {
+                    unsigned long long* __restrict__ search_stats) {
     extern __shared__ __align__(128) unsigned char smem_roll[];
     unsigned char* smem = smem_roll;
     __shared__ uint64_t bar;
@@ -549,18 +529,12 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
                 nz[s].nc = cfg.noise; nz[s].nc.step = (uint32_t)(*step_ctr); nz[s].env = (uint32_t)e;
                 nz[s].k = (uint32_t)(cfg.k_offset + kl[s]);
             }
-            // (the register-window kernels skip the certificate test where the prepare kernel switched it off;
-            //  the constant-window kernel of large single-environment steps always evaluates it: the extra
-            //  predicate costs it 1.4 % and its workloads are the ones the test pays for)
-            rollout_cost_n<kNS, DYN, !CONSTWIN>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
+            rollout_cost_n<kNS, DYN>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
         } else {
             InjectedNoise nz[kNS];
 #pragma unroll
             for (int s = 0; s < kNS; ++s) nz[s].row = (const float2*)eps + ((size_t)e * cfg.K_local + kl[s]) * T;
-            // (the register-window kernels skip the certificate test where the prepare kernel switched it off;
-            //  the constant-window kernel of large single-environment steps always evaluates it: the extra
-            //  predicate costs it 1.4 % and its workloads are the ones the test pays for)
-            rollout_cost_n<kNS, DYN, !CONSTWIN>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
+            rollout_cost_n<kNS, DYN>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
         }
 #pragma unroll
         for (int s = 0; s < kNS; ++s) {
@@ -572,10 +546,6 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
     }
     tmin = warp_min(tmin);
     if ((tid & 31) == 0) red[tid >> 5] = tmin;
-    if (hd.cert_on && (tid & 31) == 0) {                     // this step's counts for the next prepare (see there)
-        atomicAdd(env_ctl + 3 * e, (unsigned int)hits);
-        atomicAdd(env_ctl + 3 * e + 1, (unsigned int)lookups);
-    }
     if ((cfg.flags & 64) && (tid & 31) == 0) {              // MPPI_FLAG_SEARCH_STATS: warp-lookups certified / done
         atomicAdd(search_stats, (unsigned long long)hits);
         atomicAdd(search_stats + 1, (unsigned long long)lookups);

@@ -290,8 +290,7 @@ struct StepHeader {            // first 64 bytes of a step block (one per enviro
     int32_t win_start;         // updated prev_waypoints_idx (control.py:230)
     int32_t n_valid;           // rows of the window that exist (control.py:208-209 truncation)
     int32_t status;            // bit0: reached the end of the path (control.py:76)
-    int32_t cert_on;           // the rollouts evaluate the end-of-window certificate in this step (else: search always)
-    int32_t pad[6];
+    int32_t pad[7];
 };
 static_assert(sizeof(StepHeader) == 64, "header is 64 bytes");
 
@@ -506,30 +505,25 @@ MPPI_HD int nearest_wp(const Win& win, float xl, float yl) { return nearest_cand
 
 // The lookup of the rollouts: the certified row when the whole warp is certified (one vote, no
 // divergence), else the full search.  `hits` counts the skipped searches (per warp on the device).
-// ADAPT: honour the per-environment, per-step switch of the prepare kernel (`cert_on`, uniform over the
-// block); without it the test is always evaluated (a switched-off certificate is then simply never true).
-template <bool ADAPT, class Win>
-MPPI_HD int nearest_wp(const Win& win, const EndCert& cert, bool cert_on, float xl, float yl, int& hits) {
-    if (!ADAPT || cert_on) {
-        const CertTest t = cert_test(cert, xl, yl);
+template <class Win>
+MPPI_HD int nearest_wp(const Win& win, const EndCert& cert, float xl, float yl, int& hits) {
+    const CertTest t = cert_test(cert, xl, yl);
 #if defined(__CUDA_ARCH__)
-        if (__all_sync(0xffffffffu, cert_ok(t))) { ++hits; return cert_row(cert, t); }
+    if (__all_sync(0xffffffffu, cert_ok(t))) { ++hits; return cert_row(cert, t); }
 #else
-        if (cert_ok(t)) { ++hits; return cert_row(cert, t); }
+    if (cert_ok(t)) { ++hits; return cert_row(cert, t); }
 #endif
-    }
     return nearest_candidate(win, xl, yl);
 }
 
 // NS samples advance in lockstep inside one thread: they share the window registers, the per-step
 // constants and the loop overhead, and give the scheduler NS independent instruction streams.
-template <int NS, int DYN = 0, bool ADAPT = true, class Win, class Noise>
+template <int NS, int DYN = 0, class Win, class Noise>
 MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
                             const Win& win, const EndCert& cert, const RefRow* rows, const StepCtl* ctl,
                             int T, const float (&um)[NS], Noise (&noise)[NS], float (&S_out)[NS], int& hits) {
     ArmState st[NS];
     float S[NS], kS[NS], ex[NS], ey[NS], e1[NS], e2[NS];
-    const bool cert_on = hd.cert_on != 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -559,7 +553,7 @@ MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
 #endif
         for (int s = 0; s < NS; ++s) {
             fk_local(st[s], A, hd.ox, hd.oy, xl[s], yl[s]);
-            j[s] = nearest_wp<ADAPT>(win, cert, cert_on, xl[s], yl[s], hits);
+            j[s] = nearest_wp(win, cert, xl[s], yl[s], hits);
         }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -591,7 +585,7 @@ MPPI_HD float rollout_cost(const StepHeader& hd, const ArmF& A, const CostW& W,
     const float ums[1] = { um };
     float out[1];
     Noise (&nz)[1] = reinterpret_cast<Noise (&)[1]>(noise);
-    rollout_cost_n<1, DYN, true>(hd, A, W, win, cert, rows, ctl, T, ums, nz, out, hits);
+    rollout_cost_n<1, DYN>(hd, A, W, win, cert, rows, ctl, T, ums, nz, out, hits);
     return out[0];
 }
 

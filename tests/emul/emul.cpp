@@ -30,7 +30,7 @@ int emul_rollout_costs(const double* ref, int n_rows, int prev_idx, const double
     int p = prev_idx + best;
     StepHeader hd{};
     hd.q1 = (float)x0[0]; hd.q2 = (float)x0[1]; hd.d1 = (float)x0[2]; hd.d2 = (float)x0[3];
-    hd.ox = (float)ref[4 * p]; hd.oy = (float)ref[4 * p + 1]; hd.win_start = p; hd.cert_on = use_cert != 0;
+    hd.ox = (float)ref[4 * p]; hd.oy = (float)ref[4 * p + 1]; hd.win_start = p;
     WinRegs win; RefRow rows[kWindowPad]; WinEntry tab[kWindowPad];
     for (int j = 0; j < kWindowPad; ++j) make_window_row(ref, n_rows, p, j, tab[j], rows[j]);
     win.load(tab);

@@ -603,38 +603,3 @@ def test_device_built_certificates_are_sound(paths, emul):
             assert cert[13:14].view(np.int32)[0] == serial[13:14].view(np.int32)[0] == nv - 1
         eng.close()
     assert n_armed > 40
-
-
-def test_certificate_is_switched_off_where_it_does_not_pay(paths):
-    """Per environment and step the prepare kernel arms the certificate test only where it paid off in the last
-    step (>= 20 % certified warp-lookups), rests it for 15 steps otherwise and then probes again
-    (register-window kernels).  Arm at rest on waypoint 420: 8 % certified -> armed pattern 1, 0 x 15, 1, ...;
-    on waypoint 100 every lookup is certified -> always armed.  Results never depend on it."""
-    T, K = 64, 512
-    ref = cases.ref_path_for(paths, "xydq_circle.txt")
-    eps = mo.injected_noise(77, K, T, np.eye(2) * 20.0)
-    full = _engine(paths, K, T, search="full")
-    for row, expect_low in ((420, True), (100, False)):
-        x0 = paths["trajectory1"][row, 0:2].tolist() + [0.0, 0.0]
-        full.step(x0, _u0(T), row, eps)
-        S_full = full.last_costs()[0][0].cpu().numpy().copy()
-        eng = _engine(paths, K, T, search_stats=True)
-        armed, certified = [], []
-        for step in range(34 if expect_low else 4):
-            eng.step(x0, _u0(T), row, eps)
-            armed.append(int(eng.step_block(0)[36:40].view(np.int32)[0]))
-            st = eng.search_stats()
-            certified.append(st["certified"])
-            if step in (0, 1, 16, 17):
-                assert np.array_equal(eng.last_costs()[0][0].cpu().numpy(), S_full), (row, step)
-            if step == 0:
-                assert (st["fraction"] < 0.2) == expect_low and st["certified"] > 0, st
-        if expect_low:
-            assert armed == ([1] + [0] * 15) * 2 + [1, 0], armed
-            assert all((c > 0) == bool(a) for c, a in zip(certified, armed)), certified
-            assert certified[16] == certified[0] == certified[32]
-        else:
-            assert armed == [1, 1, 1, 1] and min(certified) > 0
-        eng.close()
-    full.close()
-    del ref

@@ -288,24 +288,25 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
             CU(h, cudaMemcpyToSymbolAsync(c_window, step_blocks + 64, kStepBlockFixed - 64, 0,
                                           cudaMemcpyDeviceToDevice, s));
         }
-#define MPPI_LAUNCH_ROLL_D(NOISE, CW, NS_, DYN) \
-        mppi_rollout_sm100a<NOISE, CW, NS_, DYN><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, ph ? nullptr : eps_dev, S, bmin, \
-                                                                                          (unsigned long long*)(ws + h->ws.off_stats))
-#define MPPI_LAUNCH_ROLL(NOISE, CW, NS_) MPPI_LAUNCH_ROLL_D(NOISE, CW, NS_, 0)
-        if (dc.flags & MPPI_FLAG_DYNAMICS_F1) {
-            // the reference's alternative rollout model: register-window kernels only (pick_const_window is off)
-            if (h->ns == 2) { if (ph) MPPI_LAUNCH_ROLL_D(0, false, 2, 1); else MPPI_LAUNCH_ROLL_D(1, false, 2, 1); }
-            else { if (ph) MPPI_LAUNCH_ROLL_D(0, false, 1, 1); else MPPI_LAUNCH_ROLL_D(1, false, 1, 1); }
-        } else if (h->const_window) {
-            if (h->ns == 2) { if (ph) MPPI_LAUNCH_ROLL(0, true, 2); else MPPI_LAUNCH_ROLL(1, true, 2); }
-            else { if (ph) MPPI_LAUNCH_ROLL(0, true, 1); else MPPI_LAUNCH_ROLL(1, true, 1); }
-            if (!capturing) { int rc = const_release(h, s); if (rc != MPPI_OK) return rc; }
-        } else {
-            if (h->ns == 2) { if (ph) MPPI_LAUNCH_ROLL(0, false, 2); else MPPI_LAUNCH_ROLL(1, false, 2); }
-            else { if (ph) MPPI_LAUNCH_ROLL(0, false, 1); else MPPI_LAUNCH_ROLL(1, false, 1); }
-        }
-#undef MPPI_LAUNCH_ROLL
-#undef MPPI_LAUNCH_ROLL_D
+        // kernel specialisations: noise source x window policy x samples per thread x rollout model x lookup mode.
+        // MPPI_FLAG_FULL_SEARCH selects kernels compiled without the certificate test (plain searches only);
+        // the _F1 model exists in the register-window shape only and always carries the test (prepare then
+        // writes never-true wedges for MPPI_FLAG_FULL_SEARCH).
+        const bool ns2 = h->ns == 2, f1 = (dc.flags & MPPI_FLAG_DYNAMICS_F1) != 0;
+        const bool cert = !(dc.flags & MPPI_FLAG_FULL_SEARCH);
+        unsigned long long* stats = (unsigned long long*)(ws + h->ws.off_stats);
+        const float* eps_arg = ph ? nullptr : eps_dev;
+#define MPPI_ROLL(NOISE, CW, NS_, DYN, CERT) \
+        mppi_rollout_sm100a<NOISE, CW, NS_, DYN, CERT><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, eps_arg, S, bmin, stats)
+#define MPPI_ROLL_NS(NOISE, CW, DYN, CERT) do { if (ns2) MPPI_ROLL(NOISE, CW, 2, DYN, CERT); else MPPI_ROLL(NOISE, CW, 1, DYN, CERT); } while (0)
+#define MPPI_ROLL_NOISE(CW, DYN, CERT) do { if (ph) MPPI_ROLL_NS(0, CW, DYN, CERT); else MPPI_ROLL_NS(1, CW, DYN, CERT); } while (0)
+        if (f1) MPPI_ROLL_NOISE(false, 1, true);
+        else if (h->const_window) { if (cert) MPPI_ROLL_NOISE(true, 0, true); else MPPI_ROLL_NOISE(true, 0, false); }
+        else { if (cert) MPPI_ROLL_NOISE(false, 0, true); else MPPI_ROLL_NOISE(false, 0, false); }
+        if (h->const_window && !capturing) { int rc = const_release(h, s); if (rc != MPPI_OK) return rc; }
+#undef MPPI_ROLL_NOISE
+#undef MPPI_ROLL_NS
+#undef MPPI_ROLL
     }
     if (timed) CU(h, cudaEventRecord(h->tev[2], s));
     if (noise_mode == MPPI_NOISE_PHILOX) {

@@ -481,7 +481,7 @@ __device__ __forceinline__ const EndCert& cert_of(const StepBlockView& sb) {
     if constexpr (CW) return c_window.cert; else return *sb.cert;
 }
 
-template <int NOISE, bool CONSTWIN, int kNS, int DYN = 0>
+template <int NOISE, bool CONSTWIN, int kNS, int DYN = 0, bool CERT = true>
 __global__ void __launch_bounds__(kRollThreads, CONSTWIN ? MPPI_ROLL_MIN_BLOCKS_CONST : (kNS == 1 ? 3 : 2))
 mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const char* __restrict__ step_blocks,
                     const float* __restrict__ eps, float* __restrict__ S_out, float* __restrict__ block_min,
@@ -529,12 +529,12 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
                 nz[s].nc = cfg.noise; nz[s].nc.step = (uint32_t)(*step_ctr); nz[s].env = (uint32_t)e;
                 nz[s].k = (uint32_t)(cfg.k_offset + kl[s]);
             }
-            rollout_cost_n<kNS, DYN>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
+            rollout_cost_n<kNS, DYN, CERT>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
         } else {
             InjectedNoise nz[kNS];
 #pragma unroll
             for (int s = 0; s < kNS; ++s) nz[s].row = (const float2*)eps + ((size_t)e * cfg.K_local + kl[s]) * T;
-            rollout_cost_n<kNS, DYN>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
+            rollout_cost_n<kNS, DYN, CERT>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
         }
 #pragma unroll
         for (int s = 0; s < kNS; ++s) {

@@ -518,7 +518,8 @@ MPPI_HD int nearest_wp(const Win& win, const EndCert& cert, float xl, float yl, 
 
 // NS samples advance in lockstep inside one thread: they share the window registers, the per-step
 // constants and the loop overhead, and give the scheduler NS independent instruction streams.
-template <int NS, int DYN = 0, class Win, class Noise>
+// CERT = false compiles the lookups as plain searches (the kernel shape for MPPI_FLAG_FULL_SEARCH: no test, no vote)
+template <int NS, int DYN = 0, bool CERT = true, class Win, class Noise>
 MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
                             const Win& win, const EndCert& cert, const RefRow* rows, const StepCtl* ctl,
                             int T, const float (&um)[NS], Noise (&noise)[NS], float (&S_out)[NS], int& hits) {
@@ -553,7 +554,7 @@ MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
 #endif
         for (int s = 0; s < NS; ++s) {
             fk_local(st[s], A, hd.ox, hd.oy, xl[s], yl[s]);
-            j[s] = nearest_wp(win, cert, xl[s], yl[s], hits);
+            j[s] = CERT ? nearest_wp(win, cert, xl[s], yl[s], hits) : nearest_candidate(win, xl[s], yl[s]);
         }
 #if defined(__CUDA_ARCH__)
 #pragma unroll

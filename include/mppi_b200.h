@@ -52,7 +52,7 @@ enum {
     MPPI_FLAG_DEVICE_GRAPH = 2, /* replay the step as one CUDA graph (Philox mode only)          */
     MPPI_FLAG_SMOOTH_AVERAGE = 4, /* smooth the update with control.py:329-344 instead of the median filter (needs T >= 10) */
     MPPI_FLAG_SMOOTH_NONE = 8,  /* no smoothing of the weighted noise sum                        */
-    MPPI_FLAG_FULL_SEARCH = 16, /* control.py:208-215: always run the 30-candidate search (switches off the
+    MPPI_FLAG_FULL_SEARCH = 16, /* control.py:208-215: always run the 30-candidate search (kernels compiled without the
                                    certified end-of-window shortcut; results are bit-identical either way) */
     MPPI_FLAG_DYNAMICS_F1 = 32, /* roll out with control.py:265-295 (_F1, feedback-linearised) instead of _F */
     MPPI_FLAG_SEARCH_STATS = 64 /* count certified / total warp-lookups of the rollouts (mppi_search_stats) */

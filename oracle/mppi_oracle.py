@@ -20,8 +20,10 @@ Reference lines restated (all in ``/root/reference``):
   control.py:174-198 stage / terminal cost
   control.py:200-232 nearest waypoint in a 30-point forward window, first arg-min
   control.py:234-263 arm dynamics + semi-implicit Euler (mass matrix uses link lengths, Q7)
+  control.py:265-295 the alternative rollout model _F1 (``dynamics="F1"``)
   control.py:297-314 soft-min weights
   control.py:319-327 scipy.ndimage.median_filter(size=10, mode='reflect') per column
+  control.py:329-344 the alternative smoother _moving_average_filter (``smoother="average"``)
   sys_params.py:1-13 arm constants;  utils.py:14-38 plant dynamics / forward kinematics twins
 """
 from __future__ import annotations

@@ -184,3 +184,72 @@ def test_certified_rollout_costs_are_bit_identical(emul, paths):
         S_on, _ = emul_costs(emul, c, x0, eps, p, use_cert=True)
         S_off, _ = emul_costs(emul, c, x0, eps, p, use_cert=False)
         assert np.array_equal(S_on, S_off)
+
+
+def _synthetic_window_path(kind, rng, n=40):
+    t = np.arange(n)
+    if kind == "line":
+        xy = np.stack([0.5 + 0.002 * t, 0.3 + 0.001 * t], 1)
+    elif kind == "line_noise":
+        xy = np.stack([0.5 + 0.002 * t, 0.3 + 0.001 * t], 1) + rng.normal(0, 10.0 ** rng.uniform(-9, -3.3), (n, 2))
+    elif kind == "walk":
+        xy = np.cumsum(rng.normal(0, 10.0 ** rng.uniform(-4, -2), (n, 2)), 0) + rng.uniform(-1, 1, 2)
+    elif kind == "arc":
+        r, th = 10.0 ** rng.uniform(-2, 1), rng.uniform(0, 6.28) + t * 10.0 ** rng.uniform(-4, -1.5)
+        xy = np.stack([r * np.cos(th), r * np.sin(th)], 1) + rng.uniform(-1, 1, 2)
+    elif kind == "dups":                                   # every waypoint three times
+        xy = np.stack([0.5 + 0.002 * (t // 3), 0.3 + 0.0 * t], 1)
+    elif kind == "neardup":                                # pairs of waypoints 1 nm apart
+        xy = np.stack([0.5 + 0.002 * t, 0.3 + 0.0 * t], 1)
+        xy[1::7] = xy[0::7][:len(xy[1::7])] + 1e-9
+    elif kind == "zigzag":
+        xy = np.stack([0.5 + 0.002 * t, 0.3 + 0.002 * (t % 2)], 1)
+    elif kind == "uturn":
+        th = np.linspace(0, np.pi * rng.uniform(0.5, 1.5), n)
+        xy = np.stack([0.02 * np.cos(th), 0.02 * np.sin(th)], 1) + 0.7
+    elif kind == "far":                                    # window far from the arm's base: large local coordinates
+        xy = np.stack([50 + 0.002 * t, -30 + 0.001 * t], 1)
+    elif kind == "tiny":                                   # micrometre spacing
+        xy = np.stack([0.5 + 1e-6 * t, 0.3 + 2e-6 * t], 1)
+    else:                                                  # spiral
+        th, r = t * 0.3, 0.001 * t + 0.001
+        xy = np.stack([r * np.cos(th), r * np.sin(th)], 1) + 0.4
+    return np.ascontiguousarray(np.concatenate([xy, np.zeros((n, 2))], 1))
+
+
+@pytest.mark.parametrize("kind", ["line", "line_noise", "walk", "arc", "dups", "neardup", "zigzag", "uturn", "far",
+                                  "tiny", "spiral"])
+def test_certificate_is_sound_on_adversarial_paths(emul, kind):
+    """Paths the reference files do not contain: exact and near duplicates (a tie must go to the lower index, so
+    those wedges have to be refused), zigzags, U-turns and spirals (direction spread), micrometre spacing, noise
+    from 1 nm to half a spacing, a window 58 m from the base.  Wherever a certificate is issued it agrees with
+    the exact FP32 search, also for queries hugging the wedge apex and edges."""
+    rng = np.random.default_rng(sum(kind.encode()))
+    certified, armed = 0, 0
+    for _ in range(25):
+        ref = _synthetic_window_path(kind, rng)
+        n = ref.shape[0]
+        p = int(rng.integers(0, n - 1))
+        nv = min(30, n - p)
+        N = 3000
+        base = ref[p + rng.integers(0, nv, N), 0:2] - ref[p, 0:2]
+        span = max(np.ptp(ref[p:p + nv, 0]), np.ptp(ref[p:p + nv, 1]), 1e-9)
+        qs = [base + rng.standard_normal((N, 2)) * (span * 10.0 ** rng.uniform(-4, 2, N))[:, None]]
+        _, _, cert = _probe(emul, ref, p, qs[0])
+        for off in (0, 6):
+            mx, my, k = (cert[off + 2 * i:off + 2 * i + 2].astype(np.float64) for i in range(3))
+            if not np.all(np.isfinite(k)):
+                continue
+            armed += 1
+            A = np.array([[mx[0], my[0]], [mx[1], my[1]]])
+            z = np.linalg.solve(A, -k) if abs(np.linalg.det(A)) > 1e-12 else -k[0] * np.array([mx[0], my[0]])
+            t = (10.0 ** rng.uniform(-9, 0.5, N) * rng.choice([-1, 1], N))[:, None]
+            which = rng.integers(0, 3, N)[:, None]
+            qs.append(z[None, :] + rng.standard_normal((N, 2)) * (10.0 ** rng.uniform(-10, -5, N))[:, None]
+                      + np.where(which == 0, t * np.array([-my[0], mx[0]]), 0.0)
+                      + np.where(which == 1, t * np.array([-my[1], mx[1]]), 0.0))
+        pick, full, _ = _probe(emul, ref, p, np.concatenate(qs))
+        m = pick >= 0
+        assert np.array_equal(pick[m], full[m]), kind
+        certified += int(m.sum())
+    assert armed > 0 and certified > 1000, (kind, armed, certified)

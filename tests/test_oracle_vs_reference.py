@@ -39,6 +39,39 @@ def test_fresh_random_step_matches_reference(paths, seed):
         np.testing.assert_array_equal(probe.ctrl.u_prev, c.u_prev)
 
 
+@pytest.mark.parametrize("seed", [41, 42])
+def test_alternative_model_and_smoother_match_reference(paths, seed):
+    """The reference's dead alternatives, live: its own _F1 (control.py:265-295) routed into every self._F call and
+    its own _moving_average_filter (control.py:329-344) routed into the smoother call, on fresh random steps."""
+    rng = np.random.default_rng(seed)
+    K, T = int(rng.integers(20, 70)), int(rng.integers(12, 36))
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    kw = cases.run_py_kwargs(ref, K, T, param_lambda=3.0e4, visualze_sampled_trajs=True)
+    probe = rh.ReferenceProbe(**kw)
+    probe.ctrl._F = probe.ctrl._F1
+    ref_avg = probe.ctrl._moving_average_filter
+
+    def avg(xx, window_size):
+        probe.last["w_eps_raw"] = np.array(xx, copy=True)
+        out = ref_avg(xx, window_size)
+        probe.last["w_eps_filt"] = np.array(out, copy=True)
+        return out
+    probe.ctrl._moving_median_filter = avg
+    c = mo.OracleMPPI(**kw, dynamics="F1", smoother="average")
+    p0 = int(rng.integers(0, 1900))
+    probe.ctrl.prev_waypoints_idx = p0
+    c.prev_waypoints_idx = p0
+    x = np.array(cases.X0) + rng.normal(0, 0.05, 4)
+    for s in range(2):
+        eps = mo.injected_noise(seed * 10 + s, K, T, kw["sigma"]).astype(np.float64)
+        r = probe.step(list(x), eps)
+        o = mo.step_vectorized(c, x, eps)
+        for k in ["S", "w", "w_eps_raw", "w_eps_filt", "u_new", "u0", "optimal_traj", "sampled_traj"]:
+            a, b = np.asarray(r[k]), np.asarray(o[k])
+            assert np.max(np.abs(a - b)) <= 1e-12 * max(1.0, np.max(np.abs(a))), k
+        assert r["prev_idx_after"] == o["prev_idx_after"]
+
+
 def test_plant_twin_matches_reference_utils():
     _, utils = rh.import_reference()
     rng = np.random.default_rng(5)

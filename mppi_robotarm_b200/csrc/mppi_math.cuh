@@ -28,6 +28,16 @@ constexpr int kWindowPad = 32;    // table rows (two never-selected sentinels)
 constexpr int kFilter = 10;       // control.py:122
 constexpr float kSentinel = 3.0e38f;
 
+// Which accumulators of a rollout carry a Kahan compensation term: bit 0 joint rates, bit 1 joint angles,
+// bit 2 the cost sum S.  Default: all.  (CPU study, DESIGN.md section 8: bit 2 buys nothing measurable.)
+#ifndef MPPI_KAHAN_MASK
+#ifdef MPPI_NO_KAHAN
+#define MPPI_KAHAN_MASK 0
+#else
+#define MPPI_KAHAN_MASK 7
+#endif
+#endif
+
 // ---- explicitly rounded primitives ---------------------------------------------------------
 #if defined(__CUDA_ARCH__)
 MPPI_HD float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
@@ -127,13 +137,16 @@ MPPI_HD void kahan_(float& acc, float& comp, float y) {
 template <int DYN = 0>
 MPPI_HD void arm_step(ArmState& st, const ArmF& A, float v1, float v2) {
     if (DYN == 1) {
-#ifndef MPPI_NO_KAHAN
+#if (MPPI_KAHAN_MASK & 1)
         kahan_(st.d1, st.kd1, fma_(v1, A.dt, -st.kd1));
         kahan_(st.d2, st.kd2, fma_(v2, A.dt, -st.kd2));
+#else
+        st.d1 = fma_(v1, A.dt, st.d1); st.d2 = fma_(v2, A.dt, st.d2);
+#endif
+#if (MPPI_KAHAN_MASK & 2)
         kahan_(st.q1, st.kq1, fma_(st.d1, A.dt, -st.kq1));
         kahan_(st.q2, st.kq2, fma_(st.d2, A.dt, -st.kq2));
 #else
-        st.d1 = fma_(v1, A.dt, st.d1); st.d2 = fma_(v2, A.dt, st.d2);
         st.q1 = fma_(st.d1, A.dt, st.q1); st.q2 = fma_(st.d2, A.dt, st.q2);
 #endif
         sincos_(st.q1, st.s1, st.c1);
@@ -156,17 +169,20 @@ MPPI_HD void arm_step(ArmState& st, const ArmF& A, float v1, float v2) {
     float idt = mul_(rcp_(det), A.dt);
     float n1 = fma_(A.M22, b1, -mul_(M12, b2));
     float n2 = fma_(M11, b2, -mul_(M12, b1));
-#ifndef MPPI_NO_KAHAN
     // compensated (Kahan) integration: the rounding error of each accumulator is carried, so the
     // state error stays ~1 ulp instead of growing like sqrt(T) ulp over the horizon
+#if (MPPI_KAHAN_MASK & 1)
     kahan_(st.d1, st.kd1, fma_(n1, idt, -st.kd1));
     kahan_(st.d2, st.kd2, fma_(n2, idt, -st.kd2));
-    // (the rate's own compensation term times dt, ~1e-8 * dt, is far below one ulp of q and is dropped)
-    kahan_(st.q1, st.kq1, fma_(st.d1, A.dt, -st.kq1));
-    kahan_(st.q2, st.kq2, fma_(st.d2, A.dt, -st.kq2));
 #else
     st.d1 = fma_(n1, idt, st.d1);
     st.d2 = fma_(n2, idt, st.d2);
+#endif
+    // (the rate's own compensation term times dt, ~1e-8 * dt, is far below one ulp of q and is dropped)
+#if (MPPI_KAHAN_MASK & 2)
+    kahan_(st.q1, st.kq1, fma_(st.d1, A.dt, -st.kq1));
+    kahan_(st.q2, st.kq2, fma_(st.d2, A.dt, -st.kq2));
+#else
     st.q1 = fma_(st.d1, A.dt, st.q1);
     st.q2 = fma_(st.d2, A.dt, st.q2);
 #endif
@@ -564,7 +580,7 @@ MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
             residuals(st[s], xl[s], yl[s], r, ex[s], ey[s], e1[s], e2[s]);
             float cst = wsq(W.s0, W.s1, W.s2, W.s3, ex[s], ey[s], e1[s], e2[s]);
             cst = fma_(c.g1, v1[s], fma_(c.g2, v2[s], cst));   // + gamma * u^T Sigma^-1 v  (control.py:106)
-#ifndef MPPI_NO_KAHAN
+#if (MPPI_KAHAN_MASK & 4)
             kahan_(S[s], kS[s], sub_(cst, kS[s]));
 #else
             S[s] = add_(S[s], cst);

@@ -253,3 +253,33 @@ def test_certificate_is_sound_on_adversarial_paths(emul, kind):
         assert np.array_equal(pick[m], full[m]), kind
         certified += int(m.sum())
     assert armed > 0 and certified > 1000, (kind, armed, certified)
+
+
+def test_cost_sum_compensation_is_not_what_holds_the_tolerance(emul, paths, tmp_path):
+    """Numerics study kept as a test: without the Kahan term of the cost accumulator
+    (MPPI_KAHAN_MASK=3: rates and angles only) the updated sequence stays within the same bound over the
+    reference's closed loop; without the angle compensation (mask 5) it does not keep the margin."""
+    worst = {}
+    with np.load(cases.HERE + "/closed_loop_c1.npz") as z:
+        cl = {k: z[k] for k in z.files}
+    K, T, seed0, _ = (int(v) for v in cl["meta"])
+    kw = cases.run_py_kwargs(cases.ref_path_for(paths, "xydq_circle.txt"), K, T)
+    c = mo.OracleMPPI(**kw)
+    for mask in (3, 5):
+        so = str(tmp_path / f"emul_mask{mask}.so")
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", f"-DMPPI_KAHAN_MASK={mask}", "-shared", "-fPIC", "-o", so, SRC],
+                       check=True)
+        lib = C.CDLL(so)
+        lib.emul_rollout_costs.restype = C.c_int
+        w_err = 0.0
+        for s in range(1, cl["state"].shape[0], 6):
+            prev = cl["u_new"][s - 1]
+            u = np.concatenate([prev[1:], prev[-1:]], axis=0)
+            eps = mo.injected_noise(seed0 + s, K, T, kw["sigma"])
+            S32, _ = emul_costs(lib, c, cl["state"][s], eps, int(cl["prev_idx"][s, 0]), u=u)
+            w, _, _ = mo.softmin_weights(S32.astype(np.float64), c.param_lambda)
+            un = u + mo.filter_columns(np.einsum("k,ktm->tm", w, eps.astype(np.float64)))
+            w_err = max(w_err, np.max(np.abs(un - cl["u_new"][s])) / np.max(np.abs(cl["u_new"][s])))
+        worst[mask] = w_err
+    assert worst[3] <= 5e-5, worst
+    assert worst[5] > worst[3], worst

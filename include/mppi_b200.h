@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MPPI_ABI_VERSION 2
+#define MPPI_ABI_VERSION 3
 
 enum {
     MPPI_OK = 0,
@@ -53,7 +53,7 @@ enum {
     MPPI_FLAG_SMOOTH_AVERAGE = 4, /* smooth the update with control.py:329-344 instead of the median filter (needs T >= 10) */
     MPPI_FLAG_SMOOTH_NONE = 8,  /* no smoothing of the weighted noise sum                        */
     MPPI_FLAG_FULL_SEARCH = 16, /* control.py:208-215: always run the 30-candidate search (kernels compiled without the
-                                   certified end-of-window shortcut; results are bit-identical either way) */
+                                   certified lookups; results are bit-identical either way) */
     MPPI_FLAG_DYNAMICS_F1 = 32, /* roll out with control.py:265-295 (_F1, feedback-linearised) instead of _F */
     MPPI_FLAG_SEARCH_STATS = 64 /* count certified / total warp-lookups of the rollouts (mppi_search_stats) */
 };
@@ -175,7 +175,7 @@ int mppi_replay_end(MppiHandle* h, void* stream);
 int mppi_last_costs(MppiHandle* h, const float** S_dev, const float** w_dev);
 /* The tables the prepare kernel built for environment `env` in the last step (tests / debugging), device
  * memory: 64 B header (state, window origin and start) | 32 x 16 B window coefficients | 32 x 16 B reference
- * rows | 16 x 16 B coefficient pairs | 64 B end-of-window certificate | T x 16 B step controls. */
+ * rows | 16 x 16 B coefficient pairs | 64 B lookup certificate | 32 x 32 B row records | T x 16 B step controls. */
 int mppi_step_block(MppiHandle* h, int32_t env, const void** dev_ptr, size_t* bytes);
 /* control.py:137-145 — trajectories of all samples under v[k, t-1] (index wrap included), for the
  * state / sequence / window of the last step.  traj_dev: float32 [n_env][K_local][T][4]. */
@@ -191,9 +191,10 @@ int mppi_philox_noise(MppiHandle* h, uint64_t step, float* eps_dev, void* stream
 /* Number of kernels launched by this handle so far (graph replays count their kernel nodes). */
 uint64_t mppi_launch_count(const MppiHandle* h);
 /* Nearest-waypoint lookups of the rollouts (control.py:200-215 via _c / _phi) since the last reset, counted
- * per warp (32 samples): out2[0] = lookups answered by the certified end-of-window shortcut, out2[1] = all
- * lookups.  Needs MPPI_FLAG_SEARCH_STATS; synchronises the device. */
-int mppi_search_stats(MppiHandle* h, uint64_t* out2, int32_t reset);
+ * per warp (32 samples): out3[0] = lookups answered by a certified end-of-window test, out3[1] = all lookups,
+ * out3[2] = lookups answered by a certified three-row comparison; the rest ran the 30-candidate search.
+ * Needs MPPI_FLAG_SEARCH_STATS; synchronises `stream` (the stream the steps were enqueued on). */
+int mppi_search_stats(MppiHandle* h, uint64_t* out3, int32_t reset, void* stream);
 /* Mean device time of each kernel family over the steps run with timing enabled, in microseconds:
  * out[0..5] = prepare, rollout, softmin, weighted-sum, reduce, finalize.  Returns #timed steps. */
 int mppi_set_timing(MppiHandle* h, int32_t enable);

@@ -10,7 +10,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_T = 256
 
 NOISE_PHILOX = 0
@@ -75,7 +75,7 @@ SYMBOLS = {
                                                    C.c_void_p, C.c_void_p]),
     "mppi_philox_noise": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "mppi_launch_count": (C.c_uint64, [C.c_void_p]),
-    "mppi_search_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int32]),
+    "mppi_search_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int32, C.c_void_p]),
     "mppi_set_timing": (C.c_int, [C.c_void_p, C.c_int32]),
     "mppi_get_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int32]),
     "mppi_probe_fp32": (C.c_int, [C.c_int32, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

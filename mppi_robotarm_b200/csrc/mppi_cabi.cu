@@ -100,9 +100,14 @@ bool valid_cfg(const MppiConfig* c, const char** why) {
 }
 
 // samples per thread of the rollout kernel: 2 when there is enough work to fill the GPU that way
+bool certified_kernels(const MppiConfig* c) {
+    // certified lookups (window table in shared memory) unless the caller asked for plain searches; the _F1
+    // model exists in the certified shape only (with MPPI_FLAG_FULL_SEARCH its certificate is never armed)
+    return !(c->flags & MPPI_FLAG_FULL_SEARCH) || (c->flags & MPPI_FLAG_DYNAMICS_F1);
+}
 bool pick_const_window(const MppiConfig* c) {
-    // constant-bank window: single environment and enough work to pay for the extra copy node
-    return (c->n_env == 1) && ((long long)c->K_local * c->T >= (1ll << 21)) && !(c->flags & MPPI_FLAG_DYNAMICS_F1) &&
+    // constant-bank window of the plain-search kernels: single environment and enough work to pay for the copy node
+    return !certified_kernels(c) && (c->n_env == 1) && ((long long)c->K_local * c->T >= (1ll << 21)) &&
            getenv("MPPI_NO_CONST_WINDOW") == nullptr;
 }
 
@@ -116,7 +121,7 @@ int pick_ns(const MppiConfig* c, int sm) {
     const bool cw = pick_const_window(c);
     double best_cost = 0.0; int best = 1;
     for (int ns = 1; ns <= 2; ++ns) {
-        const int per_sm = cw ? 4 : (ns == 1 ? 3 : 2);
+        const int per_sm = certified_kernels(c) ? MPPI_ROLL_MIN_BLOCKS_CERT : (cw ? MPPI_ROLL_MIN_BLOCKS_CONST : (ns == 1 ? 3 : 2));
         const long long ctas = (((long long)c->K_local + 128 * ns - 1) / (128 * ns)) * c->n_env;
         const long long slots = (long long)sm * per_sm;
         const long long full = ctas / slots, rest = ctas % slots;
@@ -169,7 +174,7 @@ void carve(const MppiConfig* c, int sm, Workspace* w) {
     w->off_eta_fused = take(E * g_wsum * sizeof(double));
     w->off_tickets = take(E * sizeof(unsigned int));
     w->off_seq = take(2 * sizeof(unsigned long long));       // [0] step sequence number, [1] exchange status
-    w->off_stats = take(2 * sizeof(unsigned long long));     // [0] certified warp-lookups, [1] warp-lookups
+    w->off_stats = take(4 * sizeof(unsigned long long));     // warp-lookups: [0] answered by an end test, [1] all, [2] by a certified triple
     w->bytes = off;
 }
 
@@ -285,15 +290,14 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
             // single environment, large K: stage this step's window coefficients in the constant bank
             if (!capturing) { int rc = const_acquire(h, s); if (rc != MPPI_OK) return rc; }
             // (window + rows + pair table are adjacent in the step block and in the constant bank: one copy)
-            CU(h, cudaMemcpyToSymbolAsync(c_window, step_blocks + 64, kStepBlockFixed - 64, 0,
+            CU(h, cudaMemcpyToSymbolAsync(c_window, step_blocks + 64, sizeof(ConstWindow), 0,
                                           cudaMemcpyDeviceToDevice, s));
         }
-        // kernel specialisations: noise source x window policy x samples per thread x rollout model x lookup mode.
-        // MPPI_FLAG_FULL_SEARCH selects kernels compiled without the certificate test (plain searches only);
-        // the _F1 model exists in the register-window shape only and always carries the test (prepare then
-        // writes never-true wedges for MPPI_FLAG_FULL_SEARCH).
+        // kernel specialisations: noise source x samples per thread x { certified lookups x rollout model,
+        // plain searches x window policy }.  MPPI_FLAG_FULL_SEARCH selects the kernels compiled without the
+        // certificate; the _F1 model exists in the certified shape only (prepare then never arms the certificate).
         const bool ns2 = h->ns == 2, f1 = (dc.flags & MPPI_FLAG_DYNAMICS_F1) != 0;
-        const bool cert = !(dc.flags & MPPI_FLAG_FULL_SEARCH);
+        const bool cert = certified_kernels(&h->cfg);
         unsigned long long* stats = (unsigned long long*)(ws + h->ws.off_stats);
         const float* eps_arg = ph ? nullptr : eps_dev;
 #define MPPI_ROLL(NOISE, CW, NS_, DYN, CERT) \
@@ -301,8 +305,9 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
 #define MPPI_ROLL_NS(NOISE, CW, DYN, CERT) do { if (ns2) MPPI_ROLL(NOISE, CW, 2, DYN, CERT); else MPPI_ROLL(NOISE, CW, 1, DYN, CERT); } while (0)
 #define MPPI_ROLL_NOISE(CW, DYN, CERT) do { if (ph) MPPI_ROLL_NS(0, CW, DYN, CERT); else MPPI_ROLL_NS(1, CW, DYN, CERT); } while (0)
         if (f1) MPPI_ROLL_NOISE(false, 1, true);
-        else if (h->const_window) { if (cert) MPPI_ROLL_NOISE(true, 0, true); else MPPI_ROLL_NOISE(true, 0, false); }
-        else { if (cert) MPPI_ROLL_NOISE(false, 0, true); else MPPI_ROLL_NOISE(false, 0, false); }
+        else if (cert) MPPI_ROLL_NOISE(false, 0, true);
+        else if (h->const_window) MPPI_ROLL_NOISE(true, 0, false);
+        else MPPI_ROLL_NOISE(false, 0, false);
         if (h->const_window && !capturing) { int rc = const_release(h, s); if (rc != MPPI_OK) return rc; }
 #undef MPPI_ROLL_NOISE
 #undef MPPI_ROLL_NS
@@ -475,7 +480,7 @@ int mppi_create(const MppiConfig* c, void* workspace, size_t workspace_bytes, vo
     h->px.world = 0;
     h->px.seq = (const unsigned long long*)(h->dev + h->ws.off_seq);
     if (cudaMemset(h->dev + h->ws.off_seq, 0, 2 * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMemset(h->dev + h->ws.off_stats, 0, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(h->dev + h->ws.off_stats, 0, 4 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(h->dev + h->ws.off_tickets, 0, sizeof(unsigned int) * c->n_env) != cudaSuccess) {
         snprintf(g_create_error, sizeof(g_create_error), "cudaMemset(tickets) failed");
         delete h;
@@ -801,16 +806,17 @@ int mppi_philox_noise(MppiHandle* h, uint64_t step, float* eps_dev, void* stream
 
 uint64_t mppi_launch_count(const MppiHandle* h) { return h ? h->launches : 0; }
 
-int mppi_search_stats(MppiHandle* h, uint64_t* out2, int32_t reset) {
-    if (!h || !out2) return MPPI_ERR_INVALID;
+int mppi_search_stats(MppiHandle* h, uint64_t* out3, int32_t reset, void* stream) {
+    if (!h || !out3) return MPPI_ERR_INVALID;
     if (!(h->cfg.flags & MPPI_FLAG_SEARCH_STATS))
         return fail(h, MPPI_ERR_INVALID, "%s", "the handle was created without MPPI_FLAG_SEARCH_STATS");
     CU(h, cudaSetDevice(h->cfg.device));
-    CU(h, cudaDeviceSynchronize());
-    unsigned long long v[2] = { 0, 0 };
-    CU(h, cudaMemcpy(v, h->dev + h->ws.off_stats, sizeof(v), cudaMemcpyDeviceToHost));
-    out2[0] = v[0]; out2[1] = v[1];
-    if (reset) CU(h, cudaMemset(h->dev + h->ws.off_stats, 0, sizeof(v)));
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long v[4] = { 0, 0, 0, 0 };
+    CU(h, cudaMemcpyAsync(v, h->dev + h->ws.off_stats, sizeof(v), cudaMemcpyDeviceToHost, s));
+    if (reset) CU(h, cudaMemsetAsync(h->dev + h->ws.off_stats, 0, sizeof(v), s));
+    CU(h, cudaStreamSynchronize(s));                    // only the stream the steps were enqueued on
+    out3[0] = v[0]; out3[1] = v[1]; out3[2] = v[2];
     return MPPI_OK;
 }
 

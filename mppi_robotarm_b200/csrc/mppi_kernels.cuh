@@ -89,9 +89,10 @@ struct LoopParams {
 };
 
 struct StepBlockView {          // pointers into one environment's step block (global or shared)
-    StepHeader* hd; WinEntry* win; RefRow* rows; float4* pairs; EndCert* cert; StepCtl* ctl;
+    StepHeader* hd; WinEntry* win; RefRow* rows; float4* pairs; WinCert* cert; RowRec* rec; StepCtl* ctl;
 };
-constexpr int kStepBlockFixed = 64 + 32 * kWindowPad + 16 * (kWindowPad / 2) + 64;   // header + win + rows + pairs + certificate
+// header + win + rows + pairs + certificate + row records
+constexpr int kStepBlockFixed = 64 + 32 * kWindowPad + 16 * (kWindowPad / 2) + 64 + 32 * kWindowPad;
 __host__ __device__ __forceinline__ StepBlockView view_step_block(void* base) {
     char* b = (char*)base;
     StepBlockView v;
@@ -99,7 +100,8 @@ __host__ __device__ __forceinline__ StepBlockView view_step_block(void* base) {
     v.win = (WinEntry*)(b + 64);
     v.rows = (RefRow*)(b + 64 + 16 * kWindowPad);
     v.pairs = (float4*)(b + 64 + 32 * kWindowPad);          // (a_2i, a_2i+1, b_2i, b_2i+1): operands of packed FFMA2
-    v.cert = (EndCert*)(b + 64 + 32 * kWindowPad + 16 * (kWindowPad / 2));   // end-of-window certificate
+    v.cert = (WinCert*)(b + 64 + 32 * kWindowPad + 16 * (kWindowPad / 2));   // lookup certificate of the window
+    v.rec = (RowRec*)(b + 64 + 32 * kWindowPad + 16 * (kWindowPad / 2) + 64);   // (a, b, c) + certificate of each row
     v.ctl = (StepCtl*)(b + kStepBlockFixed);
     return v;
 }
@@ -176,88 +178,95 @@ __device__ __forceinline__ double warp_max_d(double v) {
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-__device__ __forceinline__ double warp_min_d(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
-// FP64 reciprocal / reciprocal square root from the FP32 MUFU seed + two Newton steps (~1e-14 relative):
-// the wedge construction is a chain of divisions and square roots on the latency path of every control
-// step, and its results only feed quantities that carry >= 1e-7 of deliberate slack.
-__device__ __forceinline__ double fast_rcp(double x) {
-    double r = (double)__frcp_rn((float)x);
-    r = fma(r, fma(-x, r, 1.0), r);
-    return fma(r, fma(-x, r, 1.0), r);
-}
-__device__ __forceinline__ double fast_rsqrt(double x) {
-    double r = (double)rsqrtf((float)x);
-    r = r * fma(-0.5 * x * r, r, 1.5);
-    return r * fma(-0.5 * x * r, r, 1.5);
-}
-
-// make_wedge() of mppi_math.cuh for BOTH targets at once (w = 0: last row, w = 1: row 0; the two
-// dependency chains interleave), one lane per window row: (rx, ry) = this lane's local row, valid for
-// lane < n, n >= 2.  Every lane returns the same coefficients.
-__device__ __forceinline__ void warp_wedges(double rx, double ry, int lane, int n, double margin, double dom, EndCert& c) {
-    const int target[2] = { n - 1, 0 };
-    double tx[2], ty[2], n0x[2], n0y[2], gx[2], gy[2], sl[2];
-    bool ok[2], mine[2];
-#pragma unroll
-    for (int w = 0; w < 2; ++w) {
-        tx[w] = __shfl_sync(0xffffffffu, rx, target[w]); ty[w] = __shfl_sync(0xffffffffu, ry, target[w]);
+// Lookup certificate of one window (make_win_cert of mppi_math.cuh), one lane per row: srow = the local rows
+// in shared memory (valid for j < n), lane `a` derives row a's tangent and the bounds its two roles put on
+// the lateral range; the range is their intersection over the warp.  Every lane returns the same certificate
+// and its own row record (tx, ty, kL, kU).
+__device__ __forceinline__ void warp_win_cert(const double (*srow)[2], int lane, int n, double reach, double ox,
+                                              double oy, bool enabled, WinCert& c, RowRec& rec) {
+    cert_disable(c, n);
+    cert_row_disable(rec);
+    if (!enabled || n < 1) return;
+    const double dom = 1.01 * reach + fmax(fabs(ox), fabs(oy)) + 0.01, domw = 1.0001 * dom;
+    c.dom = (float)dom;
+    if (n == 1) {
+        if (lane == 0) { rec.kL = kCertHuge; rec.kU = -kCertHuge; }
+        c.blo = -kCertHuge; c.bhi = kCertHuge;
+        return;
     }
-#pragma unroll
-    for (int w = 0; w < 2; ++w) {
-        n0x[w] = tx[w] - tx[1 - w]; n0y[w] = ty[w] - ty[1 - w];          // target minus the other end (not normalised:
-        mine[w] = lane < n && lane != target[w];                         //  the slopes below are ratios)
-        gx[w] = tx[w] - rx; gy[w] = ty[w] - ry;
-        const double along = gx[w] * n0x[w] + gy[w] * n0y[w], across = n0x[w] * gy[w] - n0y[w] * gx[w];
-        const bool bad = mine[w] && (!(along > 0.05 * fabs(across)) || !(along > 0.0));
-        ok[w] = !__any_sync(0xffffffffu, bad) && (n0x[w] * n0x[w] + n0y[w] * n0y[w] > 0.0);
-        sl[w] = mine[w] && along > 0.0 ? across * fast_rcp(along) : 0.0;
+    double chx = srow[n - 1][0] - srow[0][0], chy = srow[n - 1][1] - srow[0][1];
+    const double ch2 = chx * chx + chy * chy;
+    if (!(ch2 > 0.0)) return;
+    const double ich = rsqrt64_(ch2);
+    chx *= ich; chy *= ich;
+    const double nux = (double)(float)(-chy), nuy = (double)(float)chx;
+    const bool valid = lane < n;
+    const double rx = valid ? srow[lane][0] : 0.0, ry = valid ? srow[lane][1] : 0.0;
+    const double cmax = warp_max_d(rx * rx + ry * ry);
+    const double ab = 2.0000001 * cmax * rsqrt64_(fmax(cmax, 1e-300));       // |a_j|, |b_j| <= 2 sqrt(cmax)
+    const double margin = cert_margin(ab, ab, cmax, domw);
+    const double wmin = kCertMinLateral * reach;
+    const double bmax = (fabs(nux) + fabs(nuy)) * domw;
+    double lo = -bmax, hi = bmax;
+    if (valid) {
+        auto row = [&](int j, double& x, double& y) { x = srow[j][0]; y = srow[j][1]; };
+        const RowGeom g = cert_row_geom(row, lane, n, nux, nuy, margin);
+        const double delta = cert_delta(g.tx, g.ty, g.k, domw);
+        rec.tx = (float)g.tx; rec.ty = (float)g.ty;
+        if (lane == 0) rec.kL = kCertHuge;
+        else if (cert_role_usable(g.L, g.b, wmin)) { rec.kL = (float)(g.k - delta); lo = fmax(lo, g.L.lo); hi = fmin(hi, g.L.hi); }
+        if (lane == n - 1) rec.kU = -kCertHuge;
+        else if (cert_role_usable(g.U, g.b, wmin)) { rec.kU = (float)(g.k + delta); lo = fmax(lo, g.U.lo); hi = fmin(hi, g.U.hi); }
     }
-    double smin[2], smax[2];
-#pragma unroll
-    for (int w = 0; w < 2; ++w) { smin[w] = mine[w] ? sl[w] : 1e300; smax[w] = mine[w] ? sl[w] : -1e300; }
+    // ---- index estimate: Kasa circle fit on centred chord coordinates, quadratic fit of the index on w ----
+    const double sj = chx * rx + chy * ry, bj = nux * rx + nuy * ry;
+    double ms = valid ? sj : 0.0, mb = valid ? bj : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {
-            smin[w] = fmin(smin[w], __shfl_xor_sync(0xffffffffu, smin[w], o));
-            smax[w] = fmax(smax[w], __shfl_xor_sync(0xffffffffu, smax[w], o));
-        }
+        lo = fmax(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmin(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        ms += __shfl_xor_sync(0xffffffffu, ms, o); mb += __shfl_xor_sync(0xffffffffu, mb, o);
     }
-    double mx[2][2], my[2][2], bx[2], by[2], tau[2];
-#pragma unroll
-    for (int w = 0; w < 2; ++w) {
-        smin[w] -= 2e-7 * (1.0 + smin[w] * smin[w]); smax[w] += 2e-7 * (1.0 + smax[w] * smax[w]);   // widen the cone
-        const double s2[2] = { smin[w], smax[w] };
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const double vx = n0x[w] - s2[i] * n0y[w], vy = n0y[w] + s2[i] * n0x[w];
-            const double inv = fast_rsqrt(vx * vx + vy * vy);
-            mx[w][i] = vx * inv; my[w][i] = vy * inv;
-        }
-        bx[w] = mx[w][0] + mx[w][1]; by[w] = my[w][0] + my[w][1];       // bisector, not normalised: z = r_t + tau * b
-        const double bn2 = bx[w] * bx[w] + by[w] * by[w];
-        ok[w] = ok[w] && bn2 > 1e-6;
-        const double g2 = gx[w] * gx[w] + gy[w] * gy[w], ng = bx[w] * gx[w] + by[w] * gy[w];
-        ok[w] = ok[w] && !__any_sync(0xffffffffu, mine[w] && !(ng > 0.0));
-        tau[w] = mine[w] && ng > 0.0 ? fmax(0.5 * (margin - g2) * fast_rcp(ng), 0.0) * 1.000001 : 0.0;
-    }
+    cert_store_range(c, nux, nuy, lo, hi, bmax);
+    if (n < 3) return;
+    const double inv_n = rcp64_((double)n);
+    ms *= inv_n; mb *= inv_n;
+    const double u = valid ? sj - ms : 0.0, v = valid ? bj - mb : 0.0, z = u * u + v * v;
+    double suu = u * u, svv = v * v, suv = u * v, suz = u * z, svz = v * z;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int w = 0; w < 2; ++w) tau[w] = fmax(tau[w], __shfl_xor_sync(0xffffffffu, tau[w], o));
+        suu += __shfl_xor_sync(0xffffffffu, suu, o); svv += __shfl_xor_sync(0xffffffffu, svv, o);
+        suv += __shfl_xor_sync(0xffffffffu, suv, o); suz += __shfl_xor_sync(0xffffffffu, suz, o);
+        svz += __shfl_xor_sync(0xffffffffu, svz, o);
     }
-#pragma unroll
-    for (int w = 0; w < 2; ++w) {
-        const double bn2 = bx[w] * bx[w] + by[w] * by[w];
-        ok[w] = ok[w] && (tau[w] * tau[w] * bn2 <= kCertMaxTau * kCertMaxTau);
+    const double det = suu * svv - suv * suv;
+    double sc = ms, bc = mb + 1.0e6;                                   // straight window: centre far away
+    if (fabs(det) > 1e-12 * suu * suu) {
+        const double idet = rcp64_(det);
+        const double uc = 0.5 * (suz * svv - svz * suv) * idet, vc = 0.5 * (svz * suu - suz * suv) * idet;
+        if (fabs(vc) > 0.0 && fabs(vc) < 1.0e6 && fabs(uc) < 1.0e6) { sc = ms + uc; bc = mb + vc; }
     }
-    if (ok[0]) cert_finish(tx[0] + tau[0] * bx[0], ty[0] + tau[0] * by[0], mx[0], my[0], dom, c.lx, c.ly, c.lk);
-    if (ok[1]) cert_finish(tx[1] + tau[1] * bx[1], ty[1] + tau[1] * by[1], mx[1], my[1], dom, c.fx, c.fy, c.fk);
+    const double w = valid ? (sj - sc) * rcp64_(bc - bj) : 0.0;
+    const double wmax = warp_max_d(fabs(w));
+    if (!(wmax > 0.0) || !(wmax < 1e30)) return;
+    const double iw = rcp64_(wmax), W = w * iw, jd = (double)lane;
+    double m0 = valid ? 1.0 : 0.0, m1 = m0 * W, m2 = m1 * W, m3 = m2 * W, m4 = m3 * W;
+    double r0 = m0 * jd, r1 = m1 * jd, r2 = m2 * jd;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m0 += __shfl_xor_sync(0xffffffffu, m0, o); m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+        m2 += __shfl_xor_sync(0xffffffffu, m2, o); m3 += __shfl_xor_sync(0xffffffffu, m3, o);
+        m4 += __shfl_xor_sync(0xffffffffu, m4, o); r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, o); r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+    }
+    const double D = m0 * (m2 * m4 - m3 * m3) - m1 * (m1 * m4 - m3 * m2) + m2 * (m1 * m3 - m2 * m2);
+    if (!(fabs(D) > 1e-300)) return;
+    const double iD = rcp64_(D);
+    const double q0 = (r0 * (m2 * m4 - m3 * m3) - m1 * (r1 * m4 - m3 * r2) + m2 * (r1 * m3 - m2 * r2)) * iD;
+    const double q1 = (m0 * (r1 * m4 - r2 * m3) - r0 * (m1 * m4 - m3 * m2) + m2 * (m1 * r2 - m2 * r1)) * iD * iw;
+    const double q2 = (m0 * (m2 * r2 - m3 * r1) - m1 * (m1 * r2 - m2 * r1) + r0 * (m1 * m3 - m2 * m2)) * iD * iw * iw;
+    c.sx = (float)chx; c.sy = (float)chy; c.s0 = (float)(-sc); c.bc = (float)bc;
+    c.c0 = (float)q0; c.c1 = (float)q1; c.c2 = (float)q2;
+    c.jhi = (fabs(q0) < 1e6 && fabs(q1) < 1e30 && fabs(q2) < 1e30) ? (float)(n - 2) : 0.f;
 }
 
 // ================================================================================================
@@ -270,6 +279,7 @@ __device__ __forceinline__ void warp_wedges(double rx, double ry, int lane, int 
 __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, const double* __restrict__ ref,
                                                           char* __restrict__ step_blocks, bool pull_inputs,
                                                           unsigned long long* __restrict__ seq) {
+    __shared__ double srow[kWindowPad][2];        // local window rows for the certificate construction
     const int e = blockIdx.x, lane = threadIdx.x, T = cfg.T;
     if (e == 0 && lane == 0) *seq += 1ull;        // step sequence number, read by every later kernel of the step
     const bool zc = io.host_in != nullptr && pull_inputs;
@@ -320,7 +330,6 @@ __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, 
         const int j2 = __shfl_xor_sync(0xffffffffu, j, o);
         if (d2 < d || (d2 == d && j2 < j)) { d = d2; j = j2; }
     }
-    const int p_old = p;
     p += j;                                                  // control.py:230
     // row p + lane of the path = preloaded row (j + lane) relative to p_old
     const int src = j + lane;                                // 0 .. 60
@@ -335,7 +344,6 @@ __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, 
         row = from_hi ? make_double4(bx, by, bz, bw) : make_double4(ax, ay, az, aw);
     }
     const double ox = __shfl_sync(0xffffffffu, row.x, 0), oy = __shfl_sync(0xffffffffu, row.y, 0);   // row p
-    (void)p_old;
     StepBlockView sb = view_step_block(step_blocks + (size_t)e * cfg.step_block_bytes);
     if (lane == 0) {
         StepHeader h;
@@ -361,24 +369,14 @@ __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, 
         // the rollouts subtract the FP32 origin from the FP32 end-effector; rows are relative to
         // the FP64 origin — the difference (<= 6e-8) is common to all candidates of a lookup
         sb.win[lane] = w; sb.rows[lane] = r;
-        {   // end-of-window certificate (make_end_cert of mppi_math.cuh, one lane per row)
+        {   // lookup certificate of the window (make_win_cert of mppi_math.cuh, one lane per row)
             const int nv = min(kWindow, n - p);
-            const bool valid = lane < nv;
-            const double rx = valid ? row.x - ox : 0.0, ry = valid ? row.y - oy : 0.0;
-            const double aox = fabs(ox), aoy = fabs(oy);
-            const double dom = 1.01 * (cfg.cost_l1 + cfg.cost_l2) + fmax(aox, aoy) + 0.01;
-            EndCert c;
-            c.dom = (float)dom; c.last = nv - 1; c.pad[0] = c.pad[1] = 0;
-            cert_disable(c.lx, c.ly, c.lk); cert_disable(c.fx, c.fy, c.fk);
-            if (!(cfg.flags & 16)) {                          // MPPI_FLAG_FULL_SEARCH switches the shortcut off
-                if (nv == 1) { c.fk[0] = c.fk[1] = 1.0f; }
-                else if (nv >= 2) {
-                    const double cmax = warp_max_d(rx * rx + ry * ry);            // > 0 for nv >= 2 unless all rows coincide
-                    const double ab = 2.0000001 * cmax * fast_rsqrt(fmax(cmax, 1e-300));  // |a_j|, |b_j| <= 2 sqrt(cmax)
-                    const double margin = cert_margin(ab, ab, cmax, 1.0001 * dom);
-                    warp_wedges(rx, ry, lane, nv, margin, 1.0001 * dom, c);
-                }
-            }
+            if (lane < kWindow) { srow[lane][0] = row.x - ox; srow[lane][1] = row.y - oy; }
+            __syncwarp();
+            WinCert c; RowRec rec;
+            warp_win_cert(srow, lane, nv, cfg.cost_l1 + cfg.cost_l2, ox, oy, !(cfg.flags & 16), c, rec);   // 16: MPPI_FLAG_FULL_SEARCH
+            rec.a = w.a; rec.b = w.b; rec.c = w.c; rec.pad = 0.f;
+            sb.rec[lane] = rec;
             if (lane == 0) *sb.cert = c;
         }
         // the same a/b coefficients once more, laid out as candidate pairs
@@ -424,11 +422,10 @@ struct InjectedNoise {          // eps read from the caller's [K,T,2] tensor
 // device, in stream order after the prepare kernel) into this constant-bank table, and the search's
 // FFMAs read them as immediate constant operands: no registers, no shared-memory loads, and two
 // register operands per FFMA instead of three.
-struct ConstWindow {                 // same layout as bytes [64, kStepBlockFixed) of a step block: ONE copy fills it
+struct ConstWindow {                 // same layout as the bytes of a step block that follow its header: ONE copy fills it
     WinEntry win[kWindowPad];
     RefRow rows[kWindowPad];         // (not read from here: the winning row is fetched from shared memory)
     float4 pairs[kWindowPad / 2];
-    EndCert cert;                    // read as immediate constant operands by the certificate test
 };
 __constant__ ConstWindow c_window;
 #ifndef MPPI_FFMA2_SEARCH
@@ -476,13 +473,22 @@ struct WinConst {
 #define MPPI_ROLL_MIN_BLOCKS_CONST 4
 #endif
 
-template <bool CW>
-__device__ __forceinline__ const EndCert& cert_of(const StepBlockView& sb) {
-    if constexpr (CW) return c_window.cert; else return *sb.cert;
-}
+#ifndef MPPI_ROLL_MIN_BLOCKS_CERT
+#define MPPI_ROLL_MIN_BLOCKS_CERT 4
+#endif
+
+// Window policy per kernel family.  CERT: certified lookups, the table stays in shared memory (any number of
+// environments).  Otherwise plain searches with the coefficients in the constant bank (CONSTWIN) or in registers.
+template <bool CONSTWIN, bool CERT> struct WinPolicy { typedef WinRegs type; };
+template <> struct WinPolicy<true, false> { typedef WinConst type; };
+template <bool CONSTWIN> struct WinPolicy<CONSTWIN, true> { typedef WinTable type; };
+__device__ __forceinline__ void win_load(WinTable& w, const StepBlockView& sb) { w.load(*sb.cert, sb.rec); }
+__device__ __forceinline__ void win_load(WinRegs& w, const StepBlockView& sb) { w.load(sb.win); }
+__device__ __forceinline__ void win_load(WinConst& w, const StepBlockView& sb) { w.load(sb.win); }
 
 template <int NOISE, bool CONSTWIN, int kNS, int DYN = 0, bool CERT = true>
-__global__ void __launch_bounds__(kRollThreads, CONSTWIN ? MPPI_ROLL_MIN_BLOCKS_CONST : (kNS == 1 ? 3 : 2))
+__global__ void __launch_bounds__(kRollThreads, CERT ? MPPI_ROLL_MIN_BLOCKS_CERT
+                                                     : (CONSTWIN ? MPPI_ROLL_MIN_BLOCKS_CONST : (kNS == 1 ? 3 : 2)))
 mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const char* __restrict__ step_blocks,
                     const float* __restrict__ eps, float* __restrict__ S_out, float* __restrict__ block_min,
                     unsigned long long* __restrict__ search_stats) {
@@ -500,12 +506,11 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
     mbar_wait(&bar, 0);
     const StepBlockView sb = view_step_block(smem);
     const StepHeader hd = *sb.hd;
-    typename std::conditional<CONSTWIN, WinConst, WinRegs>::type win;
-    win.load(sb.win);
-    // the certificate test reads its coefficients as constant-bank operands (single environment) or
-    // from the staged step block
-    const EndCert& cert = cert_of<CONSTWIN>(sb);
-    int hits = 0, lookups = 0;
+    typename WinPolicy<CONSTWIN, CERT>::type win;
+    win_load(win, sb);
+    const WinCert& cert = *sb.cert;                   // (staged step block; read by the certified lookups only)
+    LookupStats hits = { 0, 0 };
+    int lookups = 0;
 
     float tmin = INFINITY;
     const int T = cfg.T;
@@ -529,12 +534,12 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
                 nz[s].nc = cfg.noise; nz[s].nc.step = (uint32_t)(*step_ctr); nz[s].env = (uint32_t)e;
                 nz[s].k = (uint32_t)(cfg.k_offset + kl[s]);
             }
-            rollout_cost_n<kNS, DYN, CERT>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
+            rollout_cost_n<kNS, DYN>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
         } else {
             InjectedNoise nz[kNS];
 #pragma unroll
             for (int s = 0; s < kNS; ++s) nz[s].row = (const float2*)eps + ((size_t)e * cfg.K_local + kl[s]) * T;
-            rollout_cost_n<kNS, DYN, CERT>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
+            rollout_cost_n<kNS, DYN>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
         }
 #pragma unroll
         for (int s = 0; s < kNS; ++s) {
@@ -547,8 +552,9 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
     tmin = warp_min(tmin);
     if ((tid & 31) == 0) red[tid >> 5] = tmin;
     if ((cfg.flags & 64) && (tid & 31) == 0) {              // MPPI_FLAG_SEARCH_STATS: warp-lookups certified / done
-        atomicAdd(search_stats, (unsigned long long)hits);
+        atomicAdd(search_stats, (unsigned long long)hits.end);
         atomicAdd(search_stats + 1, (unsigned long long)lookups);
+        atomicAdd(search_stats + 2, (unsigned long long)hits.tri);
     }
     __syncthreads();
     if (tid == 0) {
@@ -786,7 +792,7 @@ mppi_softmin_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ct
         double r = 0.0;
 #pragma unroll
         for (int i = 0; i < kWsumThreads / 32; ++i) r += redd[i];
-        eta_part[(size_t)e * cfg.g_soft + blockIdx.x] = r;
+        eta_part[(size_t)e * gridDim.x + blockIdx.x] = r;       // [n_env][gridDim.x] (sized for g_wsum >= gridDim.x)
     }
     float* vrow = v_part + ((size_t)e * cfg.g_wsum + blockIdx.x) * 2 * cfg.T;
     for (int pr = tid; pr < n_pairs; pr += kWsumThreads) {
@@ -809,7 +815,7 @@ mppi_softmin_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ct
     const int G = gridDim.x;
     if (warp == 0) {
         double a = 0.0;
-        for (int i = lane; i < G; i += 32) a += __ldcg(eta_part + (size_t)e * cfg.g_soft + i);
+        for (int i = lane; i < G; i += 32) a += __ldcg(eta_part + (size_t)e * G + i);
         a = warp_sum(a);
         if (lane == 0) { out[0] = (double)rho; out[1] = a; tickets[e] = 0u; }
     }

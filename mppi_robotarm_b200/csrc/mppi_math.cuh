@@ -62,6 +62,25 @@ MPPI_HD int f2i(float a) { union { float f; int i; } u; u.f = a; return u.i; }
 MPPI_HD float i2f(int a) { union { float f; int i; } u; u.i = a; return u.f; }
 #endif
 
+// FP64 reciprocal / reciprocal square root.  Device: FP32 MUFU seed + two Newton steps (~1e-14 relative) —
+// the certificate construction is a chain of divisions on the latency path of every control step and
+// its results only feed quantities that carry >= 1e-9 of deliberate slack.
+#if defined(__CUDA_ARCH__)
+MPPI_HD double rcp64_(double x) {
+    double r = (double)__frcp_rn((float)x);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return fma(r, fma(-x, r, 1.0), r);
+}
+MPPI_HD double rsqrt64_(double x) {
+    double r = (double)rsqrtf((float)x);
+    r = r * fma(-0.5 * x * r, r, 1.5);
+    return r * fma(-0.5 * x * r, r, 1.5);
+}
+#else
+MPPI_HD double rcp64_(double x) { return 1.0 / x; }
+MPPI_HD double rsqrt64_(double x) { return 1.0 / sqrt(x); }
+#endif
+
 // ---- sin & cos of one angle, ~1 ulp, no slow path --------------------------------------------
 // Cody-Waite reduction by pi/2 in three FMA steps, then degree-7 / degree-8 minimax polynomials on
 // [-pi/4, pi/4].  Valid for |x| < ~1e5 rad; a diverged rollout (larger angle, Inf, NaN) yields a
@@ -196,15 +215,6 @@ MPPI_HD void fk_local(const ArmState& st, const ArmF& A, float ox, float oy, flo
     yl = fma_(A.L2, st.s12, fma_(A.L1, st.s1, -oy));
 }
 
-// Candidate key: distance (minus the common |p'|^2) with the candidate index in the 5 low mantissa
-// bits, so a plain float min returns value and arg-min together (FMNMX3 on sm_100a).
-MPPI_HD float cand_key(float a, float b, float c, float xl, float yl, int j) {
-    float d = fma_(a, xl, fma_(b, yl, c));
-    return i2f((f2i(d) & ~31) | j);
-}
-
-MPPI_HD float min3_(float a, float b, float c) { return fminf(fminf(a, b), c); }
-
 // Weighted squared residuals of (x, y, dq1, dq2) against one waypoint row (control.py:183-185).
 MPPI_HD void residuals(const ArmState& st, float xl, float yl, const RefRow& r,
                        float& ex, float& ey, float& e1, float& e2) {
@@ -310,143 +320,290 @@ struct StepHeader {            // first 64 bytes of a step block (one per enviro
 };
 static_assert(sizeof(StepHeader) == 64, "header is 64 bytes");
 
-// ---- end-of-window certificate ------------------------------------------------------------------
-// The window (control.py:208-209) is fixed for the whole horizon while the rollouts move along the
-// path at about one waypoint per step, so after ~10-20 horizon steps every sample of a warp lies
-// beyond the last window row (or, for an arm that falls back, before the first) and the 30-candidate
-// search can only return that row.  The prepare kernel derives, in FP64, two half-planes whose
-// intersection (a wedge) lies inside the Voronoi cell of the last row — and two for row 0 — with a
-// margin that covers every FP32 rounding of the search AND of the test itself: if
-//     mx_i x' + my_i y' + k_i >= 0  (i = 0, 1)   and   |x'|, |y'| <= dom
-// then the full FP32 search is guaranteed to return that row, so it is skipped when a whole warp is
-// certified.  Results are bit-identical with and without the shortcut (tests: emulation + GPU).
-// Derivation: with g_j = r_L - r_j,  d_j - d_L = |g_j|^2 + 2 g_j.(p - r_L).  All g_j lie in the cone
-// spanned by the two extreme directions m_0, m_1; for p = z + s with s.m_0 >= 0 and s.m_1 >= 0 every
-// s.g_j >= 0, hence d_j - d_L >= |g_j|^2 + 2 tau n.g_j at the apex z = r_L + tau n, and tau is chosen
-// so that this is >= the rounding margin for every j.
-struct alignas(16) EndCert {   // 64 bytes of a step block
-    float lx[2], ly[2], lk[2]; // wedge inside the cell of the last valid row
-    float fx[2], fy[2], fk[2]; // wedge inside the cell of row 0
+// ---- certified nearest-waypoint lookup ------------------------------------------------------------
+// The 30-candidate search (control.py:208-215) costs more than the arm dynamics.  The window is fixed
+// for the whole horizon while the rollouts move along a smooth path, so almost every lookup can be
+// answered from a handful of half-plane tests whose validity the prepare kernel PROVES in FP64 for the
+// window at hand.  Results are bit-identical with and without the shortcut (tests: emulation + GPU).
+//
+// Per window row a the prepare kernel stores a direction tau_a (the local path tangent, rounded to
+// FP32) and the offset k_a = -tau_a.r_a, and for the whole window a lateral coordinate b = nu.p (nu =
+// normal of the window chord, rounded to FP32) with a range [blo, bhi].  It guarantees:
+//   L(a): tau_a.p + k_a >= 0 ("p is ahead of row a"), blo <= b <= bhi, |x'|,|y'| <= dom
+//         ==> the FP32 search value D_a is strictly below D_j for every j < a;
+//   U(a): tau_a.p + k_a <= 0 ("p is behind row a"), same box  ==>  D_a < D_j for every j > a.
+// Derivation: with g = r_a - r_j, d_j - d_a = |g|^2 + 2 g.(p - r_a) is linear in p.  The region of
+// L(a) is the half-strip  V0 + beta v1 + alpha d'  (alpha >= 0, beta in [blo, bhi]) where (tau; nu) V0 =
+// (-k_a; 0), (tau; nu) v1 = (0; 1), (tau; nu) d' = (1; 0).  A linear function is bounded below on it iff
+// g.d' >= 0 and then attains its minimum at beta = blo or bhi, alpha = 0: per pair (a, j) that is one
+// sign test plus one bound on blo or bhi, and [blo, bhi] is the intersection over all pairs.  `margin`
+// covers twice the rounding of both FP32 distances, every threshold is moved by the rounding of its own
+// FP32 evaluation (cert_delta), and roles whose bounds would not even admit 1 % of the reach around
+// the path are switched off instead (k = -/+ huge: the test can never pass).
+// The rollouts use it twice (nearest_wp below): first for the two window ends — L(last) or U(0) for a
+// whole warp: the answer is that row without loading anything; else each lane guesses j0 from a
+// fitted estimate (centre of curvature + quadratic), and L(j0-1) and U(j0+1) certify that the arg-min is
+// one of j0-1, j0, j0+1, which are then compared exactly like the full search would.  The estimate needs
+// no proof: a wrong guess fails the tests and the warp runs the exact search.
+struct RowRec {                // 32 bytes per window row: search coefficients + certificate of the row
+    float a, b, c, pad;        // d_j - |p'|^2 = c + a x' + b y'
+    float tx, ty, kL, kU;      // L: tx x' + ty y' + kL >= 0,  U: tx x' + ty y' + kU <= 0
+};
+struct alignas(16) WinCert {   // 64 bytes of a step block
+    float nx, ny;              // lateral coordinate b = nx x' + ny y'
+    float blo, bhi;            // certified lateral range (blo > bhi: nothing is certified)
+    float sx, sy, s0;          // s = sx x' + sy y' + s0: along-chord coordinate relative to the fitted centre
+    float bc;                  // lateral coordinate of the fitted centre: w = s / (bc - b)
+    float c0, c1, c2;          // index estimate c0 + w (c1 + w c2)
+    float jhi;                 // j0 is clamped to [1, jhi]; jhi < 1 (fewer than 3 rows): no triples
     float dom;                 // the margins hold for |x'|, |y'| <= dom
     int32_t last;              // index of the last valid row (n_valid - 1)
     int32_t pad[2];
 };
-static_assert(sizeof(EndCert) == 64, "certificate block is 64 bytes");
+static_assert(sizeof(WinCert) == 64 && sizeof(RowRec) == 32, "certificate layout");
 
-// Certificate test for (x', y'): wl >= 0 certifies the last row, wf >= 0 certifies row 0 (the two
-// wedges are disjoint), both only inside the domain the margins were derived for.
-struct CertTest { float wl, wf; bool in_dom; };
-MPPI_HD CertTest cert_test(const EndCert& c, float xl, float yl) {
-    CertTest t;
-#if defined(__CUDA_ARCH__) && !defined(MPPI_CERT_SCALAR)
-    // the two half-planes of a wedge as one packed fma.rn.f32x2 chain (same roundings as the scalar form)
-    const unsigned long long x2 = ((unsigned long long)__float_as_uint(xl) << 32) | __float_as_uint(xl);
-    const unsigned long long y2 = ((unsigned long long)__float_as_uint(yl) << 32) | __float_as_uint(yl);
-    const unsigned long long* q = reinterpret_cast<const unsigned long long*>(&c);   // lx, ly, lk, fx, fy, fk pairs
-    unsigned long long a, b;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(a) : "l"(q[1]), "l"(y2), "l"(q[2]));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(a) : "l"(q[0]), "l"(x2), "l"(a));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(b) : "l"(q[4]), "l"(y2), "l"(q[5]));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(b) : "l"(q[3]), "l"(x2), "l"(b));
-    t.wl = fminf(__uint_as_float((unsigned)a), __uint_as_float((unsigned)(a >> 32)));
-    t.wf = fminf(__uint_as_float((unsigned)b), __uint_as_float((unsigned)(b >> 32)));
-#else
-    t.wl = fminf(fma_(c.lx[0], xl, fma_(c.ly[0], yl, c.lk[0])), fma_(c.lx[1], xl, fma_(c.ly[1], yl, c.lk[1])));
-    t.wf = fminf(fma_(c.fx[0], xl, fma_(c.fy[0], yl, c.fk[0])), fma_(c.fx[1], xl, fma_(c.fy[1], yl, c.fk[1])));
-#endif
-    t.in_dom = fmaxf(fabsf(xl), fabsf(yl)) <= c.dom;               // false for NaN
-    return t;
-}
-MPPI_HD bool cert_ok(const CertTest& t) { return t.in_dom && fmaxf(t.wl, t.wf) >= 0.0f; }
-MPPI_HD int cert_row(const EndCert& c, const CertTest& t) { return t.wl >= 0.0f ? c.last : 0; }
-// index the search is certain to return for (x', y'), or -1 when nothing is certified
-MPPI_HD int cert_pick(const EndCert& c, float xl, float yl) {
-    const CertTest t = cert_test(c, xl, yl);
-    return cert_ok(t) ? cert_row(c, t) : -1;
-}
-
-MPPI_HD void cert_disable(float (&mx)[2], float (&my)[2], float (&k)[2]) {
-    mx[0] = mx[1] = 0.f; my[0] = my[1] = 0.f; k[0] = k[1] = -INFINITY;
-}
-
-// One wedge: rows[j] = (x, y) of window row j in local coordinates (FP64), n rows valid, `target`
-// = 0 or n-1.  amax/bmax/cmax bound |a_j|, |b_j|, c_j of the FP32 table.  Serial form (host tests and
-// the reference for the warp-parallel version in the prepare kernel).
+constexpr float kCertHuge = 3.0e38f;
 constexpr double kCertU = 5.9604644775390625e-08;      // 2^-24
-constexpr double kCertMaxTau = 0.25;                   // give up when the apex would be > 25 cm past the row
+constexpr double kCertMinLateral = 0.01;               // a role must admit +-1 % of the reach around its row
+
 MPPI_HD double cert_margin(double amax, double bmax, double cmax, double dom) {
     // |D_j - d_j| <= 3u(|a x| + |b y| + c) for D = fma(a, x, fma(b, y, c)) with rounded a, b, c; the
     // test needs d_j - d_t > 2 * that; factor 2 of slack on top
     return 16.0 * kCertU * (amax * dom + bmax * dom + cmax);
 }
-MPPI_HD void cert_finish(double zx, double zy, const double (&mx)[2], const double (&my)[2], double dom,
-                         float (&ox)[2], float (&oy)[2], float (&ok)[2]) {
-    for (int i = 0; i < 2; ++i) {
-        const double k = -(mx[i] * zx + my[i] * zy);
-        // the FP32 value of mx x + my y + k differs from the exact one by <= 3u(|x| + |y| + |k|)
-        const double delta = 8.0 * kCertU * (2.0 * dom + fabs(k)) + 1e-30;
-        ox[i] = (float)mx[i]; oy[i] = (float)my[i]; ok[i] = (float)(k - delta);
-    }
+// rounding of fma(tx, x, fma(ty, y, k)) incl. the conversion of k to float, for |x|, |y| <= dom
+MPPI_HD double cert_delta(double tx, double ty, double k, double dom) {
+    return 8.0 * kCertU * ((fabs(tx) + fabs(ty)) * dom + fabs(k)) + 1e-30;
 }
-MPPI_HD void make_wedge(const double (*rows)[2], int n, int target, double margin, double dom,
-                        float (&ox)[2], float (&oy)[2], float (&ok)[2]) {
-    cert_disable(ox, oy, ok);
-    if (n < 2) return;
-    const int other = target == 0 ? n - 1 : 0;
-    double n0x = rows[target][0] - rows[other][0], n0y = rows[target][1] - rows[other][1];
-    const double n0 = sqrt(n0x * n0x + n0y * n0y);
-    if (!(n0 > 0.0)) return;
-    n0x /= n0; n0y /= n0;
-    double smin = 1e300, smax = -1e300;
-    for (int j = 0; j < n; ++j) {
-        if (j == target) continue;
-        const double gx = rows[target][0] - rows[j][0], gy = rows[target][1] - rows[j][1];
-        const double along = gx * n0x + gy * n0y, across = n0x * gy - n0y * gx;
-        if (!(along > 0.05 * fabs(across)) || !(along > 0.0)) return;   // direction spread too wide (or duplicate rows)
-        const double s = across / along;
-        smin = s < smin ? s : smin; smax = s > smax ? s : smax;
-    }
-    smin -= 1e-7 * (1.0 + smin * smin); smax += 1e-7 * (1.0 + smax * smax);     // widen the cone by ~1e-7 rad
-    double mx[2], my[2];
-    const double s2[2] = { smin, smax };
-    for (int i = 0; i < 2; ++i) {
-        const double vx = n0x - s2[i] * n0y, vy = n0y + s2[i] * n0x, vn = sqrt(vx * vx + vy * vy);
-        mx[i] = vx / vn; my[i] = vy / vn;
-    }
-    double bx = mx[0] + mx[1], by = my[0] + my[1];
-    const double bn = sqrt(bx * bx + by * by);
-    if (!(bn > 1e-3)) return;
-    bx /= bn; by /= bn;
-    double tau = 0.0;
-    for (int j = 0; j < n; ++j) {
-        if (j == target) continue;
-        const double gx = rows[target][0] - rows[j][0], gy = rows[target][1] - rows[j][1];
-        const double g2 = gx * gx + gy * gy, ng = bx * gx + by * gy;
-        if (!(ng > 0.0)) return;
-        const double t = (margin - g2) / (2.0 * ng);
-        tau = t > tau ? t : tau;
-    }
-    if (!(tau <= kCertMaxTau)) return;
-    cert_finish(rows[target][0] + tau * bx, rows[target][1] + tau * by, mx, my, dom, ox, oy, ok);
+MPPI_HD void cert_disable(WinCert& c, int n_valid) {
+    c.nx = c.ny = 0.f; c.blo = kCertHuge; c.bhi = -kCertHuge;
+    c.sx = c.sy = c.s0 = 0.f; c.bc = 1.f; c.c0 = c.c1 = c.c2 = 0.f; c.jhi = 0.f;
+    c.dom = 0.f; c.last = n_valid - 1; c.pad[0] = c.pad[1] = 0;
 }
-// rows: the n_valid local rows (FP64); reach = L1 + L2 of the cost-side kinematics; (ox, oy) = window origin
-MPPI_HD void make_end_cert(const double (*rows)[2], int n_valid, double reach, double ox, double oy,
-                           bool enabled, EndCert& c) {
-    const double aox = fabs(ox), aoy = fabs(oy);
-    const double dom = 1.01 * reach + (aox > aoy ? aox : aoy) + 0.01;
-    c.dom = (float)dom; c.last = n_valid - 1; c.pad[0] = c.pad[1] = 0;
-    cert_disable(c.lx, c.ly, c.lk); cert_disable(c.fx, c.fy, c.fk);
+MPPI_HD void cert_row_disable(RowRec& r) { r.tx = 0.f; r.ty = 0.f; r.kL = -kCertHuge; r.kU = kCertHuge; }
+
+// What one row contributes (FP64): its tangent, offset, and the bounds its two roles put on [blo, bhi].
+struct RowRole { double lo, hi; bool ok; };
+struct RowGeom { double tx, ty, k, b; RowRole L, U; };
+
+// Row a of `n` local rows (rx[], ry[] via the accessor) against every other row.  nu = window normal
+// (already rounded to FP32 and widened back).  `row(j, x, y)` fetches row j.
+template <class RowFn>
+MPPI_HD RowGeom cert_row_geom(RowFn row, int a, int n, double nux, double nuy, double margin) {
+    RowGeom g;
+    double ax, ay, px, py, qx, qy;
+    row(a, ax, ay);
+    row(a > 0 ? a - 1 : a, px, py);
+    row(a + 1 < n ? a + 1 : a, qx, qy);
+    double tx = qx - px, ty = qy - py;
+    const double tn2 = tx * tx + ty * ty;
+    g.L.ok = g.U.ok = tn2 > 0.0;
+    g.L.lo = g.U.lo = -1e300; g.L.hi = g.U.hi = 1e300;
+    const double itn = tn2 > 0.0 ? rsqrt64_(tn2) : 0.0;
+    tx *= itn; ty *= itn;
+    tx = (double)(float)tx; ty = (double)(float)ty;          // the direction the FP32 test will use
+    g.tx = tx; g.ty = ty; g.k = -(tx * ax + ty * ay); g.b = nux * ax + nuy * ay;
+    const double det = tx * nuy - ty * nux;
+    if (!(fabs(det) > 0.5)) { g.L.ok = g.U.ok = false; return g; }     // tangent more than 60 degrees off the chord
+    const double idet = rcp64_(det);
+    const double v0x = -g.k * nuy * idet, v0y = g.k * nux * idet;      // tau.V0 = -k, nu.V0 = 0
+    const double v1x = -ty * idet, v1y = tx * idet;                    // tau.v1 = 0,  nu.v1 = 1
+    const double dx = nuy * idet, dy = -nux * idet;                    // tau.d' = 1,  nu.d' = 0
+    for (int j = 0; j < n; ++j) {
+        if (j == a) continue;
+        double jx, jy;
+        row(j, jx, jy);
+        const double gx = ax - jx, gy = ay - jy;
+        RowRole& r = j < a ? g.L : g.U;
+        const double along = gx * dx + gy * dy;
+        if (j < a ? !(along > 0.0) : !(along < 0.0)) { r.ok = false; continue; }
+        const double f0 = gx * gx + gy * gy + 2.0 * (gx * (v0x - ax) + gy * (v0y - ay));
+        const double sl = 2.0 * (gx * v1x + gy * v1y);
+        if (sl > 0.0) { const double bnd = (margin - f0) * rcp64_(sl); r.lo = bnd > r.lo ? bnd : r.lo; }
+        else if (sl < 0.0) { const double bnd = (margin - f0) * rcp64_(sl); r.hi = bnd < r.hi ? bnd : r.hi; }
+        else if (!(f0 >= margin)) r.ok = false;
+    }
+    return g;
+}
+MPPI_HD bool cert_role_usable(const RowRole& r, double b, double wmin) {
+    return r.ok && r.lo <= b - wmin && r.hi >= b + wmin;
+}
+
+// [blo, bhi] as the FP32 test will see it: moved inwards by the rounding of b = fma(nx, x, ny * y), of the
+// float conversion, and by 1e-9 relative for the approximate reciprocals of the device construction.
+MPPI_HD void cert_store_range(WinCert& c, double nux, double nuy, double blo, double bhi, double bmax) {
+    const double eb = (8.0 * kCertU + 1e-9) * bmax + 1e-30;
+    c.nx = (float)nux; c.ny = (float)nuy;
+    c.blo = (float)(blo + eb); c.bhi = (float)(bhi - eb);
+}
+
+// Index estimate (no proof needed): circle through the rows (Kasa fit on centred chord coordinates), then
+// a quadratic least-squares fit of the row index on w = (s - sc) / (bc - b), which is the tangent of the
+// angle about the centre and therefore linear in the index on an arc traversed at constant speed.
+MPPI_HD void cert_fit_estimate(const double* s, const double* b, int n, WinCert& c, double sgx, double sgy) {
+    c.jhi = 0.f;
+    if (n < 3) return;
+    double ms = 0, mb = 0;
+    for (int j = 0; j < n; ++j) { ms += s[j]; mb += b[j]; }
+    ms /= n; mb /= n;
+    double suu = 0, svv = 0, suv = 0, suz = 0, svz = 0;
+    for (int j = 0; j < n; ++j) {
+        const double u = s[j] - ms, v = b[j] - mb, z = u * u + v * v;
+        suu += u * u; svv += v * v; suv += u * v; suz += u * z; svz += v * z;
+    }
+    const double det = suu * svv - suv * suv;
+    double sc = ms, bc = mb + 1.0e6;                                   // straight window: centre far away
+    if (fabs(det) > 1e-12 * suu * suu) {
+        const double uc = 0.5 * (suz * svv - svz * suv) / det, vc = 0.5 * (svz * suu - suz * suv) / det;
+        if (fabs(vc) > 0.0 && fabs(vc) < 1.0e6 && fabs(uc) < 1.0e6) { sc = ms + uc; bc = mb + vc; }
+    }
+    double wmax = 0;
+    for (int j = 0; j < n; ++j) {
+        const double w = (s[j] - sc) / (bc - b[j]);
+        wmax = fabs(w) > wmax ? fabs(w) : wmax;
+    }
+    if (!(wmax > 0.0) || !(wmax < 1e30)) return;
+    double m[5] = { 0, 0, 0, 0, 0 }, r[3] = { 0, 0, 0 };                // moments of W = w / wmax
+    for (int j = 0; j < n; ++j) {
+        const double W = (s[j] - sc) / (bc - b[j]) / wmax;
+        double p = 1.0;
+        for (int e = 0; e < 5; ++e) { m[e] += p; if (e < 3) r[e] += p * j; p *= W; }
+    }
+    // solve [m0 m1 m2; m1 m2 m3; m2 m3 m4] q = r (Cramer)
+    const double D = m[0] * (m[2] * m[4] - m[3] * m[3]) - m[1] * (m[1] * m[4] - m[3] * m[2]) + m[2] * (m[1] * m[3] - m[2] * m[2]);
+    if (!(fabs(D) > 1e-300)) return;
+    const double q0 = (r[0] * (m[2] * m[4] - m[3] * m[3]) - m[1] * (r[1] * m[4] - m[3] * r[2]) + m[2] * (r[1] * m[3] - m[2] * r[2])) / D;
+    const double q1 = (m[0] * (r[1] * m[4] - r[2] * m[3]) - r[0] * (m[1] * m[4] - m[3] * m[2]) + m[2] * (m[1] * r[2] - m[2] * r[1])) / D;
+    const double q2 = (m[0] * (m[2] * r[2] - m[3] * r[1]) - m[1] * (m[1] * r[2] - m[2] * r[1]) + r[0] * (m[1] * m[3] - m[2] * m[2])) / D;
+    c.sx = (float)sgx; c.sy = (float)sgy; c.s0 = (float)(-sc); c.bc = (float)bc;
+    c.c0 = (float)q0; c.c1 = (float)(q1 / wmax); c.c2 = (float)(q2 / (wmax * wmax));
+    const bool fin = fabs(q0) < 1e6 && fabs(q1 / wmax) < 1e30 && fabs(q2 / (wmax * wmax)) < 1e30;
+    c.jhi = fin ? (float)(n - 2) : 0.f;
+}
+
+// The certificate of one window, serial form (host tests; the prepare kernel runs the same steps with one
+// lane per row).  rows: the n_valid local rows (FP64); reach = L1 + L2 of the cost-side kinematics;
+// (ox, oy) = window origin; tab[j].{tx, ty, kL, kU} are filled for all kWindowPad rows.
+MPPI_HD void make_win_cert(const double (*rows)[2], int n_valid, double reach, double ox, double oy,
+                           bool enabled, WinCert& c, RowRec* tab) {
+    cert_disable(c, n_valid);
+    for (int j = 0; j < kWindowPad; ++j) cert_row_disable(tab[j]);
     if (!enabled || n_valid < 1) return;
-    if (n_valid == 1) { c.fk[0] = c.fk[1] = 1.0f; return; }       // a one-row window: the search can only return row 0
+    const double aox = fabs(ox), aoy = fabs(oy);
+    const double dom = 1.01 * reach + (aox > aoy ? aox : aoy) + 0.01, domw = 1.0001 * dom;
+    c.dom = (float)dom;
+    if (n_valid == 1) {                                     // a one-row window: the search can only return row 0
+        tab[0].kL = kCertHuge; tab[0].kU = -kCertHuge; c.blo = -kCertHuge; c.bhi = kCertHuge;
+        return;
+    }
+    double chx = rows[n_valid - 1][0] - rows[0][0], chy = rows[n_valid - 1][1] - rows[0][1];
+    const double chn = sqrt(chx * chx + chy * chy);
+    if (!(chn > 0.0)) return;
+    chx /= chn; chy /= chn;
+    const double nux = (double)(float)(-chy), nuy = (double)(float)chx;
     double cmax = 0;
     for (int j = 0; j < n_valid; ++j) {
         const double cc = rows[j][0] * rows[j][0] + rows[j][1] * rows[j][1];
         cmax = cc > cmax ? cc : cmax;
     }
-    const double ab = 2.0000001 * sqrt(cmax);                 // |a_j|, |b_j| <= 2 sqrt(cmax)
-    const double margin = cert_margin(ab, ab, cmax, 1.0001 * dom);
-    make_wedge(rows, n_valid, n_valid - 1, margin, 1.0001 * dom, c.lx, c.ly, c.lk);
-    make_wedge(rows, n_valid, 0, margin, 1.0001 * dom, c.fx, c.fy, c.fk);
+    const double ab = 2.0000001 * sqrt(cmax);               // |a_j|, |b_j| <= 2 sqrt(cmax)
+    const double margin = cert_margin(ab, ab, cmax, domw);
+    const double wmin = kCertMinLateral * reach;
+    auto row = [&](int j, double& x, double& y) { x = rows[j][0]; y = rows[j][1]; };
+    const double bmax = (fabs(nux) + fabs(nuy)) * domw;
+    double blo = -bmax, bhi = bmax;
+    double sj[kWindow], bj[kWindow];
+    for (int a = 0; a < n_valid; ++a) {
+        const RowGeom g = cert_row_geom(row, a, n_valid, nux, nuy, margin);
+        const double delta = cert_delta(g.tx, g.ty, g.k, domw);
+        RowRec& r = tab[a];
+        r.tx = (float)g.tx; r.ty = (float)g.ty;
+        if (a == 0) r.kL = kCertHuge;                        // no rows below row 0
+        else if (cert_role_usable(g.L, g.b, wmin)) {
+            r.kL = (float)(g.k - delta); blo = g.L.lo > blo ? g.L.lo : blo; bhi = g.L.hi < bhi ? g.L.hi : bhi;
+        }
+        if (a == n_valid - 1) r.kU = -kCertHuge;             // no rows above the last one
+        else if (cert_role_usable(g.U, g.b, wmin)) {
+            r.kU = (float)(g.k + delta); blo = g.U.lo > blo ? g.U.lo : blo; bhi = g.U.hi < bhi ? g.U.hi : bhi;
+        }
+        sj[a] = chx * rows[a][0] + chy * rows[a][1]; bj[a] = g.b;
+    }
+    // rounding of b = fma(nx, x, ny * y) and of the conversion of the bounds
+    cert_store_range(c, nux, nuy, blo, bhi, bmax);
+    cert_fit_estimate(sj, bj, n_valid, c, chx, chy);
+}
+
+// ---- the FP32 side ---------------------------------------------------------------------------------
+// Exact search over a table in memory: first arg-min of D_j = fma(a, x, fma(b, y, c)), strict `<` in index
+// order like list.index(min(d)) (the same D_j, hence the same answer, as the register tournament below).
+MPPI_HD int nearest_scan(const RowRec* tab, float xl, float yl) {
+    int best = 0;
+    float bd = fma_(tab[0].a, xl, fma_(tab[0].b, yl, tab[0].c));
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int j = 1; j < kWindow; ++j) {
+        const float d = fma_(tab[j].a, xl, fma_(tab[j].b, yl, tab[j].c));
+        if (d < bd) { bd = d; best = j; }
+    }
+    return best;
+}
+
+struct CertEnds {              // the two end tests, kept in registers by the rollouts
+    float lx, ly, lk;          // L(last)
+    float fx, fy, fk;          // U(0)
+};
+MPPI_HD CertEnds cert_ends(const WinCert& c, const RowRec* tab) {
+    CertEnds e;
+    const int last = c.last < 0 ? 0 : c.last;
+    e.lx = tab[last].tx; e.ly = tab[last].ty; e.lk = tab[last].kL;
+    e.fx = tab[0].tx; e.fy = tab[0].ty; e.fk = tab[0].kU;
+    return e;
+}
+struct LookupStats { int end, tri; };      // lookups answered by the end tests / by a certified triple
+
+MPPI_HD bool cert_in_box(const WinCert& c, float xl, float yl, float& b) {
+    b = fma_(c.nx, xl, mul_(c.ny, yl));
+    return fmaxf(fabsf(xl), fabsf(yl)) <= c.dom && b >= c.blo && b <= c.bhi;      // false for NaN
+}
+MPPI_HD int cert_guess(const WinCert& c, float xl, float yl, float b) {
+    const float s = fma_(c.sx, xl, fma_(c.sy, yl, c.s0));
+#if defined(__CUDA_ARCH__)
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(sub_(c.bc, b)));
+#else
+    const float inv = 1.0f / sub_(c.bc, b);
+#endif
+    const float w = mul_(s, inv);
+    const float est = fma_(w, fma_(w, c.c2, c.c1), c.c0);
+    const float cl = fminf(fmaxf(est, 1.0f), c.jhi);          // NaN -> 1
+    return f2i(add_(cl, 12582912.0f)) - 0x4B400000;            // round to nearest, exact for 0 <= cl < 2^22
+}
+// j0-1, j0, j0+1 compared exactly like the full search compares them
+MPPI_HD int cert_triple_pick(const RowRec* t, int j0, float xl, float yl) {
+    const float d0 = fma_(t[0].a, xl, fma_(t[0].b, yl, t[0].c));
+    const float d1 = fma_(t[1].a, xl, fma_(t[1].b, yl, t[1].c));
+    const float d2 = fma_(t[2].a, xl, fma_(t[2].b, yl, t[2].c));
+    int j = j0 - 1;
+    float d = d0;
+    if (d1 < d) { d = d1; j = j0; }
+    if (d2 < d) j = j0 + 1;
+    return j;
+}
+MPPI_HD bool cert_triple_ok(const RowRec* t, float xl, float yl) {
+    return fma_(t[0].tx, xl, fma_(t[0].ty, yl, t[0].kL)) >= 0.0f && fma_(t[2].tx, xl, fma_(t[2].ty, yl, t[2].kU)) <= 0.0f;
+}
+// Certified answer for one query, or -1 (tests; the rollouts vote per warp in nearest_wp)
+MPPI_HD int cert_pick(const WinCert& c, const RowRec* tab, float xl, float yl) {
+    float b;
+    if (!cert_in_box(c, xl, yl, b)) return -1;
+    const CertEnds e = cert_ends(c, tab);
+    if (fma_(e.lx, xl, fma_(e.ly, yl, e.lk)) >= 0.0f) return c.last;
+    if (fma_(e.fx, xl, fma_(e.fy, yl, e.fk)) <= 0.0f) return 0;
+    if (!(c.jhi >= 1.0f)) return -1;
+    const int j0 = cert_guess(c, xl, yl, b);
+    const RowRec* t = tab + (j0 - 1);
+    return cert_triple_ok(t, xl, yl) ? cert_triple_pick(t, j0, xl, yl) : -1;
 }
 
 // Where the 30 x (a, b, c) window coefficients live.  WinRegs: per-thread registers (any number of
@@ -516,29 +673,47 @@ MPPI_HD int nearest_candidate(const Win& win, float xl, float yl) {
     return (int)id[0];
 }
 
-template <class Win>
-MPPI_HD int nearest_wp(const Win& win, float xl, float yl) { return nearest_candidate(win, xl, yl); }
+// Window policy of the certified kernels: the table stays in memory (shared memory on the device), only
+// the two end tests live in registers.
+struct WinTable {
+    const RowRec* tab; CertEnds ends;
+    MPPI_HD void load(const WinCert& c, const RowRec* t) { tab = t; ends = cert_ends(c, t); }
+};
 
-// The lookup of the rollouts: the certified row when the whole warp is certified (one vote, no
-// divergence), else the full search.  `hits` counts the skipped searches (per warp on the device).
-template <class Win>
-MPPI_HD int nearest_wp(const Win& win, const EndCert& cert, float xl, float yl, int& hits) {
-    const CertTest t = cert_test(cert, xl, yl);
+// The lookup of the rollouts (control.py:200-215 via _c / _phi).  Every decision is taken per WARP (one
+// vote, no divergence): an end row when all lanes pass that end test; else the certified triples when all
+// lanes pass theirs; else the exact search.  All three return what the exact search returns.
 #if defined(__CUDA_ARCH__)
-    if (__all_sync(0xffffffffu, cert_ok(t))) { ++hits; return cert_row(cert, t); }
+#define MPPI_ALL_LANES(p) __all_sync(0xffffffffu, (p))
 #else
-    if (cert_ok(t)) { ++hits; return cert_row(cert, t); }
+#define MPPI_ALL_LANES(p) (p)
 #endif
+MPPI_HD int nearest_wp(const WinTable& win, const WinCert& c, float xl, float yl, LookupStats& st) {
+    float b;
+    const bool in = cert_in_box(c, xl, yl, b);
+    const CertEnds& e = win.ends;
+    if (MPPI_ALL_LANES(in && fma_(e.lx, xl, fma_(e.ly, yl, e.lk)) >= 0.0f)) { ++st.end; return c.last; }
+    if (MPPI_ALL_LANES(in && fma_(e.fx, xl, fma_(e.fy, yl, e.fk)) <= 0.0f)) { ++st.end; return 0; }
+    if (c.jhi >= 1.0f) {
+        const int j0 = cert_guess(c, xl, yl, b);
+        const RowRec* t = win.tab + (j0 - 1);
+        if (MPPI_ALL_LANES(in && cert_triple_ok(t, xl, yl))) { ++st.tri; return cert_triple_pick(t, j0, xl, yl); }
+    }
+    return nearest_scan(win.tab, xl, yl);
+}
+// the same for a window policy that holds the coefficients itself (kernels without the certificate)
+template <class Win>
+MPPI_HD int nearest_wp(const Win& win, const WinCert&, float xl, float yl, LookupStats&) {
     return nearest_candidate(win, xl, yl);
 }
 
 // NS samples advance in lockstep inside one thread: they share the window registers, the per-step
 // constants and the loop overhead, and give the scheduler NS independent instruction streams.
-// CERT = false compiles the lookups as plain searches (the kernel shape for MPPI_FLAG_FULL_SEARCH: no test, no vote)
-template <int NS, int DYN = 0, bool CERT = true, class Win, class Noise>
+// Win = WinTable: certified lookups; any other window policy: plain searches (MPPI_FLAG_FULL_SEARCH: no test, no vote)
+template <int NS, int DYN = 0, class Win, class Noise>
 MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
-                            const Win& win, const EndCert& cert, const RefRow* rows, const StepCtl* ctl,
-                            int T, const float (&um)[NS], Noise (&noise)[NS], float (&S_out)[NS], int& hits) {
+                            const Win& win, const WinCert& cert, const RefRow* rows, const StepCtl* ctl,
+                            int T, const float (&um)[NS], Noise (&noise)[NS], float (&S_out)[NS], LookupStats& hits) {
     ArmState st[NS];
     float S[NS], kS[NS], ex[NS], ey[NS], e1[NS], e2[NS];
 #if defined(__CUDA_ARCH__)
@@ -570,7 +745,7 @@ MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
 #endif
         for (int s = 0; s < NS; ++s) {
             fk_local(st[s], A, hd.ox, hd.oy, xl[s], yl[s]);
-            j[s] = CERT ? nearest_wp(win, cert, xl[s], yl[s], hits) : nearest_candidate(win, xl[s], yl[s]);
+            j[s] = nearest_wp(win, cert, xl[s], yl[s], hits);
         }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -597,8 +772,8 @@ MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
 
 template <int DYN = 0, class Win, class Noise>
 MPPI_HD float rollout_cost(const StepHeader& hd, const ArmF& A, const CostW& W,
-                           const Win& win, const EndCert& cert, const RefRow* rows, const StepCtl* ctl,
-                           int T, float um, Noise& noise, int& hits) {
+                           const Win& win, const WinCert& cert, const RefRow* rows, const StepCtl* ctl,
+                           int T, float um, Noise& noise, LookupStats& hits) {
     const float ums[1] = { um };
     float out[1];
     Noise (&nz)[1] = reinterpret_cast<Noise (&)[1]>(noise);

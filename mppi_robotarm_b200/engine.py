@@ -390,13 +390,17 @@ class MppiEngine:
         return out
 
     def search_stats(self, reset=True) -> dict:
-        """Nearest-waypoint lookups of the rollouts since the last reset, per warp of 32 samples:
-        how many the certified end-of-window shortcut answered, and how many there were
+        """Nearest-waypoint lookups of the rollouts since the last reset, per warp of 32 samples: how many a
+        certified end-of-window test answered (``certified``), how many a certified three-row comparison
+        (``triples``), and how many there were; the rest ran the 30-candidate search
         (engine built with search_stats=True)."""
-        buf = (C.c_uint64 * 2)()
-        _cabi.check(self.lib.mppi_search_stats(self.handle, buf, 1 if reset else 0), self.handle, "mppi_search_stats")
-        return {"certified": int(buf[0]), "lookups": int(buf[1]),
-                "fraction": (buf[0] / buf[1]) if buf[1] else 0.0}
+        buf = (C.c_uint64 * 3)()
+        _cabi.check(self.lib.mppi_search_stats(self.handle, buf, 1 if reset else 0, self.stream.cuda_stream),
+                    self.handle, "mppi_search_stats")
+        n = int(buf[1])
+        return {"certified": int(buf[0]), "triples": int(buf[2]), "lookups": n,
+                "fraction": (buf[0] / n) if n else 0.0, "triple_fraction": (buf[2] / n) if n else 0.0,
+                "searched_fraction": ((n - buf[0] - buf[2]) / n) if n else 0.0}
 
     def launch_count(self) -> int:
         return int(self.lib.mppi_launch_count(self.handle))

@@ -7,6 +7,24 @@
 #include <vector>
 using namespace mppi;
 
+// the tables the prepare kernel builds for the window starting at row p (serial form)
+struct Tables {
+    WinRegs regs; WinTable win; WinCert cert;
+    RefRow rows[kWindowPad]; WinEntry tab[kWindowPad]; RowRec rec[kWindowPad];
+};
+static void build_tables(const double* ref, int n_rows, int p, double reach, bool use_cert, Tables& tb) {
+    for (int j = 0; j < kWindowPad; ++j) make_window_row(ref, n_rows, p, j, tb.tab[j], tb.rows[j]);
+    tb.regs.load(tb.tab);
+    double lrows[kWindow][2];
+    int n_valid = 0;
+    for (int j = 0; j < kWindow && p + j < n_rows; ++j, ++n_valid) {
+        lrows[j][0] = ref[4 * (p + j)] - ref[4 * p]; lrows[j][1] = ref[4 * (p + j) + 1] - ref[4 * p + 1];
+    }
+    make_win_cert(lrows, n_valid, reach, ref[4 * p], ref[4 * p + 1], use_cert, tb.cert, tb.rec);
+    for (int j = 0; j < kWindowPad; ++j) { tb.rec[j].a = tb.tab[j].a; tb.rec[j].b = tb.tab[j].b; tb.rec[j].c = tb.tab[j].c; tb.rec[j].pad = 0.f; }
+    tb.win.load(tb.cert, tb.rec);
+}
+
 struct EpsArray {
     const float* e; int T;
     void operator()(int t, float& a, float& b) const { a = e[2 * t]; b = e[2 * t + 1]; }
@@ -31,17 +49,8 @@ int emul_rollout_costs(const double* ref, int n_rows, int prev_idx, const double
     StepHeader hd{};
     hd.q1 = (float)x0[0]; hd.q2 = (float)x0[1]; hd.d1 = (float)x0[2]; hd.d2 = (float)x0[3];
     hd.ox = (float)ref[4 * p]; hd.oy = (float)ref[4 * p + 1]; hd.win_start = p;
-    WinRegs win; RefRow rows[kWindowPad]; WinEntry tab[kWindowPad];
-    for (int j = 0; j < kWindowPad; ++j) make_window_row(ref, n_rows, p, j, tab[j], rows[j]);
-    win.load(tab);
-    // end-of-window certificate, as the prepare kernel builds it (serial form)
-    double lrows[kWindow][2];
-    int n_valid = 0;
-    for (int j = 0; j < kWindow && p + j < n_rows; ++j, ++n_valid) {
-        lrows[j][0] = ref[4 * (p + j)] - ref[4 * p]; lrows[j][1] = ref[4 * (p + j) + 1] - ref[4 * p + 1];
-    }
-    EndCert cert;
-    make_end_cert(lrows, n_valid, cl1 + cl2, ref[4 * p], ref[4 * p + 1], use_cert != 0, cert);
+    Tables tb; build_tables(ref, n_rows, p, cl1 + cl2, use_cert != 0, tb);
+    const RefRow* rows = tb.rows;
     long long hits_total = 0;
     std::vector<StepCtl> ctl(T);
     for (int t = 0; t < T; ++t) make_step_ctl(u_prev + 2 * t, gamma, sig_inv, ctl[t]);
@@ -55,51 +64,48 @@ int emul_rollout_costs(const double* ref, int n_rows, int prev_idx, const double
     // the device copy of ox/oy is FP32; fk_local subtracts exactly that value
     CostW W{ (float)(ws[0] * 1e4), (float)(ws[1] * 1e4), (float)(ws[2] * 1e4), (float)(ws[3] * 1e4),
              (float)(wt[0] * 1e4), (float)(wt[1] * 1e4), (float)(wt[2] * 1e4), (float)(wt[3] * 1e4) };
+    long long tri_total = 0;
     for (int k = 0; k < K; ++k) {
         EpsArray n{ eps + (size_t)k * T * 2, T };
-        int hits = 0;
+        LookupStats hits{0, 0};
         const float um = k < n_exploit ? 1.f : 0.f;
-        S_out[k] = dynamics_f1 ? rollout_cost<1>(hd, A, W, win, cert, rows, ctl.data(), T, um, n, hits)
-                               : rollout_cost<0>(hd, A, W, win, cert, rows, ctl.data(), T, um, n, hits);
-        hits_total += hits;
+        if (use_cert == 2)      // the kernels without the certificate: register tournament
+            S_out[k] = dynamics_f1 ? rollout_cost<1>(hd, A, W, tb.regs, tb.cert, rows, ctl.data(), T, um, n, hits)
+                                   : rollout_cost<0>(hd, A, W, tb.regs, tb.cert, rows, ctl.data(), T, um, n, hits);
+        else
+            S_out[k] = dynamics_f1 ? rollout_cost<1>(hd, A, W, tb.win, tb.cert, rows, ctl.data(), T, um, n, hits)
+                                   : rollout_cost<0>(hd, A, W, tb.win, tb.cert, rows, ctl.data(), T, um, n, hits);
+        hits_total += hits.end; tri_total += hits.tri;
     }
-    if (hits_out) *hits_out = hits_total;
+    if (hits_out) { hits_out[0] = hits_total; hits_out[1] = tri_total; }
     return p;
 }
 
-// Soundness probe of the end-of-window certificate: for n queries (x', y') in the local coordinates
-// of the window starting at row p, pick[i] = certified row or -1, full[i] = result of the FP32 search.
+// Soundness probe of the lookup certificate: for n queries (x', y') in the local coordinates of the window
+// starting at row p, pick[i] = certified row or -1, full[i] = result of the exact FP32 search (register
+// tournament), scan[i] = the in-memory form of the same search.  cert_out (optional): 64 certificate bytes
+// followed by 32 x 32 bytes of row records.
 void emul_cert_probe(const double* ref, int n_rows, int p, double reach, const float* xy, int n, int* pick, int* full,
-                     float* cert_out) {
-    WinRegs win; RefRow rows[kWindowPad]; WinEntry tab[kWindowPad];
-    for (int j = 0; j < kWindowPad; ++j) make_window_row(ref, n_rows, p, j, tab[j], rows[j]);
-    win.load(tab);
-    double lrows[kWindow][2];
-    int n_valid = 0;
-    for (int j = 0; j < kWindow && p + j < n_rows; ++j, ++n_valid) {
-        lrows[j][0] = ref[4 * (p + j)] - ref[4 * p]; lrows[j][1] = ref[4 * (p + j) + 1] - ref[4 * p + 1];
-    }
-    EndCert cert;
-    make_end_cert(lrows, n_valid, reach, ref[4 * p], ref[4 * p + 1], true, cert);
-    if (cert_out) memcpy(cert_out, &cert, sizeof(cert));
+                     int* scan, float* cert_out) {
+    Tables tb; build_tables(ref, n_rows, p, reach, true, tb);
+    if (cert_out) { memcpy(cert_out, &tb.cert, sizeof(tb.cert)); memcpy(cert_out + 16, tb.rec, sizeof(tb.rec)); }
     for (int i = 0; i < n; ++i) {
-        pick[i] = cert_pick(cert, xy[2 * i], xy[2 * i + 1]);
-        full[i] = nearest_candidate(win, xy[2 * i], xy[2 * i + 1]);
+        pick[i] = cert_pick(tb.cert, tb.rec, xy[2 * i], xy[2 * i + 1]);
+        full[i] = nearest_candidate(tb.regs, xy[2 * i], xy[2 * i + 1]);
+        if (scan) scan[i] = nearest_scan(tb.rec, xy[2 * i], xy[2 * i + 1]);
     }
 }
 
 // The same probe for a certificate that was built elsewhere (the prepare kernel on the GPU): cert_in =
-// the 64 certificate bytes of a step block.
+// the 64 certificate bytes + the 1024 bytes of row records of a step block.
 void emul_cert_probe_given(const double* ref, int n_rows, int p, const float* cert_in, const float* xy, int n,
                            int* pick, int* full) {
-    WinRegs win; RefRow rows[kWindowPad]; WinEntry tab[kWindowPad];
-    for (int j = 0; j < kWindowPad; ++j) make_window_row(ref, n_rows, p, j, tab[j], rows[j]);
-    win.load(tab);
-    EndCert cert;
-    memcpy(&cert, cert_in, sizeof(cert));
+    Tables tb; build_tables(ref, n_rows, p, 2.0, false, tb);
+    WinCert cert; RowRec rec[kWindowPad];
+    memcpy(&cert, cert_in, sizeof(cert)); memcpy(rec, cert_in + 16, sizeof(rec));
     for (int i = 0; i < n; ++i) {
-        pick[i] = cert_pick(cert, xy[2 * i], xy[2 * i + 1]);
-        full[i] = nearest_candidate(win, xy[2 * i], xy[2 * i + 1]);
+        pick[i] = cert_pick(cert, rec, xy[2 * i], xy[2 * i + 1]);
+        full[i] = nearest_candidate(tb.regs, xy[2 * i], xy[2 * i + 1]);
     }
 }
 

@@ -89,10 +89,10 @@ struct LoopParams {
 };
 
 struct StepBlockView {          // pointers into one environment's step block (global or shared)
-    StepHeader* hd; WinEntry* win; RefRow* rows; float4* pairs; WinCert* cert; RowRec* rec; StepCtl* ctl;
+    StepHeader* hd; WinEntry* win; RefRow* rows; float4* pairs; WinCert* cert; RowRec* rec; EndWedges* wed; StepCtl* ctl;
 };
-// header + win + rows + pairs + certificate + row records
-constexpr int kStepBlockFixed = 64 + 32 * kWindowPad + 16 * (kWindowPad / 2) + 64 + 32 * kWindowPad;
+// header + win + rows + pairs + certificate + row records + end wedges
+constexpr int kStepBlockFixed = 64 + 32 * kWindowPad + 16 * (kWindowPad / 2) + 64 + 32 * kWindowPad + 64;
 __host__ __device__ __forceinline__ StepBlockView view_step_block(void* base) {
     char* b = (char*)base;
     StepBlockView v;
@@ -102,6 +102,7 @@ __host__ __device__ __forceinline__ StepBlockView view_step_block(void* base) {
     v.pairs = (float4*)(b + 64 + 32 * kWindowPad);          // (a_2i, a_2i+1, b_2i, b_2i+1): operands of packed FFMA2
     v.cert = (WinCert*)(b + 64 + 32 * kWindowPad + 16 * (kWindowPad / 2));   // lookup certificate of the window
     v.rec = (RowRec*)(b + 64 + 32 * kWindowPad + 16 * (kWindowPad / 2) + 64);   // (a, b, c) + certificate of each row
+    v.wed = (EndWedges*)(b + 64 + 32 * kWindowPad + 16 * (kWindowPad / 2) + 64 + 32 * kWindowPad);   // far-field wedges of the end rows
     v.ctl = (StepCtl*)(b + kStepBlockFixed);
     return v;
 }
@@ -178,14 +179,80 @@ __device__ __forceinline__ double warp_max_d(double v) {
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+// make_wedge() of mppi_math.cuh for BOTH targets at once (w = 0: last row, w = 1: row 0; the two
+// dependency chains interleave), one lane per window row: (rx, ry) = this lane's local row, valid for
+// lane < n, n >= 2.  Every lane returns the same coefficients.
+__device__ __forceinline__ void warp_wedges(double rx, double ry, int lane, int n, double margin, double dom, EndWedges& c) {
+    const int target[2] = { n - 1, 0 };
+    double tx[2], ty[2], n0x[2], n0y[2], gx[2], gy[2], sl[2];
+    bool ok[2], mine[2];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        tx[w] = __shfl_sync(0xffffffffu, rx, target[w]); ty[w] = __shfl_sync(0xffffffffu, ry, target[w]);
+    }
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        n0x[w] = tx[w] - tx[1 - w]; n0y[w] = ty[w] - ty[1 - w];          // target minus the other end (not normalised:
+        mine[w] = lane < n && lane != target[w];                         //  the slopes below are ratios)
+        gx[w] = tx[w] - rx; gy[w] = ty[w] - ry;
+        const double along = gx[w] * n0x[w] + gy[w] * n0y[w], across = n0x[w] * gy[w] - n0y[w] * gx[w];
+        const bool bad = mine[w] && (!(along > 0.05 * fabs(across)) || !(along > 0.0));
+        ok[w] = !__any_sync(0xffffffffu, bad) && (n0x[w] * n0x[w] + n0y[w] * n0y[w] > 0.0);
+        sl[w] = mine[w] && along > 0.0 ? across * rcp64_(along) : 0.0;
+    }
+    double smin[2], smax[2];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) { smin[w] = mine[w] ? sl[w] : 1e300; smax[w] = mine[w] ? sl[w] : -1e300; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            smin[w] = fmin(smin[w], __shfl_xor_sync(0xffffffffu, smin[w], o));
+            smax[w] = fmax(smax[w], __shfl_xor_sync(0xffffffffu, smax[w], o));
+        }
+    }
+    double mx[2][2], my[2][2], bx[2], by[2], tau[2];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        smin[w] -= 2e-7 * (1.0 + smin[w] * smin[w]); smax[w] += 2e-7 * (1.0 + smax[w] * smax[w]);   // widen the cone
+        const double s2[2] = { smin[w], smax[w] };
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const double vx = n0x[w] - s2[i] * n0y[w], vy = n0y[w] + s2[i] * n0x[w];
+            const double inv = rsqrt64_(vx * vx + vy * vy);
+            mx[w][i] = vx * inv; my[w][i] = vy * inv;
+        }
+        bx[w] = mx[w][0] + mx[w][1]; by[w] = my[w][0] + my[w][1];       // bisector, not normalised: z = r_t + tau * b
+        const double bn2 = bx[w] * bx[w] + by[w] * by[w];
+        ok[w] = ok[w] && bn2 > 1e-6;
+        const double g2 = gx[w] * gx[w] + gy[w] * gy[w], ng = bx[w] * gx[w] + by[w] * gy[w];
+        ok[w] = ok[w] && !__any_sync(0xffffffffu, mine[w] && !(ng > 0.0));
+        tau[w] = mine[w] && ng > 0.0 ? fmax(0.5 * (margin - g2) * rcp64_(ng), 0.0) * 1.000001 : 0.0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int w = 0; w < 2; ++w) tau[w] = fmax(tau[w], __shfl_xor_sync(0xffffffffu, tau[w], o));
+    }
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        const double bn2 = bx[w] * bx[w] + by[w] * by[w];
+        ok[w] = ok[w] && (tau[w] * tau[w] * bn2 <= kCertMaxTau * kCertMaxTau);
+    }
+    if (ok[0]) wedge_finish(tx[0] + tau[0] * bx[0], ty[0] + tau[0] * by[0], mx[0], my[0], dom, c.lx, c.ly, c.lk);
+    if (ok[1]) wedge_finish(tx[1] + tau[1] * bx[1], ty[1] + tau[1] * by[1], mx[1], my[1], dom, c.fx, c.fy, c.fk);
+}
+
 // Lookup certificate of one window (make_win_cert of mppi_math.cuh), one lane per row: srow = the local rows
 // in shared memory (valid for j < n), lane `a` derives row a's tangent and the bounds its two roles put on
 // the lateral range; the range is their intersection over the warp.  Every lane returns the same certificate
 // and its own row record (tx, ty, kL, kU).
 __device__ __forceinline__ void warp_win_cert(const double (*srow)[2], int lane, int n, double reach, double ox,
-                                              double oy, bool enabled, WinCert& c, RowRec& rec) {
+                                              double oy, bool enabled, WinCert& c, RowRec& rec, EndWedges& wed) {
     cert_disable(c, n);
     cert_row_disable(rec);
+    wedge_disable(wed.lx, wed.ly, wed.lk); wedge_disable(wed.fx, wed.fy, wed.fk);
+    wed.pad[0] = wed.pad[1] = wed.pad[2] = wed.pad[3] = 0.f;
     if (!enabled || n < 1) return;
     const double dom = 1.01 * reach + fmax(fabs(ox), fabs(oy)) + 0.01, domw = 1.0001 * dom;
     c.dom = (float)dom;
@@ -205,18 +272,23 @@ __device__ __forceinline__ void warp_win_cert(const double (*srow)[2], int lane,
     const double cmax = warp_max_d(rx * rx + ry * ry);
     const double ab = 2.0000001 * cmax * rsqrt64_(fmax(cmax, 1e-300));       // |a_j|, |b_j| <= 2 sqrt(cmax)
     const double margin = cert_margin(ab, ab, cmax, domw);
-    const double wmin = kCertMinLateral * reach;
+    warp_wedges(rx, ry, lane, n, margin, domw, wed);
+    const double wmin = kCertMinLateral * reach, wt = kCertOffsetLateral * reach;
     const double bmax = (fabs(nux) + fabs(nuy)) * domw;
     double lo = -bmax, hi = bmax;
     if (valid) {
         auto row = [&](int j, double& x, double& y) { x = srow[j][0]; y = srow[j][1]; };
-        const RowGeom g = cert_row_geom(row, lane, n, nux, nuy, margin);
-        const double delta = cert_delta(g.tx, g.ty, g.k, domw);
+        const RowGeom g = cert_row_geom(row, lane, n, nux, nuy, margin, wt);
         rec.tx = (float)g.tx; rec.ty = (float)g.ty;
+        double push, rlo, rhi;
         if (lane == 0) rec.kL = kCertHuge;
-        else if (cert_role_usable(g.L, g.b, wmin)) { rec.kL = (float)(g.k - delta); lo = fmax(lo, g.L.lo); hi = fmin(hi, g.L.hi); }
+        else if (cert_role_form(g.L, g.b, wmin, wt, push, rlo, rhi)) {
+            rec.kL = (float)(g.k - push - cert_delta(g.tx, g.ty, g.k - push, domw)); lo = fmax(lo, rlo); hi = fmin(hi, rhi);
+        }
         if (lane == n - 1) rec.kU = -kCertHuge;
-        else if (cert_role_usable(g.U, g.b, wmin)) { rec.kU = (float)(g.k + delta); lo = fmax(lo, g.U.lo); hi = fmin(hi, g.U.hi); }
+        else if (cert_role_form(g.U, g.b, wmin, wt, push, rlo, rhi)) {
+            rec.kU = (float)(g.k + push + cert_delta(g.tx, g.ty, g.k + push, domw)); lo = fmax(lo, rlo); hi = fmin(hi, rhi);
+        }
     }
     // ---- index estimate: Kasa circle fit on centred chord coordinates, quadratic fit of the index on w ----
     const double sj = chx * rx + chy * ry, bj = nux * rx + nuy * ry;
@@ -373,11 +445,11 @@ __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, 
             const int nv = min(kWindow, n - p);
             if (lane < kWindow) { srow[lane][0] = row.x - ox; srow[lane][1] = row.y - oy; }
             __syncwarp();
-            WinCert c; RowRec rec;
-            warp_win_cert(srow, lane, nv, cfg.cost_l1 + cfg.cost_l2, ox, oy, !(cfg.flags & 16), c, rec);   // 16: MPPI_FLAG_FULL_SEARCH
+            WinCert c; RowRec rec; EndWedges wed;
+            warp_win_cert(srow, lane, nv, cfg.cost_l1 + cfg.cost_l2, ox, oy, !(cfg.flags & 16), c, rec, wed);   // 16: MPPI_FLAG_FULL_SEARCH
             rec.a = w.a; rec.b = w.b; rec.c = w.c; rec.pad = 0.f;
             sb.rec[lane] = rec;
-            if (lane == 0) *sb.cert = c;
+            if (lane == 0) { *sb.cert = c; *sb.wed = wed; }
         }
         // the same a/b coefficients once more, laid out as candidate pairs
         const float a1 = __shfl_down_sync(0xffffffffu, w.a, 1), b1 = __shfl_down_sync(0xffffffffu, w.b, 1);
@@ -482,7 +554,7 @@ struct WinConst {
 template <bool CONSTWIN, bool CERT> struct WinPolicy { typedef WinRegs type; };
 template <> struct WinPolicy<true, false> { typedef WinConst type; };
 template <bool CONSTWIN> struct WinPolicy<CONSTWIN, true> { typedef WinTable type; };
-__device__ __forceinline__ void win_load(WinTable& w, const StepBlockView& sb) { w.load(*sb.cert, sb.rec); }
+__device__ __forceinline__ void win_load(WinTable& w, const StepBlockView& sb) { w.load(*sb.cert, sb.rec, sb.wed); }
 __device__ __forceinline__ void win_load(WinRegs& w, const StepBlockView& sb) { w.load(sb.win); }
 __device__ __forceinline__ void win_load(WinConst& w, const StepBlockView& sb) { w.load(sb.win); }
 

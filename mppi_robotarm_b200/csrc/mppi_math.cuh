@@ -382,14 +382,19 @@ MPPI_HD void cert_disable(WinCert& c, int n_valid) {
 }
 MPPI_HD void cert_row_disable(RowRec& r) { r.tx = 0.f; r.ty = 0.f; r.kL = -kCertHuge; r.kU = kCertHuge; }
 
-// What one row contributes (FP64): its tangent, offset, and the bounds its two roles put on [blo, bhi].
-struct RowRole { double lo, hi; bool ok; };
+// What one row contributes (FP64): its tangent and offset, and for each of its two roles (a) the bounds the role
+// puts on [blo, bhi] when its threshold sits at the row itself, (b) how far the threshold has to be pushed
+// away from the row ("ahead by f" / "behind by f") for the role to hold on b_a +- kCertOffsetLateral * reach —
+// the fallback where the rows are closer together than the FP32 margin (a path that starts from rest).
+struct RowRole { double lo, hi, fneed; bool ok; };
 struct RowGeom { double tx, ty, k, b; RowRole L, U; };
+constexpr double kCertOffsetLateral = 0.25;            // lateral half-width of a pushed role, in units of the reach
+constexpr double kCertMaxOffset = 0.25;                // give up when the threshold would be > 25 cm from the row
 
-// Row a of `n` local rows (rx[], ry[] via the accessor) against every other row.  nu = window normal
-// (already rounded to FP32 and widened back).  `row(j, x, y)` fetches row j.
+// Row a of `n` local rows against every other row.  nu = window normal (already rounded to FP32 and widened
+// back); `row(j, x, y)` fetches row j; wt = lateral half-width of the pushed form.
 template <class RowFn>
-MPPI_HD RowGeom cert_row_geom(RowFn row, int a, int n, double nux, double nuy, double margin) {
+MPPI_HD RowGeom cert_row_geom(RowFn row, int a, int n, double nux, double nuy, double margin, double wt) {
     RowGeom g;
     double ax, ay, px, py, qx, qy;
     row(a, ax, ay);
@@ -398,7 +403,7 @@ MPPI_HD RowGeom cert_row_geom(RowFn row, int a, int n, double nux, double nuy, d
     double tx = qx - px, ty = qy - py;
     const double tn2 = tx * tx + ty * ty;
     g.L.ok = g.U.ok = tn2 > 0.0;
-    g.L.lo = g.U.lo = -1e300; g.L.hi = g.U.hi = 1e300;
+    g.L.lo = g.U.lo = -1e300; g.L.hi = g.U.hi = 1e300; g.L.fneed = g.U.fneed = 0.0;
     const double itn = tn2 > 0.0 ? rsqrt64_(tn2) : 0.0;
     tx *= itn; ty *= itn;
     tx = (double)(float)tx; ty = (double)(float)ty;          // the direction the FP32 test will use
@@ -415,18 +420,27 @@ MPPI_HD RowGeom cert_row_geom(RowFn row, int a, int n, double nux, double nuy, d
         row(j, jx, jy);
         const double gx = ax - jx, gy = ay - jy;
         RowRole& r = j < a ? g.L : g.U;
-        const double along = gx * dx + gy * dy;
-        if (j < a ? !(along > 0.0) : !(along < 0.0)) { r.ok = false; continue; }
+        const double along = j < a ? gx * dx + gy * dy : -(gx * dx + gy * dy);   // gain per unit of push
+        if (!(along > 0.0)) { r.ok = false; continue; }
         const double f0 = gx * gx + gy * gy + 2.0 * (gx * (v0x - ax) + gy * (v0y - ay));
         const double sl = 2.0 * (gx * v1x + gy * v1y);
         if (sl > 0.0) { const double bnd = (margin - f0) * rcp64_(sl); r.lo = bnd > r.lo ? bnd : r.lo; }
         else if (sl < 0.0) { const double bnd = (margin - f0) * rcp64_(sl); r.hi = bnd < r.hi ? bnd : r.hi; }
-        else if (!(f0 >= margin)) r.ok = false;
+        else if (!(f0 >= margin)) r.lo = 1e300;
+        const double need = (margin - (f0 + sl * g.b - fabs(sl) * wt)) * 0.5 * rcp64_(along);
+        r.fneed = need > r.fneed ? need : r.fneed;
     }
     return g;
 }
-MPPI_HD bool cert_role_usable(const RowRole& r, double b, double wmin) {
-    return r.ok && r.lo <= b - wmin && r.hi >= b + wmin;
+// Decide the form of one role: threshold at the row (push = 0, the role's own lateral bounds), pushed by
+// `push` (bounds b +- wt), or off.  Returns false when the role is off.
+MPPI_HD bool cert_role_form(const RowRole& r, double b, double wmin, double wt, double& push, double& lo, double& hi) {
+    push = 0.0; lo = r.lo; hi = r.hi;
+    if (!r.ok) return false;
+    if (r.lo <= b - wmin && r.hi >= b + wmin) return true;
+    if (!(r.fneed <= kCertMaxOffset)) return false;
+    push = r.fneed * (1.0 + 1e-9) + 1e-12; lo = b - wt; hi = b + wt;
+    return true;
 }
 
 // [blo, bhi] as the FP32 test will see it: moved inwards by the rounding of b = fma(nx, x, ny * y), of the
@@ -481,13 +495,95 @@ MPPI_HD void cert_fit_estimate(const double* s, const double* b, int n, WinCert&
     c.jhi = fin ? (float)(n - 2) : 0.f;
 }
 
+// ---- far-field complement of the two end tests -----------------------------------------------------
+// A sample that has flown far off the path (an arm falling from rest) is still nearest to an end row, but it
+// may lie outside the lateral box.  For those the prepare kernel also derives, for the last valid row L (and
+// for row 0), two half-planes  m_i.p' + k_i >= 0  whose intersection (a wedge) lies inside the Voronoi cell
+// of the row: with g_j = r_L - r_j,  d_j - d_L = |g_j|^2 + 2 g_j.(p - r_L).  All g_j lie in the cone spanned
+// by the two extreme directions m_0, m_1; for p = z + s with s.m_0 >= 0 and s.m_1 >= 0 every s.g_j >= 0,
+// hence d_j - d_L >= |g_j|^2 + 2 tau n.g_j at the apex z = r_L + tau n, and tau is chosen so that this is
+// >= the rounding margin for every j.  Tried after the certified triples, read from the staged table.
+struct alignas(16) EndWedges {  // 64 bytes of a step block
+    float lx[2], ly[2], lk[2]; // wedge inside the cell of the last valid row
+    float fx[2], fy[2], fk[2]; // wedge inside the cell of row 0
+    float pad[4];
+};
+static_assert(sizeof(EndWedges) == 64, "wedge block is 64 bytes");
+MPPI_HD void wedge_disable(float (&mx)[2], float (&my)[2], float (&k)[2]) {
+    mx[0] = mx[1] = 0.f; my[0] = my[1] = 0.f; k[0] = k[1] = -kCertHuge;
+}
+constexpr double kCertMaxTau = 0.25;                   // give up when the apex would be > 25 cm past the row
+MPPI_HD void wedge_finish(double zx, double zy, const double (&mx)[2], const double (&my)[2], double dom,
+                          float (&ox)[2], float (&oy)[2], float (&ok)[2]) {
+    for (int i = 0; i < 2; ++i) {
+        const double k = -(mx[i] * zx + my[i] * zy);
+        ox[i] = (float)mx[i]; oy[i] = (float)my[i]; ok[i] = (float)(k - cert_delta(mx[i], my[i], k, dom));
+    }
+}
+// One wedge, serial form (host tests and the reference for the warp-parallel version in the prepare kernel):
+// rows[j] = (x, y) of window row j in local coordinates (FP64), n rows valid, `target` = 0 or n-1.
+MPPI_HD void make_wedge(const double (*rows)[2], int n, int target, double margin, double dom,
+                        float (&ox)[2], float (&oy)[2], float (&ok)[2]) {
+    wedge_disable(ox, oy, ok);
+    if (n < 2) return;
+    const int other = target == 0 ? n - 1 : 0;
+    double n0x = rows[target][0] - rows[other][0], n0y = rows[target][1] - rows[other][1];
+    const double n0 = sqrt(n0x * n0x + n0y * n0y);
+    if (!(n0 > 0.0)) return;
+    n0x /= n0; n0y /= n0;
+    double smin = 1e300, smax = -1e300;
+    for (int j = 0; j < n; ++j) {
+        if (j == target) continue;
+        const double gx = rows[target][0] - rows[j][0], gy = rows[target][1] - rows[j][1];
+        const double along = gx * n0x + gy * n0y, across = n0x * gy - n0y * gx;
+        if (!(along > 0.05 * fabs(across)) || !(along > 0.0)) return;   // direction spread too wide (or duplicate rows)
+        const double sl = across / along;
+        smin = sl < smin ? sl : smin; smax = sl > smax ? sl : smax;
+    }
+    smin -= 1e-7 * (1.0 + smin * smin); smax += 1e-7 * (1.0 + smax * smax);     // widen the cone by ~1e-7 rad
+    double mx[2], my[2];
+    const double s2[2] = { smin, smax };
+    for (int i = 0; i < 2; ++i) {
+        const double vx = n0x - s2[i] * n0y, vy = n0y + s2[i] * n0x, vn = sqrt(vx * vx + vy * vy);
+        mx[i] = vx / vn; my[i] = vy / vn;
+    }
+    double bx = mx[0] + mx[1], by = my[0] + my[1];
+    const double bn = sqrt(bx * bx + by * by);
+    if (!(bn > 1e-3)) return;
+    bx /= bn; by /= bn;
+    double tau = 0.0;
+    for (int j = 0; j < n; ++j) {
+        if (j == target) continue;
+        const double gx = rows[target][0] - rows[j][0], gy = rows[target][1] - rows[j][1];
+        const double g2 = gx * gx + gy * gy, ng = bx * gx + by * gy;
+        if (!(ng > 0.0)) return;
+        const double t = (margin - g2) / (2.0 * ng);
+        tau = t > tau ? t : tau;
+    }
+    if (!(tau <= kCertMaxTau)) return;
+    wedge_finish(rows[target][0] + tau * bx, rows[target][1] + tau * by, mx, my, dom, ox, oy, ok);
+}
+MPPI_HD void make_end_wedges(const double (*rows)[2], int n_valid, double margin, double domw, bool enabled, EndWedges& w) {
+    wedge_disable(w.lx, w.ly, w.lk); wedge_disable(w.fx, w.fy, w.fk);
+    w.pad[0] = w.pad[1] = w.pad[2] = w.pad[3] = 0.f;
+    if (!enabled || n_valid < 2) return;
+    make_wedge(rows, n_valid, n_valid - 1, margin, domw, w.lx, w.ly, w.lk);
+    make_wedge(rows, n_valid, 0, margin, domw, w.fx, w.fy, w.fk);
+}
+// wl >= 0: inside the wedge of the last row; wf >= 0: inside the wedge of row 0 (both need |x'|, |y'| <= dom)
+MPPI_HD void wedge_test(const EndWedges& c, float xl, float yl, float& wl, float& wf) {
+    wl = fminf(fma_(c.lx[0], xl, fma_(c.ly[0], yl, c.lk[0])), fma_(c.lx[1], xl, fma_(c.ly[1], yl, c.lk[1])));
+    wf = fminf(fma_(c.fx[0], xl, fma_(c.fy[0], yl, c.fk[0])), fma_(c.fx[1], xl, fma_(c.fy[1], yl, c.fk[1])));
+}
+
 // The certificate of one window, serial form (host tests; the prepare kernel runs the same steps with one
 // lane per row).  rows: the n_valid local rows (FP64); reach = L1 + L2 of the cost-side kinematics;
 // (ox, oy) = window origin; tab[j].{tx, ty, kL, kU} are filled for all kWindowPad rows.
 MPPI_HD void make_win_cert(const double (*rows)[2], int n_valid, double reach, double ox, double oy,
-                           bool enabled, WinCert& c, RowRec* tab) {
+                           bool enabled, WinCert& c, RowRec* tab, EndWedges& wed) {
     cert_disable(c, n_valid);
     for (int j = 0; j < kWindowPad; ++j) cert_row_disable(tab[j]);
+    make_end_wedges(rows, 0, 0.0, 0.0, false, wed);
     if (!enabled || n_valid < 1) return;
     const double aox = fabs(ox), aoy = fabs(oy);
     const double dom = 1.01 * reach + (aox > aoy ? aox : aoy) + 0.01, domw = 1.0001 * dom;
@@ -508,23 +604,26 @@ MPPI_HD void make_win_cert(const double (*rows)[2], int n_valid, double reach, d
     }
     const double ab = 2.0000001 * sqrt(cmax);               // |a_j|, |b_j| <= 2 sqrt(cmax)
     const double margin = cert_margin(ab, ab, cmax, domw);
-    const double wmin = kCertMinLateral * reach;
+    make_end_wedges(rows, n_valid, margin, domw, true, wed);
+    const double wmin = kCertMinLateral * reach, wt = kCertOffsetLateral * reach;
     auto row = [&](int j, double& x, double& y) { x = rows[j][0]; y = rows[j][1]; };
     const double bmax = (fabs(nux) + fabs(nuy)) * domw;
     double blo = -bmax, bhi = bmax;
     double sj[kWindow], bj[kWindow];
     for (int a = 0; a < n_valid; ++a) {
-        const RowGeom g = cert_row_geom(row, a, n_valid, nux, nuy, margin);
-        const double delta = cert_delta(g.tx, g.ty, g.k, domw);
+        const RowGeom g = cert_row_geom(row, a, n_valid, nux, nuy, margin, wt);
         RowRec& r = tab[a];
         r.tx = (float)g.tx; r.ty = (float)g.ty;
+        double push, lo, hi;
         if (a == 0) r.kL = kCertHuge;                        // no rows below row 0
-        else if (cert_role_usable(g.L, g.b, wmin)) {
-            r.kL = (float)(g.k - delta); blo = g.L.lo > blo ? g.L.lo : blo; bhi = g.L.hi < bhi ? g.L.hi : bhi;
+        else if (cert_role_form(g.L, g.b, wmin, wt, push, lo, hi)) {
+            r.kL = (float)(g.k - push - cert_delta(g.tx, g.ty, g.k - push, domw));
+            blo = lo > blo ? lo : blo; bhi = hi < bhi ? hi : bhi;
         }
         if (a == n_valid - 1) r.kU = -kCertHuge;             // no rows above the last one
-        else if (cert_role_usable(g.U, g.b, wmin)) {
-            r.kU = (float)(g.k + delta); blo = g.U.lo > blo ? g.U.lo : blo; bhi = g.U.hi < bhi ? g.U.hi : bhi;
+        else if (cert_role_form(g.U, g.b, wmin, wt, push, lo, hi)) {
+            r.kU = (float)(g.k + push + cert_delta(g.tx, g.ty, g.k + push, domw));
+            blo = lo > blo ? lo : blo; bhi = hi < bhi ? hi : bhi;
         }
         sj[a] = chx * rows[a][0] + chy * rows[a][1]; bj[a] = g.b;
     }
@@ -542,29 +641,44 @@ MPPI_HD int nearest_scan(const RowRec* tab, float xl, float yl) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    for (int j = 1; j < kWindow; ++j) {
-        const float d = fma_(tab[j].a, xl, fma_(tab[j].b, yl, tab[j].c));
-        if (d < bd) { bd = d; best = j; }
+    for (int j0 = 1; j0 < kWindow; j0 += 5) {          // 29 = 5 x 5 + 4 candidates: blocks of five loads in flight
+        float d[5];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int i = 0; i < 5; ++i) {
+            const RowRec& r = tab[j0 + i < kWindowPad ? j0 + i : kWindowPad - 1];
+            d[i] = fma_(r.a, xl, fma_(r.b, yl, r.c));
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int i = 0; i < 5; ++i)
+            if (j0 + i < kWindow && d[i] < bd) { bd = d[i]; best = j0 + i; }
     }
     return best;
 }
 
-struct CertEnds {              // the two end tests, kept in registers by the rollouts
+struct CertEnds {              // what every lookup needs, kept in registers by the rollouts:
     float lx, ly, lk;          // L(last)
     float fx, fy, fk;          // U(0)
+    float nx, ny, blo, bhi, dom;   // the box the certificate was proven on
+    int last;
 };
 MPPI_HD CertEnds cert_ends(const WinCert& c, const RowRec* tab) {
     CertEnds e;
     const int last = c.last < 0 ? 0 : c.last;
     e.lx = tab[last].tx; e.ly = tab[last].ty; e.lk = tab[last].kL;
     e.fx = tab[0].tx; e.fy = tab[0].ty; e.fk = tab[0].kU;
+    e.nx = c.nx; e.ny = c.ny; e.blo = c.blo; e.bhi = c.bhi; e.dom = c.dom; e.last = c.last;
     return e;
 }
 struct LookupStats { int end, tri; };      // lookups answered by the end tests / by a certified triple
 
-MPPI_HD bool cert_in_box(const WinCert& c, float xl, float yl, float& b) {
+// (bitwise & on purpose: every operand is evaluated, the compiler chains predicates instead of branching)
+MPPI_HD bool cert_in_box(const CertEnds& c, float xl, float yl, float& b) {
     b = fma_(c.nx, xl, mul_(c.ny, yl));
-    return fmaxf(fabsf(xl), fabsf(yl)) <= c.dom && b >= c.blo && b <= c.bhi;      // false for NaN
+    return (fmaxf(fabsf(xl), fabsf(yl)) <= c.dom) & (b >= c.blo) & (b <= c.bhi);      // false for NaN
 }
 MPPI_HD int cert_guess(const WinCert& c, float xl, float yl, float b) {
     const float s = fma_(c.sx, xl, fma_(c.sy, yl, c.s0));
@@ -591,19 +705,25 @@ MPPI_HD int cert_triple_pick(const RowRec* t, int j0, float xl, float yl) {
     return j;
 }
 MPPI_HD bool cert_triple_ok(const RowRec* t, float xl, float yl) {
-    return fma_(t[0].tx, xl, fma_(t[0].ty, yl, t[0].kL)) >= 0.0f && fma_(t[2].tx, xl, fma_(t[2].ty, yl, t[2].kU)) <= 0.0f;
+    return (fma_(t[0].tx, xl, fma_(t[0].ty, yl, t[0].kL)) >= 0.0f) & (fma_(t[2].tx, xl, fma_(t[2].ty, yl, t[2].kU)) <= 0.0f);
 }
 // Certified answer for one query, or -1 (tests; the rollouts vote per warp in nearest_wp)
-MPPI_HD int cert_pick(const WinCert& c, const RowRec* tab, float xl, float yl) {
+MPPI_HD int cert_pick(const WinCert& c, const RowRec* tab, const EndWedges& wed, float xl, float yl) {
     float b;
-    if (!cert_in_box(c, xl, yl, b)) return -1;
     const CertEnds e = cert_ends(c, tab);
-    if (fma_(e.lx, xl, fma_(e.ly, yl, e.lk)) >= 0.0f) return c.last;
-    if (fma_(e.fx, xl, fma_(e.fy, yl, e.fk)) <= 0.0f) return 0;
-    if (!(c.jhi >= 1.0f)) return -1;
-    const int j0 = cert_guess(c, xl, yl, b);
-    const RowRec* t = tab + (j0 - 1);
-    return cert_triple_ok(t, xl, yl) ? cert_triple_pick(t, j0, xl, yl) : -1;
+    if (cert_in_box(e, xl, yl, b)) {
+        if (fma_(e.lx, xl, fma_(e.ly, yl, e.lk)) >= 0.0f) return c.last;
+        if (fma_(e.fx, xl, fma_(e.fy, yl, e.fk)) <= 0.0f) return 0;
+        if (c.jhi >= 1.0f) {
+            const int j0 = cert_guess(c, xl, yl, b);
+            const RowRec* t = tab + (j0 - 1);
+            if (cert_triple_ok(t, xl, yl)) return cert_triple_pick(t, j0, xl, yl);
+        }
+    }
+    float wl, wf;
+    wedge_test(wed, xl, yl, wl, wf);
+    if (!(fmaxf(fabsf(xl), fabsf(yl)) <= e.dom)) return -1;
+    return wl >= 0.0f ? c.last : (wf >= 0.0f ? 0 : -1);
 }
 
 // Where the 30 x (a, b, c) window coefficients live.  WinRegs: per-thread registers (any number of
@@ -676,8 +796,8 @@ MPPI_HD int nearest_candidate(const Win& win, float xl, float yl) {
 // Window policy of the certified kernels: the table stays in memory (shared memory on the device), only
 // the two end tests live in registers.
 struct WinTable {
-    const RowRec* tab; CertEnds ends;
-    MPPI_HD void load(const WinCert& c, const RowRec* t) { tab = t; ends = cert_ends(c, t); }
+    const RowRec* tab; const EndWedges* wed; CertEnds ends;
+    MPPI_HD void load(const WinCert& c, const RowRec* t, const EndWedges* w) { tab = t; wed = w; ends = cert_ends(c, t); }
 };
 
 // The lookup of the rollouts (control.py:200-215 via _c / _phi).  Every decision is taken per WARP (one
@@ -690,15 +810,21 @@ struct WinTable {
 #endif
 MPPI_HD int nearest_wp(const WinTable& win, const WinCert& c, float xl, float yl, LookupStats& st) {
     float b;
-    const bool in = cert_in_box(c, xl, yl, b);
     const CertEnds& e = win.ends;
-    if (MPPI_ALL_LANES(in && fma_(e.lx, xl, fma_(e.ly, yl, e.lk)) >= 0.0f)) { ++st.end; return c.last; }
-    if (MPPI_ALL_LANES(in && fma_(e.fx, xl, fma_(e.fy, yl, e.fk)) <= 0.0f)) { ++st.end; return 0; }
+    const bool in = cert_in_box(e, xl, yl, b);
+    if (MPPI_ALL_LANES(in & (fma_(e.lx, xl, fma_(e.ly, yl, e.lk)) >= 0.0f))) { ++st.end; return e.last; }
+    if (MPPI_ALL_LANES(in & (fma_(e.fx, xl, fma_(e.fy, yl, e.fk)) <= 0.0f))) { ++st.end; return 0; }
     if (c.jhi >= 1.0f) {
         const int j0 = cert_guess(c, xl, yl, b);
         const RowRec* t = win.tab + (j0 - 1);
-        if (MPPI_ALL_LANES(in && cert_triple_ok(t, xl, yl))) { ++st.tri; return cert_triple_pick(t, j0, xl, yl); }
+        if (MPPI_ALL_LANES(in & cert_triple_ok(t, xl, yl))) { ++st.tri; return cert_triple_pick(t, j0, xl, yl); }
     }
+    // far field: the wedges of the two end rows (samples that left the lateral box)
+    float wl, wf;
+    wedge_test(*win.wed, xl, yl, wl, wf);
+    const bool dom_ok = fmaxf(fabsf(xl), fabsf(yl)) <= e.dom;
+    if (MPPI_ALL_LANES(dom_ok & (wl >= 0.0f))) { ++st.end; return e.last; }
+    if (MPPI_ALL_LANES(dom_ok & (wf >= 0.0f))) { ++st.end; return 0; }
     return nearest_scan(win.tab, xl, yl);
 }
 // the same for a window policy that holds the coefficients itself (kernels without the certificate)

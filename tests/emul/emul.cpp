@@ -9,7 +9,7 @@ using namespace mppi;
 
 // the tables the prepare kernel builds for the window starting at row p (serial form)
 struct Tables {
-    WinRegs regs; WinTable win; WinCert cert;
+    WinRegs regs; WinTable win; WinCert cert; EndWedges wed;
     RefRow rows[kWindowPad]; WinEntry tab[kWindowPad]; RowRec rec[kWindowPad];
 };
 static void build_tables(const double* ref, int n_rows, int p, double reach, bool use_cert, Tables& tb) {
@@ -20,9 +20,9 @@ static void build_tables(const double* ref, int n_rows, int p, double reach, boo
     for (int j = 0; j < kWindow && p + j < n_rows; ++j, ++n_valid) {
         lrows[j][0] = ref[4 * (p + j)] - ref[4 * p]; lrows[j][1] = ref[4 * (p + j) + 1] - ref[4 * p + 1];
     }
-    make_win_cert(lrows, n_valid, reach, ref[4 * p], ref[4 * p + 1], use_cert, tb.cert, tb.rec);
+    make_win_cert(lrows, n_valid, reach, ref[4 * p], ref[4 * p + 1], use_cert, tb.cert, tb.rec, tb.wed);
     for (int j = 0; j < kWindowPad; ++j) { tb.rec[j].a = tb.tab[j].a; tb.rec[j].b = tb.tab[j].b; tb.rec[j].c = tb.tab[j].c; tb.rec[j].pad = 0.f; }
-    tb.win.load(tb.cert, tb.rec);
+    tb.win.load(tb.cert, tb.rec, &tb.wed);
 }
 
 struct EpsArray {
@@ -83,28 +83,28 @@ int emul_rollout_costs(const double* ref, int n_rows, int prev_idx, const double
 
 // Soundness probe of the lookup certificate: for n queries (x', y') in the local coordinates of the window
 // starting at row p, pick[i] = certified row or -1, full[i] = result of the exact FP32 search (register
-// tournament), scan[i] = the in-memory form of the same search.  cert_out (optional): 64 certificate bytes
-// followed by 32 x 32 bytes of row records.
+// tournament), scan[i] = the in-memory form of the same search.  cert_out (optional): 64 certificate bytes,
+// 32 x 32 bytes of row records, 64 bytes of end wedges (the layout of a step block).
 void emul_cert_probe(const double* ref, int n_rows, int p, double reach, const float* xy, int n, int* pick, int* full,
                      int* scan, float* cert_out) {
     Tables tb; build_tables(ref, n_rows, p, reach, true, tb);
-    if (cert_out) { memcpy(cert_out, &tb.cert, sizeof(tb.cert)); memcpy(cert_out + 16, tb.rec, sizeof(tb.rec)); }
+    if (cert_out) { memcpy(cert_out, &tb.cert, sizeof(tb.cert)); memcpy(cert_out + 16, tb.rec, sizeof(tb.rec)); memcpy(cert_out + 16 + 256, &tb.wed, sizeof(tb.wed)); }
     for (int i = 0; i < n; ++i) {
-        pick[i] = cert_pick(tb.cert, tb.rec, xy[2 * i], xy[2 * i + 1]);
+        pick[i] = cert_pick(tb.cert, tb.rec, tb.wed, xy[2 * i], xy[2 * i + 1]);
         full[i] = nearest_candidate(tb.regs, xy[2 * i], xy[2 * i + 1]);
         if (scan) scan[i] = nearest_scan(tb.rec, xy[2 * i], xy[2 * i + 1]);
     }
 }
 
 // The same probe for a certificate that was built elsewhere (the prepare kernel on the GPU): cert_in =
-// the 64 certificate bytes + the 1024 bytes of row records of a step block.
+// the 64 certificate bytes + the 1024 bytes of row records + the 64 bytes of end wedges of a step block.
 void emul_cert_probe_given(const double* ref, int n_rows, int p, const float* cert_in, const float* xy, int n,
                            int* pick, int* full) {
     Tables tb; build_tables(ref, n_rows, p, 2.0, false, tb);
-    WinCert cert; RowRec rec[kWindowPad];
-    memcpy(&cert, cert_in, sizeof(cert)); memcpy(rec, cert_in + 16, sizeof(rec));
+    WinCert cert; RowRec rec[kWindowPad]; EndWedges wed;
+    memcpy(&cert, cert_in, sizeof(cert)); memcpy(rec, cert_in + 16, sizeof(rec)); memcpy(&wed, cert_in + 16 + 256, sizeof(wed));
     for (int i = 0; i < n; ++i) {
-        pick[i] = cert_pick(cert, rec, xy[2 * i], xy[2 * i + 1]);
+        pick[i] = cert_pick(cert, rec, wed, xy[2 * i], xy[2 * i + 1]);
         full[i] = nearest_candidate(tb.regs, xy[2 * i], xy[2 * i + 1]);
     }
 }

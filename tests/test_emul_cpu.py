@@ -110,7 +110,7 @@ def test_host_noise_moments(emul):
 # ---------------------------------------------------------------------------------------------
 # certified nearest-waypoint lookups (mppi_math.cuh: WinCert / RowRec)
 # ---------------------------------------------------------------------------------------------
-CERT_FLOATS = 16 + 32 * 8      # 64 certificate bytes + 32 row records of 32 bytes
+CERT_FLOATS = 16 + 32 * 8 + 16      # 64 certificate bytes + 32 row records of 32 bytes + 64 bytes of end wedges
 
 
 def _probe(emul, ref, p, xy):
@@ -129,10 +129,22 @@ def cert_boundary_queries(cert, rng, N):
     to 1 mm off it) at lateral positions spread over, and right at, the certified lateral range."""
     c = cert.astype(np.float64)
     nx, ny, blo, bhi = c[0:4]
-    rec = c[16:].reshape(32, 8)
+    rec = c[16:16 + 256].reshape(32, 8)
     out = []
+    for o in (272, 278):                         # apex and edges of the two far-field wedges
+        mx, my, k = (c[o + 2 * i:o + 2 * i + 2] for i in range(3))
+        A = np.array([[mx[0], my[0]], [mx[1], my[1]]])
+        if np.any(np.abs(k) > 1e30) or abs(np.linalg.det(A)) < 1e-9:
+            continue
+        z = np.linalg.solve(A, -k)
+        M = 4 * N
+        t = (10.0 ** rng.uniform(-7, 0.5, M) * rng.choice([-1, 1], M))[:, None]
+        which = rng.integers(0, 3, M)[:, None]
+        out.append(z[None, :] + rng.standard_normal((M, 2)) * (10.0 ** rng.uniform(-9, -5, M))[:, None]
+                   + np.where(which == 0, t * np.array([-my[0], mx[0]]), 0.0)
+                   + np.where(which == 1, t * np.array([-my[1], mx[1]]), 0.0))
     if not (blo < bhi):
-        return np.zeros((0, 2))
+        return np.concatenate(out) if out else np.zeros((0, 2))
     for a in range(32):
         tx, ty = rec[a, 4:6]
         for k in rec[a, 6:8]:

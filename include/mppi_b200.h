@@ -80,6 +80,12 @@ typedef struct MppiConfig {
     double arm[7];              /* m1, m2, l1, l2, lc1, lc2, g  (sys_params.py:4-10)             */
     double cost_l1, cost_l2;    /* self.l1, self.l2 of the cost-side kinematics (control.py:55-56)*/
     uint64_t seed;              /* Philox key                                                    */
+    /* Joint-limit stage cost (BASELINE north_star item 1).  NOT in the reference, whose only limits are the
+     * commented-out clamps of _g (control.py:166-172): every horizon step adds
+     * joint_limit_weight * 1e4 * (viol(q1)^2 + viol(q2)^2), viol(q) = max(q - hi, lo - q, 0).
+     * joint_limit_weight = 0 (default) gives the reference's step, and launches kernels without the term. */
+    double joint_limit_lo[2], joint_limit_hi[2];
+    double joint_limit_weight;
 } MppiConfig;
 
 #define MPPI_MAX_T 256

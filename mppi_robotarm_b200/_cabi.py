@@ -36,6 +36,7 @@ class MppiConfig(C.Structure):
         ("stage_cost_weight", C.c_double * 4), ("terminal_cost_weight", C.c_double * 4),
         ("arm", C.c_double * 7), ("cost_l1", C.c_double), ("cost_l2", C.c_double),
         ("seed", C.c_uint64),
+        ("joint_limit_lo", C.c_double * 2), ("joint_limit_hi", C.c_double * 2), ("joint_limit_weight", C.c_double),
     ]
 
 

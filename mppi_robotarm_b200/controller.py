@@ -55,6 +55,9 @@ class MPPIControllerForPathTracking:
             dynamics: str = "F",        # rollout model: "F" (control.py:234-263) or "F1" (control.py:265-295)
             search: str = "certified",  # nearest-waypoint lookups: "certified" shortcut or always "full" (same results)
             search_stats: bool = False,  # count how many lookups the shortcut answered (engine.search_stats())
+            joint_limit_lo=None,        # joint-limit stage cost (not in the reference: its clamps are commented out,
+            joint_limit_hi=None,        #  control.py:166-172): (q1, q2) bounds in rad, None = unbounded
+            joint_limit_weight: float = 0.0,   # weight of 1e4 * (violation of q1)^2 + (violation of q2)^2 per horizon step; 0 = off
     ) -> None:
         # same attributes as control.py:37-65
         self.dim_x = 4
@@ -92,6 +95,8 @@ class MPPIControllerForPathTracking:
         self.dynamics = dynamics
         self._search = search
         self._search_stats = search_stats
+        self.joint_limit_lo, self.joint_limit_hi = joint_limit_lo, joint_limit_hi
+        self.joint_limit_weight = joint_limit_weight
         self._engine_obj = None
         self._engine_ref_path = None
         self.last = {}               # intermediates of the last step (rho, eta, raw / filtered update)
@@ -114,7 +119,8 @@ class MPPIControllerForPathTracking:
                 optimal_traj=bool(self.visualize_optimal_traj), use_graph=self._use_graph,
                 smoother=self.smoother, shard=self._shard(), process_group=self._group,
                 exchange=self._exchange, search=self._search, search_stats=self._search_stats,
-                dynamics=self.dynamics)
+                dynamics=self.dynamics, joint_limit_lo=self.joint_limit_lo, joint_limit_hi=self.joint_limit_hi,
+                joint_limit_weight=self.joint_limit_weight)
             self._engine_ref_path = self.ref_path
         elif self.ref_path is not self._engine_ref_path:
             # the reference reads self.ref_path on every call (control.py:208); follow a re-assignment

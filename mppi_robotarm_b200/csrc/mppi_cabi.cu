@@ -96,14 +96,21 @@ bool valid_cfg(const MppiConfig* c, const char** why) {
     }
     if (c->max_ref_rows < 2) { *why = "max_ref_rows < 2"; return false; }
     if (!(c->param_lambda > 0.0)) { *why = "param_lambda must be > 0"; return false; }
+    if (!(c->joint_limit_weight >= 0.0)) { *why = "joint_limit_weight must be >= 0"; return false; }
+    if (c->joint_limit_weight > 0.0) {
+        if (!(c->joint_limit_lo[0] <= c->joint_limit_hi[0]) || !(c->joint_limit_lo[1] <= c->joint_limit_hi[1])) {
+            *why = "joint limits need lo <= hi"; return false;
+        }
+        if (c->flags & MPPI_FLAG_DYNAMICS_F1) { *why = "the joint-limit cost is built for the rollout model _F only"; return false; }
+    }
     return true;
 }
 
 // samples per thread of the rollout kernel: 2 when there is enough work to fill the GPU that way
 bool certified_kernels(const MppiConfig* c) {
     // certified lookups (window table in shared memory) unless the caller asked for plain searches; the _F1
-    // model exists in the certified shape only (with MPPI_FLAG_FULL_SEARCH its certificate is never armed)
-    return !(c->flags & MPPI_FLAG_FULL_SEARCH) || (c->flags & MPPI_FLAG_DYNAMICS_F1);
+    // model and the joint-limit cost exist in the certified shape only (with MPPI_FLAG_FULL_SEARCH the certificate is never armed)
+    return !(c->flags & MPPI_FLAG_FULL_SEARCH) || (c->flags & MPPI_FLAG_DYNAMICS_F1) || c->joint_limit_weight > 0.0;
 }
 bool pick_const_window(const MppiConfig* c) {
     // constant-bank window of the plain-search kernels: single environment and enough work to pay for the copy node
@@ -205,6 +212,12 @@ void fill_dev_cfg(MppiHandle* h) {
     d.cost.s2 = (float)(c.stage_cost_weight[2] * 1e4); d.cost.s3 = (float)(c.stage_cost_weight[3] * 1e4);
     d.cost.t0 = (float)(c.terminal_cost_weight[0] * 1e4); d.cost.t1 = (float)(c.terminal_cost_weight[1] * 1e4);
     d.cost.t2 = (float)(c.terminal_cost_weight[2] * 1e4); d.cost.t3 = (float)(c.terminal_cost_weight[3] * 1e4);
+    {   // joint limits: +-inf would turn into NaN in (q - hi)^2 * 0; clamp the bounds to a huge finite value
+        auto lim = [](double v) { return (float)(v > 1e30 ? 1e30 : (v < -1e30 ? -1e30 : v)); };
+        d.cost.jw = (float)(c.joint_limit_weight * 1e4);
+        d.cost.lo1 = lim(c.joint_limit_lo[0]); d.cost.hi1 = lim(c.joint_limit_hi[0]);
+        d.cost.lo2 = lim(c.joint_limit_lo[1]); d.cost.hi2 = lim(c.joint_limit_hi[1]);
+    }
     d.noise.key = philox_expand_key((uint32_t)(c.seed & 0xffffffffu), (uint32_t)(c.seed >> 32));
     d.noise.step = 0;
     d.noise.L11 = (float)c.sigma_chol[0]; d.noise.L21 = (float)c.sigma_chol[2]; d.noise.L22 = (float)c.sigma_chol[3];
@@ -297,11 +310,12 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
         // plain searches x window policy }.  MPPI_FLAG_FULL_SEARCH selects the kernels compiled without the
         // certificate; the _F1 model exists in the certified shape only (prepare then never arms the certificate).
         const bool ns2 = h->ns == 2, f1 = (dc.flags & MPPI_FLAG_DYNAMICS_F1) != 0;
-        const bool cert = certified_kernels(&h->cfg);
+        const bool cert = certified_kernels(&h->cfg), jl = h->cfg.joint_limit_weight > 0.0;
         unsigned long long* stats = (unsigned long long*)(ws + h->ws.off_stats);
         const float* eps_arg = ph ? nullptr : eps_dev;
-#define MPPI_ROLL(NOISE, CW, NS_, DYN, CERT) \
-        mppi_rollout_sm100a<NOISE, CW, NS_, DYN, CERT><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, eps_arg, S, bmin, stats)
+#define MPPI_ROLL(NOISE, CW, NS_, DYN, CERT) do { \
+        if (CERT && DYN == 0 && jl) mppi_rollout_sm100a<NOISE, false, NS_, 0, true, true><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, eps_arg, S, bmin, stats); \
+        else mppi_rollout_sm100a<NOISE, CW, NS_, DYN, CERT><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, eps_arg, S, bmin, stats); } while (0)
 #define MPPI_ROLL_NS(NOISE, CW, DYN, CERT) do { if (ns2) MPPI_ROLL(NOISE, CW, 2, DYN, CERT); else MPPI_ROLL(NOISE, CW, 1, DYN, CERT); } while (0)
 #define MPPI_ROLL_NOISE(CW, DYN, CERT) do { if (ph) MPPI_ROLL_NS(0, CW, DYN, CERT); else MPPI_ROLL_NS(1, CW, DYN, CERT); } while (0)
         if (f1) MPPI_ROLL_NOISE(false, 1, true);

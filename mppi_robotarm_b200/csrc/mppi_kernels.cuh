@@ -546,7 +546,7 @@ struct WinConst {
 #endif
 
 #ifndef MPPI_ROLL_MIN_BLOCKS_CERT
-#define MPPI_ROLL_MIN_BLOCKS_CERT 4
+#define MPPI_ROLL_MIN_BLOCKS_CERT 5      // <= 102 registers: 20 warps per SM (A/B on B200: profiles/r2_variants.md)
 #endif
 
 // Window policy per kernel family.  CERT: certified lookups, the table stays in shared memory (any number of
@@ -558,7 +558,7 @@ __device__ __forceinline__ void win_load(WinTable& w, const StepBlockView& sb) {
 __device__ __forceinline__ void win_load(WinRegs& w, const StepBlockView& sb) { w.load(sb.win); }
 __device__ __forceinline__ void win_load(WinConst& w, const StepBlockView& sb) { w.load(sb.win); }
 
-template <int NOISE, bool CONSTWIN, int kNS, int DYN = 0, bool CERT = true>
+template <int NOISE, bool CONSTWIN, int kNS, int DYN = 0, bool CERT = true, bool JL = false>
 __global__ void __launch_bounds__(kRollThreads, CERT ? MPPI_ROLL_MIN_BLOCKS_CERT
                                                      : (CONSTWIN ? MPPI_ROLL_MIN_BLOCKS_CONST : (kNS == 1 ? 3 : 2)))
 mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const char* __restrict__ step_blocks,
@@ -598,6 +598,7 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
             // a padding sample past the end recomputes the last one (its result is not stored)
             kl[s] = min(kl0 + s * kRollThreads, cfg.K_local - 1);
             um[s] = (cfg.k_offset + kl[s]) < cfg.n_exploit ? 1.0f : 0.0f;
+            asm volatile("" : "+f"(um[s]));            // keep it in a register: not re-derived in every horizon step
         }
         if (NOISE == 0) {
             PhiloxNoise nz[kNS];
@@ -606,12 +607,12 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
                 nz[s].nc = cfg.noise; nz[s].nc.step = (uint32_t)(*step_ctr); nz[s].env = (uint32_t)e;
                 nz[s].k = (uint32_t)(cfg.k_offset + kl[s]);
             }
-            rollout_cost_n<kNS, DYN>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
+            rollout_cost_n<kNS, DYN, JL>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
         } else {
             InjectedNoise nz[kNS];
 #pragma unroll
             for (int s = 0; s < kNS; ++s) nz[s].row = (const float2*)eps + ((size_t)e * cfg.K_local + kl[s]) * T;
-            rollout_cost_n<kNS, DYN>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
+            rollout_cost_n<kNS, DYN, JL>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
         }
 #pragma unroll
         for (int s = 0; s < kNS; ++s) {
@@ -624,7 +625,7 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
     tmin = warp_min(tmin);
     if ((tid & 31) == 0) red[tid >> 5] = tmin;
     if ((cfg.flags & 64) && (tid & 31) == 0) {              // MPPI_FLAG_SEARCH_STATS: warp-lookups certified / done
-        atomicAdd(search_stats, (unsigned long long)hits.end);
+        atomicAdd(search_stats, (unsigned long long)(lookups - hits.tri - hits.scan));
         atomicAdd(search_stats + 1, (unsigned long long)lookups);
         atomicAdd(search_stats + 2, (unsigned long long)hits.tri);
     }

@@ -27,14 +27,20 @@ constexpr int kWindow = 30;       // SEARCH_IDX_LEN, control.py:203
 constexpr int kWindowPad = 32;    // table rows (two never-selected sentinels)
 constexpr int kFilter = 10;       // control.py:122
 constexpr float kSentinel = 3.0e38f;
+#ifndef MPPI_UNROLL_T
+#define MPPI_UNROLL_T 2
+#endif
+constexpr int kUnrollT = MPPI_UNROLL_T;     // unroll factor of the horizon loop of the rollouts
 
 // Which accumulators of a rollout carry a Kahan compensation term: bit 0 joint rates, bit 1 joint angles,
-// bit 2 the cost sum S.  Default: all.  (CPU study, DESIGN.md section 8: bit 2 buys nothing measurable.)
+// bit 2 the cost sum S.  Default: rates and angles.  (Study kept as tests/test_emul_cpu.py::
+// test_cost_sum_compensation_is_not_what_holds_the_tolerance: compensating S changes neither the update nor S
+// beyond 1e-7 max S; the angle term is the one that holds the 1e-4 bound, the rate term second.)
 #ifndef MPPI_KAHAN_MASK
 #ifdef MPPI_NO_KAHAN
 #define MPPI_KAHAN_MASK 0
 #else
-#define MPPI_KAHAN_MASK 7
+#define MPPI_KAHAN_MASK 3
 #endif
 #endif
 
@@ -82,9 +88,10 @@ MPPI_HD double rsqrt64_(double x) { return 1.0 / sqrt(x); }
 #endif
 
 // ---- sin & cos of one angle, ~1 ulp, no slow path --------------------------------------------
-// Cody-Waite reduction by pi/2 in three FMA steps, then degree-7 / degree-8 minimax polynomials on
-// [-pi/4, pi/4].  Valid for |x| < ~1e5 rad; a diverged rollout (larger angle, Inf, NaN) yields a
-// garbage-but-finite or NaN cost that the soft-min kernel maps to weight 0.
+// Cody-Waite reduction by pi/2 in two FMA steps (the third term of pi/2, 5.4e-15 per quadrant, is below
+// 1e-11 for |x| < 3000 rad: a thousandth of an ulp of the result), then degree-7 / degree-8 minimax
+// polynomials on [-pi/4, pi/4].  A diverged rollout (huge angle, Inf, NaN) yields a garbage-but-finite or
+// NaN cost that the soft-min kernel maps to weight 0.
 MPPI_HD void sincos_(float x, float& s, float& c) {
     const float kMagic = 12582912.0f;                      // 1.5 * 2^23: round-to-nearest trick
     float kf = fma_(x, 0.636619772367581343f, kMagic);
@@ -92,7 +99,9 @@ MPPI_HD void sincos_(float x, float& s, float& c) {
     kf = sub_(kf, kMagic);
     float r = fma_(kf, -1.57079601287841796875f, x);
     r = fma_(kf, -3.1391647326017846e-07f, r);
+#ifdef MPPI_CW3
     r = fma_(kf, -5.3903025299577648e-15f, r);
+#endif
     float r2 = mul_(r, r);
     // sin(r) = r + r*r2*(S1 + r2*(S2 + r2*S3))
     float ps = fma_(r2, -1.9515295891e-4f, 8.3321608736e-3f);
@@ -121,7 +130,15 @@ struct ArmF {
 struct CostW {           // weights already multiplied by 1e4 (control.py:185, 198)
     float s0, s1, s2, s3;
     float t0, t1, t2, t3;
+    // joint-limit stage cost (north_star item 1; not in the reference — its only limits are the commented-out
+    // clamps of _g, control.py:166-172): jw * (viol(q1)^2 + viol(q2)^2), viol(q) = max(q - hi, lo - q, 0)
+    float jw, lo1, hi1, lo2, hi2;
 };
+MPPI_HD float joint_limit_cost(const CostW& W, float q1, float q2) {
+    const float v1 = fmaxf(fmaxf(sub_(q1, W.hi1), sub_(W.lo1, q1)), 0.0f);
+    const float v2 = fmaxf(fmaxf(sub_(q2, W.hi2), sub_(W.lo2, q2)), 0.0f);
+    return mul_(W.jw, fma_(v1, v1, mul_(v2, v2)));
+}
 
 struct WinEntry { float a, b, c, pad; };     // d_j - |p'|^2 = c + a*x' + b*y'   (local coordinates)
 struct RefRow { float rx, ry, rd1, rd2; };   // waypoint in local coordinates + reference joint rates
@@ -274,16 +291,21 @@ MPPI_HD float u01_(uint32_t x) {          // (0, 1]
 }
 
 // Box-Muller: two uniforms -> two independent N(0,1)
+MPPI_HD float u02pi_(uint32_t x) {       // 2 pi * (0, 1], one FMA
+    return fma_((float)x, 1.4629180792671596e-09f, 7.3145903963357980e-10f);
+}
 MPPI_HD void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
-    float u = u01_(a), v = u01_(b);
+    float u = u01_(a);
 #if defined(__CUDA_ARCH__)
     float r;                                                          // sqrt(-2 ln u), MUFU.SQRT (no slow path)
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(mul_(-1.3862943611198906f, __log2f(u))));
+    float lg;                                                         // u >= 2^-33: never denormal, so .ftz changes nothing
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(mul_(-1.3862943611198906f, lg)));
     float sn, cs;
-    __sincosf(mul_(6.2831853071795865f, v), &sn, &cs);
+    __sincosf(u02pi_(b), &sn, &cs);
 #else
     float r = sqrtf(mul_(-1.3862943611198906f, log2f(u)));
-    float th = mul_(6.2831853071795865f, v);
+    float th = u02pi_(b);
     float sn = sinf(th), cs = cosf(th);
 #endif
     z0 = mul_(r, cs); z1 = mul_(r, sn);
@@ -673,7 +695,8 @@ MPPI_HD CertEnds cert_ends(const WinCert& c, const RowRec* tab) {
     e.nx = c.nx; e.ny = c.ny; e.blo = c.blo; e.bhi = c.bhi; e.dom = c.dom; e.last = c.last;
     return e;
 }
-struct LookupStats { int end, tri; };      // lookups answered by the end tests / by a certified triple
+struct LookupStats { int tri, scan; };     // lookups answered by a certified triple / by the exact search (the rest: end tests)
+struct LookupMode { bool far; };           // per sample slot, warp-uniform: the last lookup was answered by a far-field wedge
 
 // (bitwise & on purpose: every operand is evaluated, the compiler chains predicates instead of branching)
 MPPI_HD bool cert_in_box(const CertEnds& c, float xl, float yl, float& b) {
@@ -808,12 +831,20 @@ struct WinTable {
 #else
 #define MPPI_ALL_LANES(p) (p)
 #endif
-MPPI_HD int nearest_wp(const WinTable& win, const WinCert& c, float xl, float yl, LookupStats& st) {
-    float b;
+MPPI_HD int nearest_wp(const WinTable& win, const WinCert& c, float xl, float yl, LookupStats& st, LookupMode& md) {
     const CertEnds& e = win.ends;
+    if (md.far) {                              // a sample that left the lateral box usually stays out: wedges first
+        float wl, wf;
+        wedge_test(*win.wed, xl, yl, wl, wf);
+        const bool dom_ok = fmaxf(fabsf(xl), fabsf(yl)) <= e.dom;
+        if (MPPI_ALL_LANES(dom_ok & (wl >= 0.0f))) return e.last;
+        if (MPPI_ALL_LANES(dom_ok & (wf >= 0.0f))) return 0;
+        md.far = false;
+    }
+    float b;
     const bool in = cert_in_box(e, xl, yl, b);
-    if (MPPI_ALL_LANES(in & (fma_(e.lx, xl, fma_(e.ly, yl, e.lk)) >= 0.0f))) { ++st.end; return e.last; }
-    if (MPPI_ALL_LANES(in & (fma_(e.fx, xl, fma_(e.fy, yl, e.fk)) <= 0.0f))) { ++st.end; return 0; }
+    if (MPPI_ALL_LANES(in & (fma_(e.lx, xl, fma_(e.ly, yl, e.lk)) >= 0.0f))) return e.last;
+    if (MPPI_ALL_LANES(in & (fma_(e.fx, xl, fma_(e.fy, yl, e.fk)) <= 0.0f))) return 0;
     if (c.jhi >= 1.0f) {
         const int j0 = cert_guess(c, xl, yl, b);
         const RowRec* t = win.tab + (j0 - 1);
@@ -823,24 +854,28 @@ MPPI_HD int nearest_wp(const WinTable& win, const WinCert& c, float xl, float yl
     float wl, wf;
     wedge_test(*win.wed, xl, yl, wl, wf);
     const bool dom_ok = fmaxf(fabsf(xl), fabsf(yl)) <= e.dom;
-    if (MPPI_ALL_LANES(dom_ok & (wl >= 0.0f))) { ++st.end; return e.last; }
-    if (MPPI_ALL_LANES(dom_ok & (wf >= 0.0f))) { ++st.end; return 0; }
+    if (MPPI_ALL_LANES(dom_ok & (wl >= 0.0f))) { md.far = true; return e.last; }
+    if (MPPI_ALL_LANES(dom_ok & (wf >= 0.0f))) { md.far = true; return 0; }
+    ++st.scan;
     return nearest_scan(win.tab, xl, yl);
 }
 // the same for a window policy that holds the coefficients itself (kernels without the certificate)
 template <class Win>
-MPPI_HD int nearest_wp(const Win& win, const WinCert&, float xl, float yl, LookupStats&) {
+MPPI_HD int nearest_wp(const Win& win, const WinCert&, float xl, float yl, LookupStats& st, LookupMode&) {
+    ++st.scan;
     return nearest_candidate(win, xl, yl);
 }
 
 // NS samples advance in lockstep inside one thread: they share the window registers, the per-step
 // constants and the loop overhead, and give the scheduler NS independent instruction streams.
 // Win = WinTable: certified lookups; any other window policy: plain searches (MPPI_FLAG_FULL_SEARCH: no test, no vote)
-template <int NS, int DYN = 0, class Win, class Noise>
+// JL: the stage cost carries the joint-limit term (a template flag: the default kernels do not contain it)
+template <int NS, int DYN = 0, bool JL = false, class Win, class Noise>
 MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
                             const Win& win, const WinCert& cert, const RefRow* rows, const StepCtl* ctl,
                             int T, const float (&um)[NS], Noise (&noise)[NS], float (&S_out)[NS], LookupStats& hits) {
     ArmState st[NS];
+    LookupMode md[NS];
     float S[NS], kS[NS], ex[NS], ey[NS], e1[NS], e2[NS];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -848,7 +883,11 @@ MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
     for (int s = 0; s < NS; ++s) {
         arm_init(st[s], hd.q1, hd.q2, hd.d1, hd.d2);
         S[s] = 0.f; kS[s] = 0.f; ex[s] = 0.f; ey[s] = 0.f; e1[s] = 0.f; e2[s] = 0.f;
+        md[s].far = false;
     }
+#if defined(__CUDA_ARCH__)
+#pragma unroll kUnrollT
+#endif
     for (int t = 0; t < T; ++t) {
         const StepCtl c = ctl[t];
         float v1[NS], v2[NS], xl[NS], yl[NS];
@@ -871,7 +910,7 @@ MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
 #endif
         for (int s = 0; s < NS; ++s) {
             fk_local(st[s], A, hd.ox, hd.oy, xl[s], yl[s]);
-            j[s] = nearest_wp(win, cert, xl[s], yl[s], hits);
+            j[s] = nearest_wp(win, cert, xl[s], yl[s], hits, md[s]);
         }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -881,6 +920,7 @@ MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
             residuals(st[s], xl[s], yl[s], r, ex[s], ey[s], e1[s], e2[s]);
             float cst = wsq(W.s0, W.s1, W.s2, W.s3, ex[s], ey[s], e1[s], e2[s]);
             cst = fma_(c.g1, v1[s], fma_(c.g2, v2[s], cst));   // + gamma * u^T Sigma^-1 v  (control.py:106)
+            if (JL) cst = add_(cst, joint_limit_cost(W, st[s].q1, st[s].q2));
 #if (MPPI_KAHAN_MASK & 4)
             kahan_(S[s], kS[s], sub_(cst, kS[s]));
 #else
@@ -896,14 +936,14 @@ MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
         S_out[s] = add_(S[s], sub_(wsq(W.t0, W.t1, W.t2, W.t3, ex[s], ey[s], e1[s], e2[s]), kS[s]));
 }
 
-template <int DYN = 0, class Win, class Noise>
+template <int DYN = 0, bool JL = false, class Win, class Noise>
 MPPI_HD float rollout_cost(const StepHeader& hd, const ArmF& A, const CostW& W,
                            const Win& win, const WinCert& cert, const RefRow* rows, const StepCtl* ctl,
                            int T, float um, Noise& noise, LookupStats& hits) {
     const float ums[1] = { um };
     float out[1];
     Noise (&nz)[1] = reinterpret_cast<Noise (&)[1]>(noise);
-    rollout_cost_n<1, DYN>(hd, A, W, win, cert, rows, ctl, T, ums, nz, out, hits);
+    rollout_cost_n<1, DYN, JL>(hd, A, W, win, cert, rows, ctl, T, ums, nz, out, hits);
     return out[0];
 }
 

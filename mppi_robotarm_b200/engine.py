@@ -48,7 +48,8 @@ class MppiEngine:
                  terminal_cost_weight, arm_params, ref_path, param_exploration=0.0, cost_l1=1.0, cost_l2=1.0,
                  n_env=1, seed=0, device=None, optimal_traj=True, use_graph=True, smoother="median",
                  shard: ShardSpec | None = None, process_group=None, max_ref_rows=None, exchange="nccl",
-                 search="certified", search_stats=False, dynamics="F"):
+                 search="certified", search_stats=False, dynamics="F", joint_limit_lo=None, joint_limit_hi=None,
+                 joint_limit_weight=0.0):
         import torch
         self.torch = torch
         self.lib = _cabi.load()
@@ -98,6 +99,14 @@ class MppiEngine:
         cfg.arm[:] = arm_vector(arm_params)
         cfg.cost_l1, cfg.cost_l2 = float(cost_l1), float(cost_l2)
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        # joint-limit stage cost (extension; weight 0 = the reference's step, and kernels without the term)
+        lo = (-np.inf, -np.inf) if joint_limit_lo is None else tuple(float(v) for v in joint_limit_lo)
+        hi = (np.inf, np.inf) if joint_limit_hi is None else tuple(float(v) for v in joint_limit_hi)
+        if len(lo) != 2 or len(hi) != 2:
+            raise ValueError("joint_limit_lo / joint_limit_hi need one value per joint (q1, q2)")
+        cfg.joint_limit_lo[:] = lo
+        cfg.joint_limit_hi[:] = hi
+        cfg.joint_limit_weight = float(joint_limit_weight)
         self.cfg = cfg
 
         lay = _cabi.MppiIoLayout()

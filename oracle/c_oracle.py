@@ -15,7 +15,8 @@ class OracleCfg(C.Structure):
     _fields_ = [("dt", C.c_double), ("lam", C.c_double), ("gamma", C.c_double), ("sig_inv", C.c_double * 4),
                 ("ws", C.c_double * 4), ("wt", C.c_double * 4),
                 ("m1", C.c_double), ("m2", C.c_double), ("l1", C.c_double), ("l2", C.c_double),
-                ("lc1", C.c_double), ("lc2", C.c_double), ("g", C.c_double), ("cl1", C.c_double), ("cl2", C.c_double)]
+                ("lc1", C.c_double), ("lc2", C.c_double), ("g", C.c_double), ("cl1", C.c_double), ("cl2", C.c_double),
+                ("jl_lo", C.c_double * 2), ("jl_hi", C.c_double * 2), ("jl_w", C.c_double)]
 
 
 def build(force=False):
@@ -45,6 +46,9 @@ def make_cfg(c) -> OracleCfg:
     for k in ("m1", "m2", "l1", "l2", "lc1", "lc2", "g"):
         setattr(o, k, float(c.arm[k]))
     o.cl1, o.cl2 = float(c.cost_l1), float(c.cost_l2)
+    o.jl_lo[:] = [float(v) for v in getattr(c, "joint_limit_lo", (-np.inf, -np.inf))]
+    o.jl_hi[:] = [float(v) for v in getattr(c, "joint_limit_hi", (np.inf, np.inf))]
+    o.jl_w = float(getattr(c, "joint_limit_weight", 0.0))
     return o
 
 
@@ -77,3 +81,10 @@ def weighted_sum(S, eps, lam):
 
 def num_threads() -> int:
     return int(lib().oracle_num_threads())
+
+
+def set_num_threads(n: int) -> int:
+    """OpenMP team size of the next calls (bench.py sets it from the affinity mask: torchrun exports
+    OMP_NUM_THREADS=1 to its workers)."""
+    lib().oracle_set_num_threads(int(n))
+    return num_threads()

@@ -24,6 +24,7 @@ typedef struct {
     double ws[4], wt[4];
     double m1, m2, l1, l2, lc1, lc2, g;
     double cl1, cl2;
+    double jl_lo[2], jl_hi[2], jl_w;   /* joint-limit stage cost (extension, weight 0 = the reference) */
 } oracle_cfg;
 
 static void arm_step(const oracle_cfg* c, double* q1, double* q2, double* d1, double* d2, double v1, double v2) {
@@ -60,6 +61,13 @@ static double track_cost(const oracle_cfg* c, const double* win, int n_win, cons
     return cost * 10000;
 }
 
+static double joint_limit_cost(const oracle_cfg* c, double q1, double q2) {
+    if (c->jl_w == 0.0) return 0.0;
+    double v1 = fmax(fmax(q1 - c->jl_hi[0], c->jl_lo[0] - q1), 0.0);
+    double v2 = fmax(fmax(q2 - c->jl_hi[1], c->jl_lo[1] - q2), 0.0);
+    return c->jl_w * (v1 * v1 + v2 * v2) * 10000;
+}
+
 /* S[k] for k in [0, K): eps is [K][T][2] (double), u is [T][2], window = ref rows [p, p+n_win) */
 void oracle_rollout_costs(const oracle_cfg* c, const double* win, int n_win, const double* x0,
                           const double* u, const double* eps, int K, int T, int n_exploit, double* S) {
@@ -73,7 +81,8 @@ void oracle_rollout_costs(const oracle_cfg* c, const double* win, int n_win, con
             arm_step(c, &q1, &q2, &d1, &d2, v1, v2);
             double ui0 = u[2 * t] * c->sig_inv[0] + u[2 * t + 1] * c->sig_inv[2];
             double ui1 = u[2 * t] * c->sig_inv[1] + u[2 * t + 1] * c->sig_inv[3];
-            s += track_cost(c, win, n_win, c->ws, q1, q2, d1, d2) + c->gamma * (ui0 * v1 + ui1 * v2);
+            s += track_cost(c, win, n_win, c->ws, q1, q2, d1, d2) + c->gamma * (ui0 * v1 + ui1 * v2)
+               + joint_limit_cost(c, q1, q2);
         }
         s += track_cost(c, win, n_win, c->wt, q1, q2, d1, d2);
         S[k] = s;
@@ -93,6 +102,14 @@ double oracle_weighted_sum(const double* S, const double* eps, int K, int T, dou
         for (int i = 0; i < 2 * T; ++i) w_eps[i] += w[k] * e[i];
     }
     return rho;
+}
+
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
 }
 
 int oracle_num_threads(void) {

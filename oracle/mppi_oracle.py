@@ -62,6 +62,11 @@ class OracleMPPI:
     arm: dict = field(default_factory=default_arm_params)
     cost_l1: float = 1.0      # control.py:55
     cost_l2: float = 1.0      # control.py:56
+    # joint-limit stage cost (BASELINE.json north_star item 1; NOT in the reference, whose only limits are the
+    # commented-out clamps of _g, control.py:166-172): weight 0 = the reference's step, bit for bit
+    joint_limit_lo: tuple = (-np.inf, -np.inf)
+    joint_limit_hi: tuple = (np.inf, np.inf)
+    joint_limit_weight: float = 0.0
 
     def __post_init__(self):
         self.T = int(self.horizon_step_T)
@@ -155,6 +160,20 @@ def tracking_cost(q1, q2, d1, d2, win, weights, l1, l2):
     c = (weights[0] * (x - r[..., 0]) ** 2 + weights[1] * (y - r[..., 1]) ** 2
          + weights[2] * (d1 - r[..., 2]) ** 2 + weights[3] * (d2 - r[..., 3]) ** 2)
     return c * COST_SCALE
+
+
+def joint_limit_cost(q1, q2, lo, hi, weight):
+    """Extension (north_star item 1), zero by default: weight * (viol(q1)^2 + viol(q2)^2) * 1e4 with
+    viol(q) = max(q - hi, lo - q, 0), added to the stage cost of every horizon step."""
+    v1 = np.maximum(np.maximum(q1 - hi[0], lo[0] - q1), 0.0)
+    v2 = np.maximum(np.maximum(q2 - hi[1], lo[1] - q2), 0.0)
+    return weight * (v1 * v1 + v2 * v2) * COST_SCALE
+
+
+def _stage_extra(c, s):
+    if c.joint_limit_weight == 0.0:
+        return 0.0
+    return joint_limit_cost(s[0], s[1], c.joint_limit_lo, c.joint_limit_hi, c.joint_limit_weight)
 
 
 def softmin_weights(S, lam):
@@ -302,7 +321,7 @@ def step_loops(c: OracleMPPI, observed_x, eps) -> dict:
                 v[k, t] = eps[k, t]
             s = arm_step(*s, v[k, t, 0], v[k, t, 1], c.arm, c.delta_t, c.dynamics)
             S[k] += float(tracking_cost(*s, win, c.stage_cost_weight, c.cost_l1, c.cost_l2)) \
-                + c.param_gamma * u[t] @ sig_inv @ v[k, t]
+                + c.param_gamma * u[t] @ sig_inv @ v[k, t] + float(_stage_extra(c, s))
         S[k] += float(tracking_cost(*s, win, c.terminal_cost_weight, c.cost_l1, c.cost_l2))
     return _finish(c, x0, eps, v, S, out)
 
@@ -322,7 +341,7 @@ def step_vectorized(c: OracleMPPI, observed_x, eps) -> dict:
     for t in range(T):
         s = arm_step(*s, v[:, t, 0], v[:, t, 1], c.arm, c.delta_t, c.dynamics)
         ctrl = c.param_gamma * ((u[t] @ sig_inv) @ v[:, t, :].T)
-        S += tracking_cost(*s, win, c.stage_cost_weight, c.cost_l1, c.cost_l2) + ctrl
+        S += tracking_cost(*s, win, c.stage_cost_weight, c.cost_l1, c.cost_l2) + ctrl + _stage_extra(c, s)
     S += tracking_cost(*s, win, c.terminal_cost_weight, c.cost_l1, c.cost_l2)
     return _finish(c, x0, eps, v, S, out)
 
@@ -343,7 +362,7 @@ def rollout_costs(c: OracleMPPI, x0, eps, prev_idx=None, u=None) -> np.ndarray:
     for t in range(T):
         s = arm_step(*s, v[:, t, 0], v[:, t, 1], c.arm, c.delta_t, c.dynamics)
         S += tracking_cost(*s, win, c.stage_cost_weight, c.cost_l1, c.cost_l2) \
-            + c.param_gamma * ((u[t] @ sig_inv) @ v[:, t, :].T)
+            + c.param_gamma * ((u[t] @ sig_inv) @ v[:, t, :].T) + _stage_extra(c, s)
     S += tracking_cost(*s, win, c.terminal_cost_weight, c.cost_l1, c.cost_l2)
     return S
 

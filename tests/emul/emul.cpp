@@ -75,7 +75,7 @@ int emul_rollout_costs(const double* ref, int n_rows, int prev_idx, const double
         else
             S_out[k] = dynamics_f1 ? rollout_cost<1>(hd, A, W, tb.win, tb.cert, rows, ctl.data(), T, um, n, hits)
                                    : rollout_cost<0>(hd, A, W, tb.win, tb.cert, rows, ctl.data(), T, um, n, hits);
-        hits_total += hits.end; tri_total += hits.tri;
+        hits_total += T - hits.tri - hits.scan; tri_total += hits.tri;
     }
     if (hits_out) { hits_out[0] = hits_total; hits_out[1] = tri_total; }
     return p;

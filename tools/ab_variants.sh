@@ -1,10 +1,12 @@
 #!/bin/bash
-# A/B the rollout-kernel build variants in build/variants/*.so at the bench shape (K=2^20, T=100, tracking state).
+# A/B the rollout-kernel build variants in build/variants/*.so (tools/build_variants.py) at the bench shape
+# (K=2^20, T=100, tracking state), the 8-GPU shard size and the latency shape.
 for lib in build/variants/*.so; do
-  echo "== $lib"
-  MPPI_B200_LIB=$PWD/$lib python tools/profile_step.py --K 1048576 --T 100 --steps 12 --timing "$@" 2>&1 | tail -3 | head -1
+  for shape in "1048576 100" "131072 100" "16384 50"; do
+    set -- $shape
+    echo "== $lib K=$1 T=$2 $(MPPI_B200_LIB=$PWD/$lib python tools/profile_step.py --K $1 --T $2 --steps 12 --timing 2>&1 | grep -o "'rollout': [0-9.]*")"
+  done
 done
-for lib in build/variants/v0_default.so build/variants/v2_cconst_mb5.so; do
-  echo "== $lib NS=1"
-  MPPI_NS=1 MPPI_B200_LIB=$PWD/$lib python tools/profile_step.py --K 1048576 --T 100 --steps 12 --timing "$@" 2>&1 | tail -3 | head -1
+for lib in ${NS1_LIBS:-}; do
+  echo "== $lib NS=1 K=1048576 $(MPPI_NS=1 MPPI_B200_LIB=$PWD/$lib python tools/profile_step.py --K 1048576 --T 100 --steps 12 --timing 2>&1 | grep -o "'rollout': [0-9.]*")"
 done

@@ -55,7 +55,13 @@ enum {
     MPPI_FLAG_FULL_SEARCH = 16, /* control.py:208-215: always run the 30-candidate search (kernels compiled without the
                                    certified lookups; results are bit-identical either way) */
     MPPI_FLAG_DYNAMICS_F1 = 32, /* roll out with control.py:265-295 (_F1, feedback-linearised) instead of _F */
-    MPPI_FLAG_SEARCH_STATS = 64 /* count certified / total warp-lookups of the rollouts (mppi_search_stats) */
+    MPPI_FLAG_SEARCH_STATS = 64, /* count certified / total warp-lookups of the rollouts (mppi_search_stats) */
+    MPPI_FLAG_RESIDENT_STATE = 128 /* the controller state (u_prev, prev_idx, step counter: control.py:59, 65) stays on the
+                                   device between steps: each step reads only x0 from io_host, applies the shift of
+                                   control.py:148-149 and the index update of control.py:230 itself, and delivers only
+                                   the compact results (new_idx, status, rho, eta, u0).  mppi_upload_state() /
+                                   mppi_download_state() move the rest on demand (many environments: 36 B instead of
+                                   5 KB per environment and step over PCIe at T = 64) */
 };
 
 /* Hyper-parameters: control.py:21-65 + sys_params.py:3-10, fixed for the life of a handle. */
@@ -101,8 +107,12 @@ typedef struct MppiIoLayout {
     size_t off_step;            /* uint64 [1]             control-step counter (Philox)          */
     /* outputs, valid after mppi_wait()                                                          */
     size_t off_new_idx;         /* int32  [n_env]         updated waypoint index (control.py:230)*/
+    size_t off_status;          /* int32  [n_env]         bit 0: peer exchange timed out, update skipped */
     size_t off_rho;             /* double [n_env]         min cost (control.py:303)              */
     size_t off_eta;             /* double [n_env]         normaliser (control.py:306-308)        */
+    size_t off_u0;              /* double [n_env][2]      the control calc_control_input returns (control.py:152:
+                                                          first row of the shifted sequence)     */
+    /* [off_new_idx, off_w_eps_raw) = the compact results of MPPI_FLAG_RESIDENT_STATE            */
     size_t off_w_eps_raw;       /* double [n_env][T][2]   weighted noise sum (control.py:115-118)*/
     size_t off_w_eps_filt;      /* double [n_env][T][2]   after the median filter (control.py:122)*/
     size_t off_u_new;           /* double [n_env][T][2]   u + filtered update (control.py:126)   */
@@ -144,6 +154,13 @@ int mppi_step_combine(MppiHandle* h, const double* gathered_dev, int32_t world, 
 
 int mppi_wait(MppiHandle* h);
 
+/* MPPI_FLAG_RESIDENT_STATE: push the controller state in io_host (u_prev, prev_idx, step counter; x0 too) to the
+ * device / fetch the device's controller state and the full outputs of the last step into io_host.  Both are
+ * enqueued on `stream`; mppi_wait() (or a stream synchronise) completes them.  A resident handle must be
+ * uploaded once before its first step and after every host-side change of the state. */
+int mppi_upload_state(MppiHandle* h, void* stream);
+int mppi_download_state(MppiHandle* h, void* stream);
+
 /* Device-resident closed loop — n_steps ticks of run.py:48-59 without a host round trip (Philox noise,
  * whole sample set on this handle).  Per tick: the MPPI step above; u = first row of the shifted
  * sequence (what calc_control_input returns, control.py:152); plant dq += dt*Arm_Dynamic(q,dq,u),
@@ -160,12 +177,15 @@ int mppi_closed_loop(MppiHandle* h, int32_t n_steps, double plant_dt, double* lo
  * buffer of mppi_exchange_bytes() bytes, ZERO-INITIALISED, that all ranks of the node have mapped over
  * NVLink (peer / symmetric memory).  peer_bufs[r] = address of rank r's buffer as mapped on THIS GPU.
  * The last block of the weight-sum kernel stores this shard's (rho_g, eta_g, V_g) into every peer's
- * buffer and raises a flag; the finalize kernel of each rank waits for its `world` flags (with a ~3 s
- * timeout, reported by mppi_exchange_status() != 0) and combines.  mppi_step_sharded() = the whole step. */
+ * buffer and raises a flag, then waits for its `world` flags (bounded: mppi_set_exchange_timeout) and
+ * combines.  mppi_step_sharded() = the whole step. */
 size_t mppi_exchange_bytes(const MppiConfig* cfg, int32_t world);
 int mppi_set_peer_exchange(MppiHandle* h, int32_t rank, int32_t world, void* const* peer_bufs);
 int mppi_step_sharded(MppiHandle* h, int32_t noise_mode, const float* eps_dev, void* stream);
+/* != 0 when the last finished step (after mppi_wait) skipped its update because a peer's partial did not arrive
+ * within the timeout (default 3000 ms): u_new = u_prev, rho = eta = NaN.  The next step starts clean. */
 int mppi_exchange_status(MppiHandle* h);
+int mppi_set_exchange_timeout(MppiHandle* h, double milliseconds);
 
 /* Caller-side CUDA-graph capture of the sharded step (mppi_step_local + the caller's collective +
  * mppi_step_combine on one capturing stream): while capture mode is on, the library enqueues only

@@ -22,6 +22,7 @@ FLAG_SMOOTH_NONE = 8
 FLAG_FULL_SEARCH = 16
 FLAG_DYNAMICS_F1 = 32
 FLAG_SEARCH_STATS = 64
+FLAG_RESIDENT_STATE = 128
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_WORKSPACE = 0, -1, -2, -3, -4
 
@@ -42,8 +43,8 @@ class MppiConfig(C.Structure):
 
 class MppiIoLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in (
-        "bytes", "off_x0", "off_u_prev", "off_prev_idx", "off_step", "off_new_idx", "off_rho", "off_eta",
-        "off_w_eps_raw", "off_w_eps_filt", "off_u_new", "off_opt_traj")]
+        "bytes", "off_x0", "off_u_prev", "off_prev_idx", "off_step", "off_new_idx", "off_status", "off_rho", "off_eta",
+        "off_u0", "off_w_eps_raw", "off_w_eps_filt", "off_u_new", "off_opt_traj")]
 
 
 # name -> (restype, argtypes); must list every symbol include/mppi_b200.h declares
@@ -61,11 +62,14 @@ SYMBOLS = {
     "mppi_step_local": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mppi_step_combine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "mppi_wait": (C.c_int, [C.c_void_p]),
+    "mppi_upload_state": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mppi_download_state": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mppi_closed_loop": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mppi_exchange_bytes": (C.c_size_t, [C.POINTER(MppiConfig), C.c_int32]),
     "mppi_set_peer_exchange": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "mppi_step_sharded": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "mppi_exchange_status": (C.c_int, [C.c_void_p]),
+    "mppi_set_exchange_timeout": (C.c_int, [C.c_void_p, C.c_double]),
     "mppi_set_capture_mode": (C.c_int, [C.c_void_p, C.c_int32]),
     "mppi_replay_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mppi_replay_end": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -66,6 +66,7 @@ struct MppiHandle {
     bool capture_mode;         // caller is capturing: enqueue capturable work only
     uint64_t capture_kernels;  // kernels enqueued while capture mode was on (= per replay)
     cudaEvent_t const_ev;      // recorded after this handle's last reader of the constant-bank window
+    uint64_t step_scratch;     // source of the step-counter upload of a resident handle
     char err[512];
 };
 
@@ -128,7 +129,8 @@ int pick_ns(const MppiConfig* c, int sm) {
     const bool cw = pick_const_window(c);
     double best_cost = 0.0; int best = 1;
     for (int ns = 1; ns <= 2; ++ns) {
-        const int per_sm = certified_kernels(c) ? MPPI_ROLL_MIN_BLOCKS_CERT : (cw ? MPPI_ROLL_MIN_BLOCKS_CONST : (ns == 1 ? 3 : 2));
+        const int per_sm = certified_kernels(c) ? (ns == 1 ? MPPI_ROLL_MIN_BLOCKS_CERT_NS1 : MPPI_ROLL_MIN_BLOCKS_CERT)
+                                                : (cw ? MPPI_ROLL_MIN_BLOCKS_CONST : (ns == 1 ? 3 : 2));
         const long long ctas = (((long long)c->K_local + 128 * ns - 1) / (128 * ns)) * c->n_env;
         const long long slots = (long long)sm * per_sm;
         const long long full = ctas / slots, rest = ctas % slots;
@@ -264,6 +266,7 @@ struct StepOpts {
                                // (false: device mirror only — the ticks of the device closed loop)
     bool use_px = false;       // exchange the partial triple through peer memory (sharded step)
     bool record_done = true;   // record the completion event after the step
+    bool fuse_finalize = false;   // combine / filter / update run in the last block of the fused weight-sum kernel
 };
 
 // enqueue everything up to this shard's partial triple
@@ -288,12 +291,18 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
     const double* ref = (const double*)(ws + h->ws.off_ref);
 
     // host_io = false: the step works on the device mirror only (ticks of the device closed loop)
-    const bool zc = h->zero_copy && copy_inputs;
+    const bool resident = (dc.flags & MPPI_FLAG_RESIDENT_STATE) != 0;
+    const int pull = (h->zero_copy && copy_inputs) ? (resident ? 1 : 3) : 0;
     const DevIo& dio = copy_inputs ? h->dio : h->dio_dev;
-    if (copy_inputs && !h->zero_copy)
-        CU(h, cudaMemcpyAsync(ws + h->ws.off_in, h->host, h->in_bytes, cudaMemcpyHostToDevice, s));
+    if (copy_inputs && !h->zero_copy) {
+        if (resident)        // only the observed states travel; the controller state lives on the device
+            CU(h, cudaMemcpyAsync(ws + h->ws.off_in + h->io.off_x0, h->host + h->io.off_x0,
+                                  (size_t)dc.n_env * 4 * sizeof(double), cudaMemcpyHostToDevice, s));
+        else
+            CU(h, cudaMemcpyAsync(ws + h->ws.off_in, h->host, h->in_bytes, cudaMemcpyHostToDevice, s));
+    }
     if (timed) CU(h, cudaEventRecord(h->tev[0], s));
-    mppi_prepare_sm100a<<<dc.n_env, 32, 0, s>>>(dc, dio, ref, step_blocks, zc,
+    mppi_prepare_sm100a<<<dc.n_env, 32, 0, s>>>(dc, dio, ref, step_blocks, pull,
                                                 (unsigned long long*)(ws + h->ws.off_seq));
     if (timed) CU(h, cudaEventRecord(h->tev[1], s));
     {
@@ -338,7 +347,8 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
         const size_t sm = (size_t)(kWsumThreads / 32) * ((dc.T + 1) / 2) * sizeof(float4);
         mppi_softmin_wsum_philox_sm100a<<<dim3(g, dc.n_env), kWsumThreads, sm, s>>>(
             dc, step_ctr, S, bmin, w, (double*)(ws + h->ws.off_eta_fused), v_part,
-            (unsigned int*)(ws + h->ws.off_tickets), rho, partial_dev, use_px ? h->px : PeerExchange{});
+            (unsigned int*)(ws + h->ws.off_tickets), rho, partial_dev, use_px ? h->px : PeerExchange{},
+            dio, o.fuse_finalize ? 1 : 0);
         if (timed) { CU(h, cudaEventRecord(h->tev[3], s)); CU(h, cudaEventRecord(h->tev[4], s)); }
         h->launches += 3;
     } else {
@@ -363,14 +373,18 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
 int enqueue_combine(MppiHandle* h, const double* gathered_dev, int world, cudaStream_t s, const StepOpts& o) {
     const bool timed = o.timed, record_done = o.record_done && !o.capturing, copy_outputs = o.host_io, use_px = o.use_px;
     if (world < 1 || world > 64) return fail(h, MPPI_ERR_INVALID, "%s", "world must be in [1, 64]");
-    mppi_finalize_sm100a<<<h->dc.n_env, 256, 0, s>>>(h->dc, copy_outputs ? h->dio : h->dio_dev, gathered_dev, world,
-                                                     use_px ? h->px : PeerExchange{},
-                                                     (int*)(h->dev + h->ws.off_seq + sizeof(unsigned long long)));
+    if (!o.fuse_finalize) {      // (fused: the last block of the weight-sum kernel has done this already)
+        mppi_finalize_sm100a<<<h->dc.n_env, 256, 0, s>>>(h->dc, copy_outputs ? h->dio : h->dio_dev, gathered_dev, world,
+                                                         use_px ? h->px : PeerExchange{});
+        h->launches += 1;
+    }
     if (timed) CU(h, cudaEventRecord(h->tev[6], s));
     CU(h, cudaGetLastError());
-    if (copy_outputs && !h->zero_copy) CU(h, cudaMemcpyAsync(h->host + h->out_off, h->dev + h->ws.off_out, h->out_bytes, cudaMemcpyDeviceToHost, s));
+    if (copy_outputs && !h->zero_copy) {
+        const size_t n = (h->dc.flags & MPPI_FLAG_RESIDENT_STATE) ? h->io.off_w_eps_raw - h->io.off_new_idx : h->out_bytes;
+        CU(h, cudaMemcpyAsync(h->host + h->out_off, h->dev + h->ws.off_out, n, cudaMemcpyDeviceToHost, s));
+    }
     if (record_done) CU(h, cudaEventRecord(h->done, s));      // not inside a stream capture
-    h->launches += 1;
     return MPPI_OK;
 }
 
@@ -403,8 +417,10 @@ int mppi_io_layout(const MppiConfig* c, MppiIoLayout* o) {
     o->off_step = take(sizeof(uint64_t));
     off = align_up(off, 256);
     o->off_new_idx = take(E * sizeof(int32_t));
+    o->off_status = take(E * sizeof(int32_t));
     o->off_rho = take(E * sizeof(double));
     o->off_eta = take(E * sizeof(double));
+    o->off_u0 = take(E * 2 * sizeof(double));
     o->off_w_eps_raw = take(E * T * 2 * sizeof(double));
     o->off_w_eps_filt = take(E * T * 2 * sizeof(double));
     o->off_u_new = take(E * T * 2 * sizeof(double));
@@ -466,8 +482,10 @@ int mppi_create(const MppiConfig* c, void* workspace, size_t workspace_bytes, vo
     h->dio.prev_idx = (const int32_t*)(din + h->io.off_prev_idx);
     h->dio.step = (const uint64_t*)(din + h->io.off_step);
     h->dio.new_idx = (int32_t*)(dout + h->io.off_new_idx);
+    h->dio.status = (int32_t*)(dout + h->io.off_status);
     h->dio.rho = (double*)(dout + h->io.off_rho);
     h->dio.eta = (double*)(dout + h->io.off_eta);
+    h->dio.u0 = (double*)(dout + h->io.off_u0);
     h->dio.w_eps_raw = (double*)(dout + h->io.off_w_eps_raw);
     h->dio.w_eps_filt = (double*)(dout + h->io.off_w_eps_filt);
     h->dio.u_new = (double*)(dout + h->io.off_u_new);
@@ -492,6 +510,7 @@ int mppi_create(const MppiConfig* c, void* workspace, size_t workspace_bytes, vo
         }
     }
     h->px.world = 0;
+    h->px.timeout_ns = 3000000000ull;
     h->px.seq = (const unsigned long long*)(h->dev + h->ws.off_seq);
     if (cudaMemset(h->dev + h->ws.off_seq, 0, 2 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(h->dev + h->ws.off_stats, 0, 4 * sizeof(unsigned long long)) != cudaSuccess ||
@@ -601,7 +620,7 @@ int mppi_step(MppiHandle* h, int32_t noise_mode, const float* eps_dev, void* str
             const uint64_t before = h->launches;
             cudaGraph_t g = nullptr;
             CU(h, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            StepOpts o; o.capturing = true;
+            StepOpts o; o.capturing = true; o.fuse_finalize = true;
             int rc = enqueue_local(h, noise_mode, nullptr, partial, s, o);
             if (rc == MPPI_OK) rc = enqueue_combine(h, partial, 1, s, o);
             cudaError_t ce = cudaStreamEndCapture(s, &g);
@@ -622,6 +641,7 @@ int mppi_step(MppiHandle* h, int32_t noise_mode, const float* eps_dev, void* str
         return MPPI_OK;
     }
     StepOpts o; o.timed = h->timing;
+    o.fuse_finalize = noise_mode == MPPI_NOISE_PHILOX && !h->timing;      // (timed: finalize as its own kernel, own timer)
     int rc = enqueue_local(h, noise_mode, eps_dev, partial, s, o);
     if (rc != MPPI_OK) return rc;
     rc = enqueue_combine(h, partial, 1, s, o);
@@ -642,7 +662,7 @@ int mppi_set_peer_exchange(MppiHandle* h, int32_t rank, int32_t world, void* con
         return fail(h, MPPI_ERR_INVALID, "%s", "peer exchange needs 1 <= world <= 16, 0 <= rank < world and the peer buffer table");
     for (int r = 0; r < world; ++r)
         if (!peer_bufs[r] || ((uintptr_t)peer_bufs[r] & 15)) return fail(h, MPPI_ERR_INVALID, "%s", "null or misaligned peer buffer");
-    h->px.rank = rank; h->px.world = world;
+    h->px.rank = rank; h->px.world = world;   // (timeout_ns keeps its value)
     for (int r = 0; r < kMaxPeers; ++r) h->px.buf[r] = r < world ? (char*)peer_bufs[r] : nullptr;
     h->px.slot_bytes = (size_t)world * h->cfg.n_env * (2 + 2 * h->cfg.T) * sizeof(double);
     h->px.flags_off = align_up(2 * h->px.slot_bytes, 256);
@@ -664,7 +684,7 @@ int mppi_step_sharded(MppiHandle* h, int32_t noise_mode, const float* eps_dev, v
             const uint64_t before = h->launches;
             cudaGraph_t g = nullptr;
             CU(h, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            StepOpts o; o.capturing = true; o.use_px = true;
+            StepOpts o; o.capturing = true; o.use_px = true; o.fuse_finalize = true;
             int rc = enqueue_local(h, noise_mode, nullptr, partial, s, o);
             if (rc == MPPI_OK) rc = enqueue_combine(h, local_slots, h->px.world, s, o);
             cudaError_t ce = cudaStreamEndCapture(s, &g);
@@ -684,7 +704,7 @@ int mppi_step_sharded(MppiHandle* h, int32_t noise_mode, const float* eps_dev, v
         h->have_step = true;
         return MPPI_OK;
     }
-    StepOpts o; o.use_px = true;
+    StepOpts o; o.use_px = true; o.fuse_finalize = noise_mode == MPPI_NOISE_PHILOX;
     int rc = enqueue_local(h, noise_mode, eps_dev, partial, s, o);
     if (rc != MPPI_OK) return rc;
     return enqueue_combine(h, local_slots, h->px.world, s, o);
@@ -692,9 +712,44 @@ int mppi_step_sharded(MppiHandle* h, int32_t noise_mode, const float* eps_dev, v
 
 int mppi_exchange_status(MppiHandle* h) {
     if (!h) return MPPI_ERR_INVALID;
-    int st = 0;
-    CU(h, cudaMemcpy(&st, h->dev + h->ws.off_seq + sizeof(unsigned long long), sizeof(int), cudaMemcpyDeviceToHost));
-    return st;
+    // the status words of the last step were delivered to io_host with its other results (valid after mppi_wait)
+    const int32_t* st = (const int32_t*)(h->host + h->io.off_status);
+    int any = 0;
+    for (int e = 0; e < h->cfg.n_env; ++e) any |= st[e];
+    return any & 1;
+}
+
+int mppi_set_exchange_timeout(MppiHandle* h, double milliseconds) {
+    if (!h) return MPPI_ERR_INVALID;
+    if (!(milliseconds > 0.0)) return fail(h, MPPI_ERR_INVALID, "%s", "the exchange timeout must be > 0 ms");
+    h->px.timeout_ns = (unsigned long long)(milliseconds * 1.0e6);
+    if (h->sharded_exec) { cudaGraphExecDestroy(h->sharded_exec); h->sharded_exec = nullptr; }   // (a kernel argument)
+    return MPPI_OK;
+}
+
+int mppi_upload_state(MppiHandle* h, void* stream) {
+    if (!h) return MPPI_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(h, cudaMemcpyAsync(h->dev + h->ws.off_in, h->host, h->in_bytes, cudaMemcpyHostToDevice, s));
+    if (h->cfg.flags & MPPI_FLAG_RESIDENT_STATE) {
+        // the prepare kernel of a resident handle advances the step counter BEFORE using it
+        h->step_scratch = *(const uint64_t*)(h->host + h->io.off_step) - 1ull;
+        CU(h, cudaMemcpyAsync(h->dev + h->ws.off_in + h->io.off_step, &h->step_scratch, sizeof(uint64_t),
+                              cudaMemcpyHostToDevice, s));
+    }
+    CU(h, cudaEventRecord(h->done, s));
+    return MPPI_OK;
+}
+
+int mppi_download_state(MppiHandle* h, void* stream) {
+    if (!h) return MPPI_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    // u_prev, prev_idx and the step counter as the device holds them (x0 is the caller's own)
+    CU(h, cudaMemcpyAsync(h->host + h->io.off_u_prev, h->dev + h->ws.off_in + h->io.off_u_prev,
+                          h->in_bytes - h->io.off_u_prev, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaMemcpyAsync(h->host + h->out_off, h->dev + h->ws.off_out, h->out_bytes, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaEventRecord(h->done, s));
+    return MPPI_OK;
 }
 
 int mppi_closed_loop(MppiHandle* h, int32_t n_steps, double plant_dt, double* log_dev, int32_t* stop_dev,
@@ -716,12 +771,16 @@ int mppi_closed_loop(MppiHandle* h, int32_t n_steps, double plant_dt, double* lo
     CU(h, cudaMemcpyAsync(lp_dev, &lp, sizeof(lp), cudaMemcpyHostToDevice, s));
     CU(h, cudaMemsetAsync(stop_dev, 0x7f, sizeof(int32_t) * h->cfg.n_env, s));
     CU(h, cudaMemcpyAsync(ws + h->ws.off_in, h->host, h->in_bytes, cudaMemcpyHostToDevice, s));
+    if (h->cfg.flags & MPPI_FLAG_RESIDENT_STATE) {      // (the prepare kernel advances the counter before using it)
+        h->step_scratch = *(const uint64_t*)(h->host + h->io.off_step) - 1ull;
+        CU(h, cudaMemcpyAsync(ws + h->ws.off_in + h->io.off_step, &h->step_scratch, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    }
     if (!h->tick_exec || h->tick_stream != stream) {
         if (h->tick_exec) { cudaGraphExecDestroy(h->tick_exec); h->tick_exec = nullptr; }
         const uint64_t before = h->launches;
         cudaGraph_t g = nullptr;
         CU(h, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        StepOpts o; o.capturing = true; o.host_io = false;
+        StepOpts o; o.capturing = true; o.host_io = false; o.fuse_finalize = true;
         int rc = enqueue_local(h, MPPI_NOISE_PHILOX, nullptr, partial, s, o);
         if (rc == MPPI_OK) rc = enqueue_combine(h, partial, 1, s, o);
         if (rc == MPPI_OK) {

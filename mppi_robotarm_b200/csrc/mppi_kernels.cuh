@@ -125,6 +125,7 @@ struct PeerExchange {
     size_t slot_bytes;            // world * n_env * (2 + 2T) * 8
     size_t flags_off;             // 2 * slot_bytes rounded up to 256
     const unsigned long long* seq;   // step sequence number of this handle (device memory, set by prepare)
+    unsigned long long timeout_ns;   // how long the combine waits for a peer's partial (mppi_set_exchange_timeout)
 };
 __device__ __forceinline__ double* px_slot(const PeerExchange& px, int on_rank, int parity, int from_rank, int n_env,
                                            int e, int n) {
@@ -158,7 +159,9 @@ struct DevIo {
     const int32_t* prev_idx; // [n_env]
     const uint64_t* step;    // [1]
     int32_t* new_idx;        // [n_env]
+    int32_t* status;         // [n_env] bit 0: the peer exchange timed out (the update was skipped)
     double* rho; double* eta;            // [n_env]
+    double* u0;              // [n_env][2] first row of the shifted sequence (what calc_control_input returns)
     double* w_eps_raw; double* w_eps_filt; double* u_new;   // [n_env][T][2]
     double* opt_traj;                    // [n_env][T][4]
     // zero-copy mode: the caller's pinned block is read / written directly by the kernels
@@ -348,17 +351,21 @@ __device__ __forceinline__ void warp_win_cert(const double (*srow)[2], int lane,
 // early as its address is known: (1) all inputs at once — from the caller's pinned block over PCIe
 // (zero-copy) or from the device mirror; (2) the 60 reference rows the new window can touch, while the
 // FP64 forward kinematics run; the rows of the final window are then picked by shuffles, not reloaded.
+// pull: which inputs are read from the caller's pinned block (zero-copy): bit 0 the observed state, bit 1 the
+// controller state (sequence, waypoint index, step counter).  MPPI_FLAG_RESIDENT_STATE (128) keeps the controller
+// state on the device between steps: the step counter then advances here.
 __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, const double* __restrict__ ref,
-                                                          char* __restrict__ step_blocks, bool pull_inputs,
+                                                          char* __restrict__ step_blocks, int pull,
                                                           unsigned long long* __restrict__ seq) {
     __shared__ double srow[kWindowPad][2];        // local window rows for the certificate construction
     const int e = blockIdx.x, lane = threadIdx.x, T = cfg.T;
     if (e == 0 && lane == 0) *seq += 1ull;        // step sequence number, read by every later kernel of the step
-    const bool zc = io.host_in != nullptr && pull_inputs;
+    const bool zx = io.host_in != nullptr && (pull & 1), zc = io.host_in != nullptr && (pull & 2);
     const ptrdiff_t back = zc ? io.in_delta : 0;  // zero-copy: read the pinned block instead of the mirror
-    const double* sx = (const double*)((const char*)(io.x0 + 4 * e) - back);
+    const double* sx = (const double*)((const char*)(io.x0 + 4 * e) - (zx ? io.in_delta : 0));
     const double2* su = (const double2*)((const char*)(io.u_prev + (size_t)e * T * 2) - back);
     const int32_t* sp = (const int32_t*)((const char*)(io.prev_idx + e) - back);
+    if ((cfg.flags & 128) && e == 0 && lane == 0) *const_cast<uint64_t*>(io.step) += 1;   // resident state: next control step
     // ---- (1) inputs --------------------------------------------------------------------------------
     constexpr int kTS = (MPPI_MAX_T_INTERNAL + 31) / 32;
     double2 uu[kTS];
@@ -373,11 +380,13 @@ __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, 
     const double4* ref4 = (const double4*)ref;
     const double4 r_lo = ref4[min(p + lane, n - 1)];
     const double4 r_hi = ref4[min(p + 32 + lane, n - 1)];
-    if (zc) {                                     // fill the device mirror every later kernel reads
+    if (zx && lane == 0) {                        // fill the device mirror every later kernel reads
         double* dx = const_cast<double*>(io.x0) + 4 * e;
+        dx[0] = q1; dx[1] = q2; dx[2] = dq1; dx[3] = dq2;
+    }
+    if (zc) {
         double2* du = (double2*)(const_cast<double*>(io.u_prev) + (size_t)e * T * 2);
         if (lane == 0) {
-            dx[0] = q1; dx[1] = q2; dx[2] = dq1; dx[3] = dq2;
             const_cast<int32_t*>(io.prev_idx)[e] = *sp;
             if (e == 0) *const_cast<uint64_t*>(io.step) = stp;
         }
@@ -548,6 +557,9 @@ struct WinConst {
 #ifndef MPPI_ROLL_MIN_BLOCKS_CERT
 #define MPPI_ROLL_MIN_BLOCKS_CERT 5      // <= 102 registers: 20 warps per SM (A/B on B200: profiles/r2_variants.md)
 #endif
+#ifndef MPPI_ROLL_MIN_BLOCKS_CERT_NS1
+#define MPPI_ROLL_MIN_BLOCKS_CERT_NS1 5  // the one-sample-per-thread kernel (small shards, latency runs)
+#endif
 
 // Window policy per kernel family.  CERT: certified lookups, the table stays in shared memory (any number of
 // environments).  Otherwise plain searches with the coefficients in the constant bank (CONSTWIN) or in registers.
@@ -559,7 +571,7 @@ __device__ __forceinline__ void win_load(WinRegs& w, const StepBlockView& sb) { 
 __device__ __forceinline__ void win_load(WinConst& w, const StepBlockView& sb) { w.load(sb.win); }
 
 template <int NOISE, bool CONSTWIN, int kNS, int DYN = 0, bool CERT = true, bool JL = false>
-__global__ void __launch_bounds__(kRollThreads, CERT ? MPPI_ROLL_MIN_BLOCKS_CERT
+__global__ void __launch_bounds__(kRollThreads, CERT ? (kNS == 1 ? MPPI_ROLL_MIN_BLOCKS_CERT_NS1 : MPPI_ROLL_MIN_BLOCKS_CERT)
                                                      : (CONSTWIN ? MPPI_ROLL_MIN_BLOCKS_CONST : (kNS == 1 ? 3 : 2)))
 mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const char* __restrict__ step_blocks,
                     const float* __restrict__ eps, float* __restrict__ S_out, float* __restrict__ block_min,
@@ -764,6 +776,167 @@ mppi_wsum_injected_sm100a(DevCfg cfg, const float* __restrict__ w, const float* 
     }
 }
 
+// ================================================================================================
+// 6. finalize: combine the gathered partials of all ranks (identically on every rank), normalise,
+//    median-filter, update the sequence, roll the optimal trajectory out (control.py:122-134).
+// ================================================================================================
+__device__ __forceinline__ int reflect_idx(int i, int n) {          // scipy 'reflect': d c b a | a b c d | d c b a
+    const int period = 2 * n;
+    i %= period; if (i < 0) i += period;
+    return i >= n ? period - 1 - i : i;
+}
+
+struct FinalizeSmem {
+    double raw[2 * MPPI_MAX_T_INTERNAL];
+    double unew[2 * MPPI_MAX_T_INTERNAL];
+    __align__(16) float tr[8 * MPPI_MAX_T_INTERNAL];    // optimal trajectory: (value, compensation) per state and step
+    double scale[64];
+    double eta_s;
+    int timed_out;
+};
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Everything after this GPU's partial triple, for environment e, by all threads of the calling block:
+// wait for the peers' triples (peer exchange only), combine, normalise, filter, update, optimal trajectory.
+// `gathered` = double [world][n_env][2 + 2T] (ignored with the peer exchange: its slots are read instead).
+__device__ __forceinline__ void finalize_env(const DevCfg& cfg, const DevIo& io, int e, const double* gathered, int world,
+                                             const PeerExchange& px, FinalizeSmem& sm) {
+    const int tid = threadIdx.x, T = cfg.T;
+    if (tid == 0) sm.timed_out = 0;
+    __syncthreads();
+    if (px.world > 0) {
+        // wait until every rank's triple of THIS step has landed in the local exchange buffer
+        const unsigned long long seq = *px.seq;
+        const int par = (int)(seq & 1ull);
+        if (tid < px.world) {
+            volatile const unsigned long long* f = px_flag(px, px.rank, par, tid, cfg.n_env, e);
+            const unsigned long long t0 = global_ns();
+            while (*f < seq) {
+                if (global_ns() - t0 > px.timeout_ns) { sm.timed_out = 1; break; }   // a peer died or is far behind
+                __nanosleep(64);
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        gathered = (const double*)(px.buf[px.rank] + (size_t)par * px.slot_bytes);
+        world = px.world;
+    }
+    // A partial that did not arrive must not be combined (its slot holds an older step): the update is
+    // skipped (u_new = u_prev, zero update, NaN rho / eta) and bit 0 of the status word tells the caller.
+    const bool skip = sm.timed_out != 0;
+    const size_t stride_rank = (size_t)cfg.n_env * (2 + 2 * T);
+    const double* g0 = gathered + (size_t)e * (2 + 2 * T);
+    if (tid == 0) {
+        double rho = g0[0];
+        for (int g = 1; g < world; ++g) rho = fmin(rho, g0[g * stride_rank]);
+        double eta = 0.0;
+        for (int g = 0; g < world; ++g) {
+            // a shard with no finite cost reports rho_g = +inf and eta_g = 0
+            const double sg = exp(-(g0[g * stride_rank] - rho) * cfg.inv_lambda);
+            sm.scale[g] = sg;
+            eta += sg * g0[g * stride_rank + 1];
+        }
+        sm.eta_s = eta;
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
+        out_store(io, io.rho + e, skip ? nan : rho); out_store(io, io.eta + e, skip ? nan : eta);
+        out_store(io, io.status + e, skip ? 1 : 0);
+    }
+    __syncthreads();
+    for (int c = tid; c < 2 * T; c += blockDim.x) {
+        double v = 0.0;
+        for (int g = 0; g < world; ++g) {
+            const double sg = sm.scale[g];
+            if (sg != 0.0) v += sg * g0[g * stride_rank + 2 + c];
+        }
+        v = skip ? 0.0 : v / sm.eta_s;
+        sm.raw[c] = v;
+        out_store(io, io.w_eps_raw + (size_t)e * 2 * T + c, v);
+    }
+    __syncthreads();
+    // scipy.ndimage.median_filter(size=10, mode='reflect') per column (control.py:319-327):
+    // window offsets -5..+4, output = element of rank 5 of the sorted window
+    for (int c = tid; c < 2 * T; c += blockDim.x) {
+        const int t = c >> 1, m = c & 1;
+        double med;
+        if (cfg.flags & 8) {                                  // MPPI_FLAG_SMOOTH_NONE
+            med = sm.raw[c];
+        } else if (cfg.flags & 4) {                           // MPPI_FLAG_SMOOTH_AVERAGE, control.py:329-344
+            // np.convolve(x, ones/10, 'same') = sum of x/10 over [t-5, t+4] clipped to the array, then the
+            // first and last ceil(10/2)-1 rows (and row 0) rescaled by 10/(number of terms)
+            const int lo = max(0, t - kFilter / 2), hi = min(T - 1, t + (kFilter - 1) / 2);
+            double acc = 0.0;
+            for (int k = lo; k <= hi; ++k) acc += sm.raw[2 * k + m] * (1.0 / kFilter);
+            const int n_conv = (kFilter + 1) / 2;
+            if (t == 0) acc *= (double)kFilter / n_conv;
+            else if (t < n_conv) acc *= (double)kFilter / (t + n_conv);
+            if (t > T - n_conv && t != 0) acc *= (double)kFilter / ((T - t) + n_conv - (kFilter % 2));
+            med = acc;
+        } else {
+            double win[kFilter];
+#pragma unroll
+            for (int o = 0; o < kFilter; ++o) win[o] = sm.raw[2 * reflect_idx(t + o - kFilter / 2, T) + m];
+            med = win[0];
+#pragma unroll
+            for (int a = 0; a < kFilter; ++a) {
+                int rank = 0;
+#pragma unroll
+                for (int b = 0; b < kFilter; ++b) rank += (win[b] < win[a]) || (win[b] == win[a] && b < a);
+                if (rank == kFilter / 2) med = win[a];
+            }
+        }
+        const double u = io.u_prev[(size_t)e * 2 * T + c] + med;        // control.py:126
+        sm.unew[c] = u;
+        out_store(io, io.w_eps_filt + (size_t)e * 2 * T + c, med);
+        out_store(io, io.u_new + (size_t)e * 2 * T + c, u);
+    }
+    __syncthreads();
+    // What calc_control_input returns as the control (control.py:148-152, quirk Q2: the first row AFTER the
+    // shift), and — MPPI_FLAG_RESIDENT_STATE — the controller state of the next step, kept on the device:
+    // shifted sequence (control.py:148-149) and waypoint index (control.py:230).  An environment at the end
+    // of its path (control.py:76-78: the reference raises there) is frozen.
+    {
+        const bool ended = io.new_idx[e] >= cfg.n_ref_rows - 1;
+        const int t1 = (T > 1 && !ended) ? 1 : 0;
+        if (tid < 2) out_store(io, io.u0 + 2 * e + tid, ended ? io.u_prev[(size_t)e * 2 * T + tid] : sm.unew[2 * t1 + tid]);
+        if (cfg.flags & 128) {
+            double* up = const_cast<double*>(io.u_prev) + (size_t)e * 2 * T;
+            if (!ended)
+                for (int c = tid; c < 2 * T; c += blockDim.x) up[c] = sm.unew[2 * min((c >> 1) + 1, T - 1) + (c & 1)];
+            if (tid == 0) const_cast<int32_t*>(io.prev_idx)[e] = io.new_idx[e];
+        }
+    }
+    // control.py:129-134: x <- F(x, u[t-1]) for t = 0..T-1 (t = 0 wraps to the last control, Q3).
+    // The recurrence is serial: one thread runs it and parks (value, compensation) pairs in shared
+    // memory; all threads then convert and store the trajectory (keeps global / PCIe stores off the chain).
+    if (cfg.flags & 1) {
+        if (tid == 0) {
+            const double* x0 = io.x0 + 4 * e;
+            ArmState st; arm_init(st, (float)x0[0], (float)x0[1], (float)x0[2], (float)x0[3]);
+            for (int t = 0; t < T; ++t) {
+                const int tc = t == 0 ? T - 1 : t - 1;
+                if (cfg.flags & 32) arm_step<1>(st, cfg.arm, (float)sm.unew[2 * tc], (float)sm.unew[2 * tc + 1]);   // MPPI_FLAG_DYNAMICS_F1
+                else arm_step<0>(st, cfg.arm, (float)sm.unew[2 * tc], (float)sm.unew[2 * tc + 1]);
+                float4* o = (float4*)(sm.tr + 8 * t);
+                o[0] = make_float4(st.q1, st.q2, st.d1, st.d2);
+                o[1] = make_float4(st.kq1, st.kq2, st.kd1, st.kd2);
+            }
+        }
+        __syncthreads();
+        double* o = io.opt_traj + (size_t)e * 4 * T;
+        for (int c = tid; c < 4 * T; c += blockDim.x) {
+            const int t = c >> 2, k = c & 3;
+            out_store(io, o + c, (double)sm.tr[8 * t + k] - (double)sm.tr[8 * t + 4 + k]);
+        }
+    } else {
+        for (int c = tid; c < 4 * T; c += blockDim.x) out_store(io, io.opt_traj + (size_t)e * 4 * T + c, 0.0);
+    }
+}
+
 constexpr int kPairSlots = MPPI_MAX_T_INTERNAL / 2 / 32;      // Philox calls per lane and sample (weight-sum kernel)
 
 // ================================================================================================
@@ -780,7 +953,8 @@ mppi_softmin_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ct
                                 const float* __restrict__ block_min, float* __restrict__ w,
                                 double* __restrict__ eta_part, float* __restrict__ v_part,
                                 unsigned int* __restrict__ tickets, float* __restrict__ rho_out,
-                                double* __restrict__ partial, PeerExchange px) {
+                                double* __restrict__ partial, PeerExchange px, DevIo io, int fuse_finalize) {
+    __shared__ FinalizeSmem fin;                              // (used by the last block only)
     extern __shared__ __align__(16) unsigned char smem_wsum[];
     float4* sh = (float4*)smem_wsum;                          // [warps][pairs]
     __shared__ float redf[kWsumThreads / 32];
@@ -899,6 +1073,14 @@ mppi_softmin_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ct
         out[2 + c] = a;
     }
     if (px.world > 0) px_put(px, out, cfg.n_env, e, 2 + 2 * cfg.T);   // fused exchange: triple -> every peer
+    // fused combine / filter / update / optimal trajectory: one kernel boundary less per control step.  With
+    // the peer exchange this block then waits for the other ranks' triples (their last blocks put them the
+    // same way; every rank's kernel is resident on its own GPU, so the wait cannot deadlock).
+    if (fuse_finalize) {
+        __threadfence();
+        __syncthreads();
+        finalize_env(cfg, io, e, partial, 1, px, fin);
+    }
 }
 
 // ================================================================================================
@@ -945,130 +1127,12 @@ mppi_reduce_sm100a(DevCfg cfg, int n_wsum_blocks, const float* __restrict__ rho,
 }
 
 // ================================================================================================
-// 6. finalize: combine the gathered partials of all ranks (identically on every rank), normalise,
-//    median-filter, update the sequence, roll the optimal trajectory out (control.py:122-134).
+// 6b. finalize as a kernel of its own (injected-noise mode, NCCL exchange, timed runs)
 // ================================================================================================
-__device__ __forceinline__ int reflect_idx(int i, int n) {          // scipy 'reflect': d c b a | a b c d | d c b a
-    const int period = 2 * n;
-    i %= period; if (i < 0) i += period;
-    return i >= n ? period - 1 - i : i;
-}
-
 __global__ void __launch_bounds__(256)
-mppi_finalize_sm100a(DevCfg cfg, DevIo io, const double* gathered, int world, PeerExchange px,
-                     int* __restrict__ px_status) {
-    __shared__ double raw[2 * MPPI_MAX_T_INTERNAL];
-    __shared__ double unew[2 * MPPI_MAX_T_INTERNAL];
-    __shared__ __align__(16) float tr[8 * MPPI_MAX_T_INTERNAL];    // optimal trajectory: (value, compensation) per state and step
-    __shared__ double scale[64];
-    __shared__ double eta_s;
-    const int e = blockIdx.x, tid = threadIdx.x, T = cfg.T;
-    if (px.world > 0) {
-        // wait until every rank's triple of THIS step has landed in the local exchange buffer
-        const unsigned long long seq = *px.seq;
-        const int par = (int)(seq & 1ull);
-        if (tid < px.world) {
-            volatile const unsigned long long* f = px_flag(px, px.rank, par, tid, cfg.n_env, e);
-            const long long t0 = clock64();
-            while (*f < seq) {
-                if (clock64() - t0 > 6000000000ll) { atomicExch(px_status, 1); break; }   // ~3 s: a peer died
-                __nanosleep(64);
-            }
-        }
-        __threadfence_system();
-        __syncthreads();
-        gathered = (const double*)(px.buf[px.rank] + (size_t)par * px.slot_bytes);
-        world = px.world;
-    }
-    const size_t stride_rank = (size_t)cfg.n_env * (2 + 2 * T);
-    const double* g0 = gathered + (size_t)e * (2 + 2 * T);
-    if (tid == 0) {
-        double rho = g0[0];
-        for (int g = 1; g < world; ++g) rho = fmin(rho, g0[g * stride_rank]);
-        double eta = 0.0;
-        for (int g = 0; g < world; ++g) {
-            // a shard with no finite cost reports rho_g = +inf and eta_g = 0
-            const double sg = exp(-(g0[g * stride_rank] - rho) * cfg.inv_lambda);
-            scale[g] = sg;
-            eta += sg * g0[g * stride_rank + 1];
-        }
-        eta_s = eta;
-        out_store(io, io.rho + e, rho); out_store(io, io.eta + e, eta);
-    }
-    __syncthreads();
-    for (int c = tid; c < 2 * T; c += blockDim.x) {
-        double v = 0.0;
-        for (int g = 0; g < world; ++g) {
-            const double sg = scale[g];
-            if (sg != 0.0) v += sg * g0[g * stride_rank + 2 + c];
-        }
-        v /= eta_s;
-        raw[c] = v;
-        out_store(io, io.w_eps_raw + (size_t)e * 2 * T + c, v);
-    }
-    __syncthreads();
-    // scipy.ndimage.median_filter(size=10, mode='reflect') per column (control.py:319-327):
-    // window offsets -5..+4, output = element of rank 5 of the sorted window
-    for (int c = tid; c < 2 * T; c += blockDim.x) {
-        const int t = c >> 1, m = c & 1;
-        double med;
-        if (cfg.flags & 8) {                                  // MPPI_FLAG_SMOOTH_NONE
-            med = raw[c];
-        } else if (cfg.flags & 4) {                           // MPPI_FLAG_SMOOTH_AVERAGE, control.py:329-344
-            // np.convolve(x, ones/10, 'same') = sum of x/10 over [t-5, t+4] clipped to the array, then the
-            // first and last ceil(10/2)-1 rows (and row 0) rescaled by 10/(number of terms)
-            const int lo = max(0, t - kFilter / 2), hi = min(T - 1, t + (kFilter - 1) / 2);
-            double acc = 0.0;
-            for (int k = lo; k <= hi; ++k) acc += raw[2 * k + m] * (1.0 / kFilter);
-            const int n_conv = (kFilter + 1) / 2;
-            if (t == 0) acc *= (double)kFilter / n_conv;
-            else if (t < n_conv) acc *= (double)kFilter / (t + n_conv);
-            if (t > T - n_conv && t != 0) acc *= (double)kFilter / ((T - t) + n_conv - (kFilter % 2));
-            med = acc;
-        } else {
-            double win[kFilter];
-#pragma unroll
-            for (int o = 0; o < kFilter; ++o) win[o] = raw[2 * reflect_idx(t + o - kFilter / 2, T) + m];
-            med = win[0];
-#pragma unroll
-            for (int a = 0; a < kFilter; ++a) {
-                int rank = 0;
-#pragma unroll
-                for (int b = 0; b < kFilter; ++b) rank += (win[b] < win[a]) || (win[b] == win[a] && b < a);
-                if (rank == kFilter / 2) med = win[a];
-            }
-        }
-        const double u = io.u_prev[(size_t)e * 2 * T + c] + med;        // control.py:126
-        unew[c] = u;
-        out_store(io, io.w_eps_filt + (size_t)e * 2 * T + c, med);
-        out_store(io, io.u_new + (size_t)e * 2 * T + c, u);
-    }
-    __syncthreads();
-    // control.py:129-134: x <- F(x, u[t-1]) for t = 0..T-1 (t = 0 wraps to the last control, Q3).
-    // The recurrence is serial: one thread runs it and parks (value, compensation) pairs in shared
-    // memory; all threads then convert and store the trajectory (keeps global / PCIe stores off the chain).
-    if (cfg.flags & 1) {
-        if (tid == 0) {
-            const double* x0 = io.x0 + 4 * e;
-            ArmState st; arm_init(st, (float)x0[0], (float)x0[1], (float)x0[2], (float)x0[3]);
-            for (int t = 0; t < T; ++t) {
-                const int tc = t == 0 ? T - 1 : t - 1;
-                if (cfg.flags & 32) arm_step<1>(st, cfg.arm, (float)unew[2 * tc], (float)unew[2 * tc + 1]);   // MPPI_FLAG_DYNAMICS_F1
-                else arm_step<0>(st, cfg.arm, (float)unew[2 * tc], (float)unew[2 * tc + 1]);
-                float4* o = (float4*)(tr + 8 * t);
-                o[0] = make_float4(st.q1, st.q2, st.d1, st.d2);
-                o[1] = make_float4(st.kq1, st.kq2, st.kd1, st.kd2);
-            }
-        }
-        __syncthreads();
-        double* o = io.opt_traj + (size_t)e * 4 * T;
-        for (int c = tid; c < 4 * T; c += blockDim.x) {
-            const int t = c >> 2, k = c & 3;
-            out_store(io, o + c, (double)tr[8 * t + k] - (double)tr[8 * t + 4 + k]);
-        }
-    } else {
-        for (int c = tid; c < 4 * T; c += blockDim.x) out_store(io, io.opt_traj + (size_t)e * 4 * T + c, 0.0);
-    }
+mppi_finalize_sm100a(DevCfg cfg, DevIo io, const double* gathered, int world, PeerExchange px) {
+    __shared__ FinalizeSmem sm;
+    finalize_env(cfg, io, blockIdx.x, gathered, world, px, sm);
 }
 
 // ================================================================================================
@@ -1164,7 +1228,7 @@ mppi_plant_sm100a(DevCfg cfg, DevIo io, const char* __restrict__ step_blocks, Lo
             row[6] = (double)io.new_idx[e]; row[7] = io.rho[e];
         }
         if (e == 0) {
-            *const_cast<uint64_t*>(io.step) += 1;                // next tick draws fresh Philox noise
+            if (!(cfg.flags & 128)) *const_cast<uint64_t*>(io.step) += 1;   // next tick draws fresh Philox noise (resident state: prepare does it)
             lp_ptr->tick = lp.tick + 1;
         }
     }

@@ -49,7 +49,7 @@ class MppiEngine:
                  n_env=1, seed=0, device=None, optimal_traj=True, use_graph=True, smoother="median",
                  shard: ShardSpec | None = None, process_group=None, max_ref_rows=None, exchange="nccl",
                  search="certified", search_stats=False, dynamics="F", joint_limit_lo=None, joint_limit_hi=None,
-                 joint_limit_weight=0.0):
+                 joint_limit_weight=0.0, resident_state=False, exchange_timeout_ms=None):
         import torch
         self.torch = torch
         self.lib = _cabi.load()
@@ -89,7 +89,11 @@ class MppiEngine:
                      | {"median": 0, "average": _cabi.FLAG_SMOOTH_AVERAGE, "none": _cabi.FLAG_SMOOTH_NONE}[smoother]
                      | (_cabi.FLAG_FULL_SEARCH if search == "full" else 0)
                      | (_cabi.FLAG_SEARCH_STATS if search_stats else 0)
-                     | (_cabi.FLAG_DYNAMICS_F1 if dynamics == "F1" else 0))
+                     | (_cabi.FLAG_DYNAMICS_F1 if dynamics == "F1" else 0)
+                     | (_cabi.FLAG_RESIDENT_STATE if resident_state else 0))
+        self.resident_state = bool(resident_state)
+        if self.resident_state and self.shard.world != 1:
+            raise ValueError("resident_state keeps the whole controller state on one GPU (unsharded handles only)")
         cfg.max_ref_rows = int(max_ref_rows or ref.shape[0])
         cfg.delta_t, cfg.param_lambda, cfg.param_gamma = float(delta_t), float(param_lambda), float(param_gamma)
         cfg.sigma_chol[:] = chol.reshape(-1).tolist()
@@ -136,8 +140,10 @@ class MppiEngine:
         self.in_prev_idx = view(lay.off_prev_idx, np.int32, (E,))
         self.in_step = view(lay.off_step, np.uint64, (1,))
         self.out_new_idx = view(lay.off_new_idx, np.int32, (E,))
+        self.out_status = view(lay.off_status, np.int32, (E,))
         self.out_rho = view(lay.off_rho, np.float64, (E,))
         self.out_eta = view(lay.off_eta, np.float64, (E,))
+        self.out_u0 = view(lay.off_u0, np.float64, (E, 2))
         self.out_w_eps_raw = view(lay.off_w_eps_raw, np.float64, (E, T, 2))
         self.out_w_eps_filt = view(lay.off_w_eps_filt, np.float64, (E, T, 2))
         self.out_u_new = view(lay.off_u_new, np.float64, (E, T, 2))
@@ -156,6 +162,9 @@ class MppiEngine:
         self.set_ref_path(ref)
         if self.exchange == "p2p":
             self._setup_peer_exchange()
+            if exchange_timeout_ms is not None:
+                _cabi.check(self.lib.mppi_set_exchange_timeout(self.handle, float(exchange_timeout_ms)), self.handle,
+                            "mppi_set_exchange_timeout")
 
     def _setup_peer_exchange(self):
         """Map one exchange buffer per rank into every rank's address space (torch symmetric memory over
@@ -240,6 +249,29 @@ class MppiEngine:
         """One MPPI step.  Results are then readable from the ``out_*`` views (valid until the next
         step).  ``eps`` = None draws Philox noise in-kernel; otherwise it is injected."""
         self.write_inputs(x0, u_prev, prev_idx)
+        if self.resident_state:
+            self.upload_state()
+        self.launch(eps)
+        self.wait()
+        if self.resident_state:
+            self.download_state()
+
+    # ---- resident controller state (many environments: only x0 in, compact results out) ----------------
+    def upload_state(self):
+        """Push in_x0 / in_u_prev / in_prev_idx and the step counter to the device (resident_state engines: once
+        before the first step and after every host-side change of the controller state)."""
+        self.in_step[0] = self.step_counter
+        _cabi.check(self.lib.mppi_upload_state(self.handle, self.stream.cuda_stream), self.handle, "mppi_upload_state")
+
+    def download_state(self):
+        """Fetch the device's controller state (in_u_prev, in_prev_idx) and the full outputs of the last step."""
+        _cabi.check(self.lib.mppi_download_state(self.handle, self.stream.cuda_stream), self.handle, "mppi_download_state")
+        _cabi.check(self.lib.mppi_wait(self.handle), self.handle, "mppi_wait")
+
+    def step_resident(self, x0, eps=None):
+        """One step of a resident_state engine: only the observed states go in; afterwards out_new_idx, out_status,
+        out_rho, out_eta and out_u0 are valid (everything else stays on the device until download_state())."""
+        self.in_x0[...] = np.asarray(x0, dtype=np.float64).reshape(self.n_env, 4)
         self.launch(eps)
         self.wait()
 
@@ -313,8 +345,10 @@ class MppiEngine:
 
     def wait(self):
         _cabi.check(self.lib.mppi_wait(self.handle), self.handle, "mppi_wait")
-        if self.exchange == "p2p" and self.lib.mppi_exchange_status(self.handle) != 0:
-            raise RuntimeError("peer exchange timed out: a rank did not deliver its partial within ~3 s")
+        if self.exchange == "p2p" and self.out_status.any():
+            # the step skipped its update (u_new = u_prev) instead of combining a stale partial; the next step is clean
+            raise RuntimeError("peer exchange timed out: a rank did not deliver its partial in time; this step's "
+                               "update was skipped (u_new == u_prev)")
 
     def closed_loop(self, x0, u_prev, prev_idx, n_steps, plant_dt):
         """n_steps ticks of the run.py loop entirely on the device (Philox noise, FP64 plant).
@@ -332,7 +366,8 @@ class MppiEngine:
                                               stop.data_ptr(), self.stream.cuda_stream), self.handle, "mppi_closed_loop")
         self.last_mode, self.last_eps_ptr = _cabi.NOISE_PHILOX, None
         self.wait()
-        self.step_counter = int(self.in_step[0])
+        # (a resident engine's device counter holds the step last used, the host-driven one the next step)
+        self.step_counter = int(self.in_step[0]) + (1 if self.resident_state else 0)
         with torch.cuda.stream(self.stream):
             out = log.cpu().numpy(), stop.cpu().numpy()
         return out

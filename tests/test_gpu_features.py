@@ -189,7 +189,8 @@ def test_batched_environments_equal_independent_controllers(paths):
     rows = [0, 300, 900, 1500, 1975]
     X = np.array([[traj1[r, 0], traj1[r, 1], 0.05 * i, -0.03 * i] for i, r in enumerate(rows)])
     kw = cases.run_py_kwargs(ref, K, T)
-    bat = BatchedMPPIController(B, **{k: v for k, v in kw.items()}, visualize_optimal_traj=True, seed=5)
+    bat = BatchedMPPIController(B, **{k: v for k, v in kw.items()}, visualize_optimal_traj=True, seed=5,
+                                return_sequences=True)
     bat.prev_waypoints_idx = np.array(rows)
     eps = np.stack([mo.injected_noise(50 + b, K, T, kw["sigma"]) for b in range(B)])
     u0, useq, opt = bat.calc_control_input(X, eps=eps)
@@ -207,6 +208,56 @@ def test_batched_environments_equal_independent_controllers(paths):
     e = bat.engine.philox_noise(step=1).cpu().numpy()
     assert abs(np.corrcoef(e[0, ..., 0].ravel(), e[1, ..., 0].ravel())[0, 1]) < 0.03
     bat.close()
+
+
+def test_resident_controller_state_equals_host_driven_steps(paths):
+    """BatchedMPPIController keeps sequences, waypoint indices and the step counter on the device
+    (MPPI_FLAG_RESIDENT_STATE: only x0 in, (new_idx, u0) out per step).  Six steps, one environment reaching the end
+    of its path on the way (it must freeze, control.py:76-78): controls, indices and the fetched sequences are
+    the very floats of an engine whose state is shifted on the host (control.py:126, 148-149) every step —
+    also for a block too large for zero-copy (320 environments: DMA path, compact read-back)."""
+    from mppi_robotarm_b200.batched import BatchedMPPIController
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    traj1 = paths["trajectory1"]
+    for B, K, T in ((4, 256, 16), (320, 64, 24)):
+        rows = np.array(([0, 400, 1000, 1990] * (B // 4))[:B])
+        X = np.array([[traj1[r, 0], traj1[r, 1], 0.0, 0.0] for r in rows])
+        kw = cases.run_py_kwargs(ref, K, T)
+        bat = BatchedMPPIController(B, **kw, seed=21, visualize_optimal_traj=True)
+        bat.prev_waypoints_idx = rows
+        eng = _engine(paths, K, T, n_env=B, seed=21)
+        assert (eng.layout.bytes > 65536) == (B == 320)
+        u = np.tile([10.0, -2.0], (B, T, 1))
+        p = rows.astype(np.int64).copy()
+        finished = np.zeros(B, bool)
+        for step in range(6):
+            x = X + 0.001 * step
+            u0, useq, opt = bat.calc_control_input(x)
+            assert useq is None and opt is None
+            eng.step(x, u, p, None)
+            p = eng.out_new_idx.astype(np.int64)
+            ended = p >= ref.shape[0] - 1
+            live = ~ended
+            finished |= ended
+            u_ret = u[:, 0].copy()
+            u[live] = eng.out_u_new[live]
+            u[live, :-1] = u[live, 1:]
+            u_ret[live] = u[live, 0]
+            np.testing.assert_array_equal(bat.last_waypoint_idx(), p)
+            np.testing.assert_array_equal(u0, u_ret)
+            np.testing.assert_array_equal(bat.finished, finished)
+            if step in (2, 5):                      # reading the attribute fetches the device's sequences
+                np.testing.assert_array_equal(bat.u_prev, u)
+                np.testing.assert_array_equal(bat.prev_waypoints_idx, p)
+                np.testing.assert_array_equal(bat.engine.out_opt_traj, eng.out_opt_traj)
+        assert finished.any() and not finished.all()
+        # a host-side change of the state is pushed before the next step
+        bat.u_prev[...] = 0.5 * u
+        u0, _, _ = bat.calc_control_input(X)
+        eng.step(X, 0.5 * u, p, None)
+        live = eng.out_new_idx < ref.shape[0] - 1
+        np.testing.assert_array_equal(u0[live], eng.out_u_new[live, 1])
+        bat.close(); eng.close()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -503,7 +554,7 @@ def test_batched_device_closed_loop_equals_single_environment_loops(paths):
         if t < 20:
             np.testing.assert_allclose(log[t, :, 0:4], X, rtol=0, atol=1e-9)
             np.testing.assert_allclose(log[t, :, 4:6], u0, rtol=0, atol=1e-7)
-            np.testing.assert_array_equal(log[t, :, 6].astype(np.int64), host.prev_waypoints_idx)
+            np.testing.assert_array_equal(log[t, :, 6].astype(np.int64), host.last_waypoint_idx())
     assert np.max(np.abs(log[-1, :, 0:4] - X)) <= 0.3
     np.testing.assert_array_equal(dev.prev_waypoints_idx >= np.array(rows), True)
     dev.close(); host.close()
@@ -574,6 +625,7 @@ def test_certified_search_batched_environments(paths):
         b.u_prev[...] = np.array(us)
         b.prev_waypoints_idx[...] = ps
         b.calc_control_input(np.array(xs))
+        b.engine.download_state()          # (the sequences stay on the device unless asked for)
         res[mode] = (b.engine.last_costs()[0].cpu().numpy().copy(), b.engine.out_u_new.copy(), b.engine.search_stats())
         b.close()
     assert np.array_equal(res["certified"][0], res["full"][0])

@@ -254,3 +254,89 @@ def test_grid_stride_path_with_more_samples_than_the_grid_covers(paths):
     S64 = mo.rollout_costs(mo.OracleMPPI(**kw), np.array(cases.X0), eps_tail, prev_idx=int(eng.out_new_idx[0]))
     assert H.rel_err(S[-2000:].cpu().numpy().astype(np.float64), S64) <= TOL_S
     eng.close()
+
+
+def test_joint_limit_cost_against_the_oracle(paths):
+    """north_star item 1 names a joint-limit cost; the reference has none (its clamps are commented out,
+    control.py:166-172), so it is an extension with default weight 0.  Non-zero weight: costs and update
+    against the FP64 oracle carrying the same term, for both noise sources and both samples-per-thread
+    kernels.  Weight 0, or limits that are never reached: the very same floats as without the option."""
+    from control import MPPIControllerForPathTracking
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    lim = dict(joint_limit_lo=(1.10, -1.30), joint_limit_hi=(1.20, -1.20), joint_limit_weight=3.0)
+    for K, T in ((2048, 30), (300000, 10)):
+        kw = cases.run_py_kwargs(ref, K, T, visualize_optimal_traj=False)
+        eps = mo.injected_noise(9, K, T, kw["sigma"])
+        c = mo.OracleMPPI(**kw, **lim)
+        o = mo.step_vectorized(c, cases.X0, eps.astype(np.float64))
+        ctrl = MPPIControllerForPathTracking(**kw, noise="numpy", verbose=False, **lim)
+        H.inject(ctrl, eps)
+        H.quiet_step(ctrl, cases.X0)
+        eng = ctrl._engine()
+        S = eng.last_costs()[0][0].cpu().numpy().astype(np.float64)
+        assert H.rel_err(S, o["S"]) <= TOL_S, (K, T)
+        assert H.rel_err(eng.out_u_new[0], o["u_new"]) <= TOL_U, (K, T)
+        plain = mo.rollout_costs(mo.OracleMPPI(**kw), np.array(cases.X0), eps.astype(np.float64), prev_idx=0)
+        assert np.mean(o["S"] > plain * (1 + 1e-6)) > 0.5          # the term really is in play
+        ctrl.close()
+    # Philox noise source with the term: equals the injected-noise kernels on the exported draw
+    K, T = 4096, 40
+    kw = cases.run_py_kwargs(ref, K, T, visualize_optimal_traj=False)
+    a = MPPIControllerForPathTracking(**kw, noise="philox", seed=3, verbose=False, **lim)
+    ea = a._engine()
+    eps = ea.philox_noise(step=0)
+    ea.step(cases.X0, a.u_prev, 0, None)
+    b = MPPIControllerForPathTracking(**kw, noise="philox", seed=3, verbose=False, **lim)
+    eb = b._engine()
+    eb.step(cases.X0, b.u_prev, 0, eps)
+    assert bool((ea.last_costs()[0] == eb.last_costs()[0]).all())
+    # switched off / never reached: bit-identical to a controller built without the option
+    base = MPPIControllerForPathTracking(**kw, noise="philox", seed=3, verbose=False)
+    e0 = base._engine()
+    e0.step(cases.X0, base.u_prev, 0, None)
+    for off in (dict(joint_limit_lo=(1.1, -1.3), joint_limit_hi=(1.2, -1.2), joint_limit_weight=0.0),
+                dict(joint_limit_lo=(-50, -50), joint_limit_hi=(50, 50), joint_limit_weight=3.0),
+                dict(joint_limit_weight=3.0)):
+        cc = MPPIControllerForPathTracking(**kw, noise="philox", seed=3, verbose=False, **off)
+        ec = cc._engine()
+        ec.step(cases.X0, cc.u_prev, 0, None)
+        assert bool((ec.last_costs()[0] == e0.last_costs()[0]).all()), off
+        np.testing.assert_array_equal(ec.out_u_new, e0.out_u_new)
+        cc.close()
+    assert not bool((ea.last_costs()[0] == e0.last_costs()[0]).all())
+    a.close(); b.close(); base.close()
+
+
+@pytest.mark.parametrize("tick", [100, 500, 1000])
+def test_bench_state_against_the_oracle_on_a_sample_subset(paths, tick):
+    """The state bench.py times (K = 2^20, T = 100, Philox, a tick of the reference's own closed loop: most
+    lookups are answered by the certified end tests and triples there): 3000 random samples of the exported
+    in-kernel noise are rolled out by the FP64 oracle and compared with the kernel's costs."""
+    import torch
+    from control import MPPIControllerForPathTracking
+    with np.load(cases.HERE + "/closed_loop_c1.npz") as z:
+        cl = {k: z[k] for k in z.files}
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    K, T = 1 << 20, 100
+    prev = cl["u_new"][tick - 1]
+    u = np.concatenate([prev[1:], np.repeat(prev[-1:], T - prev.shape[0] + 1, axis=0)], axis=0)[:T]
+    x0, p0 = cl["state"][tick], int(cl["prev_idx"][tick, 0])
+    kw = cases.run_py_kwargs(ref, K, T, visualize_optimal_traj=False)
+    ctrl = MPPIControllerForPathTracking(**kw, noise="philox", seed=1234, verbose=False, search_stats=True)
+    eng = ctrl._engine()
+    eng.step(x0, u, p0, None)
+    st = eng.search_stats()
+    S = eng.last_costs()[0][0]
+    idx = np.sort(np.random.default_rng(tick).choice(K, 3000, replace=False))
+    eps = eng.philox_noise(step=0)[0][torch.from_numpy(idx).to(S.device)].cpu().numpy().astype(np.float64)
+    c = mo.OracleMPPI(**cases.run_py_kwargs(ref, 3000, T))
+    p1 = int(eng.out_new_idx[0])
+    assert p1 == int(cl["prev_idx"][tick, 1])
+    S64 = mo.rollout_costs(c, x0, eps, prev_idx=p1, u=u)
+    S32 = S[torch.from_numpy(idx).to(S.device)].cpu().numpy().astype(np.float64)
+    err = np.abs(S32 - S64) / np.max(S64)
+    flips = int((err > TOL_S).sum())
+    print(f"tick {tick}: max rel err {err.max():.2e}, near-tie flips {flips}, lookups {st}")
+    assert flips <= 3000 // 64 and err.max() <= 20 * TOL_S, (tick, np.sort(err)[-3:])
+    assert st["searched_fraction"] < 0.01 and st["fraction"] > 0.8, st
+    ctrl.close()

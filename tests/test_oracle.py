@@ -134,3 +134,28 @@ def test_exploit_count_matches_python_comparison():
     for K in (1, 7, 50, 64, 100, 4096):
         for ex in (0.0, 0.25, 0.33, 0.5, 0.999, 1.0):
             assert mo.exploit_count(K, ex) == sum(1 for k in range(K) if k < (1.0 - ex) * K)
+
+
+def test_joint_limit_cost_python_and_c_oracle_agree(paths):
+    """The joint-limit stage cost is an extension (weight 0 = the reference): both restatements define it
+    the same way, it vanishes inside the limits, and it grows quadratically with the violation."""
+    from oracle import c_oracle
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    K, T = 256, 30
+    kw = cases.run_py_kwargs(ref, K, T)
+    eps = mo.injected_noise(5, K, T, kw["sigma"]).astype(np.float64)
+    base = mo.rollout_costs(mo.OracleMPPI(**kw), np.array(cases.X0), eps, prev_idx=0)
+    lim = dict(joint_limit_lo=(1.10, -1.30), joint_limit_hi=(1.20, -1.20), joint_limit_weight=3.0)
+    c = mo.OracleMPPI(**kw, **lim)
+    S_py = mo.rollout_costs(c, np.array(cases.X0), eps, prev_idx=0)
+    S_c = c_oracle.rollout_costs(c, np.array(cases.X0), eps, 0)
+    np.testing.assert_allclose(S_c, S_py, rtol=1e-12)
+    assert np.all(S_py >= base) and np.mean(S_py > base * (1 + 1e-9)) > 0.9      # these arms fall out of the 0.1 rad box
+    wide = mo.OracleMPPI(**kw, joint_limit_lo=(-50, -50), joint_limit_hi=(50, 50), joint_limit_weight=3.0)
+    np.testing.assert_array_equal(mo.rollout_costs(wide, np.array(cases.X0), eps, prev_idx=0), base)
+    assert mo.joint_limit_cost(1.5, 0.0, (0, -1), (1, 1), 2.0) == 2.0 * 0.25 * 1e4
+    assert mo.joint_limit_cost(-0.5, 2.0, (0, -1), (1, 1), 2.0) == 2.0 * (0.25 + 1.0) * 1e4
+    # the step as a whole carries the term too (loops and vectorised forms agree)
+    a = mo.step_loops(mo.OracleMPPI(**cases.run_py_kwargs(ref, 24, 8), **lim), cases.X0, eps[:24, :8])
+    b = mo.step_vectorized(mo.OracleMPPI(**cases.run_py_kwargs(ref, 24, 8), **lim), cases.X0, eps[:24, :8])
+    np.testing.assert_allclose(a["S"], b["S"], rtol=1e-12)

@@ -53,6 +53,28 @@ def circle_joint_reference(n: int = 3000, snap: bool = True, turn: float = 1.0) 
     return np.stack([q1, q2, xe, ye], axis=1)
 
 
+def computed_torque(q, dq, v, params: dict | None = None) -> np.ndarray:
+    """u = M(q) v + C(q, dq) dq + G(q): the feedback-linearising torque of utils.py:65-84."""
+    p = params or SYS_PARAMS()
+    m1, m2, l1, l2, lc1, lc2, g = (p[k] for k in ("m1", "m2", "l1", "l2", "lc1", "lc2", "g"))
+    q, dq, v = (np.asarray(a, dtype=np.float64) for a in (q, dq, v))
+    c2, s2 = np.cos(q[1]), np.sin(q[1])
+    m12 = m2 * l1 * lc2 * c2 + m2 * lc2 ** 2 + l2
+    M = np.array([[m1 * lc1 ** 2 + l1 + m2 * (l1 ** 2 + lc2 ** 2 + 2 * l1 * lc2 * c2) + l2, m12],
+                  [m12, m2 * lc2 ** 2 + l2]])
+    h = m2 * l1 * lc2 * s2
+    C = np.array([[-h * dq[1], -h * dq[0] - h * dq[1]], [h * dq[0], 0.0]])
+    G = np.array([m1 * lc1 * g * np.cos(q[0]) + m2 * g * (lc2 * np.cos(q[0] + q[1]) + l1 * np.cos(q[0])),
+                  m2 * lc2 * g * np.cos(q[0] + q[1])])
+    return M @ v + C @ dq + G
+
+
+def pd_outer_loop(q, dq, r, dr, ddr, kp: float = 100.0, kd: float = 20.0) -> np.ndarray:
+    """v = ddr - kd (dq - dr) - kp (q - r) (utils.py:87-93)."""
+    q, dq, r, dr, ddr = (np.asarray(a, dtype=np.float64) for a in (q, dq, r, dr, ddr))
+    return ddr - kd * (dq - dr) - kp * (q - r)
+
+
 def record_tracking_run(n: int = 2000, Ts: float = 0.0025, kp: float = 100.0, kd: float = 20.0,
                         params: dict | None = None) -> np.ndarray:
     """[n, 6] rows (x, y, dq1, dq2, u1, u2): the arm tracks the circle under the reference's computed-torque
@@ -60,7 +82,7 @@ def record_tracking_run(n: int = 2000, Ts: float = 0.0025, kp: float = 100.0, kd
     integrated with the semi-implicit Euler step of run.py:53-55 at Ts."""
     from utils import Arm_Dynamic          # this repo's plant twin (FP64)
     p = params or SYS_PARAMS()
-    m1, m2, l1, l2, lc1, lc2, g = (p[k] for k in ("m1", "m2", "l1", "l2", "lc1", "lc2", "g"))
+    l1, l2 = p["l1"], p["l2"]
     # the recorded file covers theta in [0, 6.2546]: a smooth circle, no snap zone
     tgt = circle_joint_reference(n + 2, snap=False, turn=0.9955)[:, 0:2]
     r = tgt[:n]
@@ -69,16 +91,7 @@ def record_tracking_run(n: int = 2000, Ts: float = 0.0025, kp: float = 100.0, kd
     q, dq = r[0].copy(), np.zeros(2)
     out = np.zeros((n, 6))
     for k in range(n):
-        v = ddr[k] - kd * (dq - dr[k]) - kp * (q - r[k])
-        c2, s2 = np.cos(q[1]), np.sin(q[1])
-        M = np.array([[m1 * lc1 ** 2 + l1 + m2 * (l1 ** 2 + lc2 ** 2 + 2 * l1 * lc2 * c2) + l2,
-                       m2 * l1 * lc2 * c2 + m2 * lc2 ** 2 + l2],
-                      [m2 * l1 * lc2 * c2 + m2 * lc2 ** 2 + l2, m2 * lc2 ** 2 + l2]])
-        h = m2 * l1 * lc2 * s2
-        C = np.array([[-h * dq[1], -h * dq[0] - h * dq[1]], [h * dq[0], 0.0]])
-        G = np.array([m1 * lc1 * g * np.cos(q[0]) + m2 * g * (lc2 * np.cos(q[0] + q[1]) + l1 * np.cos(q[0])),
-                      m2 * lc2 * g * np.cos(q[0] + q[1])])
-        u = M @ v + C @ dq + G
+        u = computed_torque(q, dq, pd_outer_loop(q, dq, r[k], dr[k], ddr[k], kp, kd), p)
         dq = dq + Ts * Arm_Dynamic(q, dq, u)
         q = q + Ts * dq
         out[k] = (l1 * np.cos(q[0]) + l2 * np.cos(q[0] + q[1]), l1 * np.sin(q[0]) + l2 * np.sin(q[0] + q[1]),

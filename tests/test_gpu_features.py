@@ -359,6 +359,54 @@ def _run_py_controller(ref, **extra):
         visualze_sampled_trajs=True, verbose=False, **extra)
 
 
+def test_reference_run_py_runs_unchanged_on_the_gpu(tmp_path, monkeypatch, capsys):
+    """The reference's own run.py, byte for byte (staged by oracle/make_ref.py; skipped where no copy exists),
+    executed with THIS repository's control.py / utils.py / sys_params.py on the path, the exported data file in
+    the working directory and matplotlib stubbed: 50 ticks of its loop (run.py:48-59) on the GPU."""
+    import os
+    import runpy
+    import sys
+    from oracle import make_ref, ref_harness as rh
+    src = make_ref.staged_dir()
+    if src is None:
+        pytest.skip("no staged copy of the reference (oracle/_ref/) on this machine")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import export_ref_paths
+    export_ref_paths.export(str(tmp_path))
+    monkeypatch.chdir(tmp_path)
+    rh._install_stubs()
+    for name in ("control", "utils", "sys_params"):
+        monkeypatch.delitem(sys.modules, name, raising=False)
+    monkeypatch.syspath_prepend(root)
+    import control
+
+    class _Enough(Exception):
+        pass
+    seen = {"ticks": 0, "ctrl": None, "u": []}
+    real = control.MPPIControllerForPathTracking.calc_control_input
+
+    def counted(self, observed_x):
+        if seen["ticks"] == 50:
+            raise _Enough
+        out = real(self, observed_x)
+        seen["ticks"] += 1
+        seen["ctrl"] = self
+        seen["u"].append(np.array(out[0], copy=True))
+        assert out[3].shape == (100, 30, 4)                   # run.py asks for the sampled trajectories
+        return out
+    monkeypatch.setattr(control.MPPIControllerForPathTracking, "calc_control_input", counted)
+    with pytest.raises(_Enough):
+        runpy.run_path(os.path.join(src, "run.py"), run_name="__main__")
+    text = capsys.readouterr().out
+    c = seen["ctrl"]
+    assert seen["ticks"] == 50 and type(c).__module__ == "mppi_robotarm_b200.controller"
+    assert (c.K, c.T, c.visualze_sampled_trajs) == (100, 30, True)
+    assert "50     state = " in text and "======================updated=======================" in text
+    assert np.all(np.isfinite(seen["u"])) and 0 < c.prev_waypoints_idx < 200
+    c.close()
+
+
 def test_free_running_same_noise_follows_the_reference_run(paths):
     """Same seeded noise as the reference's recorded 1500-step run, free running (errors feed back).
     Stated bound (closed loop is chaotic w.r.t. rounding even in FP64): joints within

@@ -107,3 +107,34 @@ def test_reference_run_py_drives_our_control_module_unchanged(tmp_path, monkeypa
         runpy.run_path(os.path.join(rh.REFERENCE_DIR, "run.py"), run_name="__main__")
     import control
     assert control.MPPIControllerForPathTracking.__module__ == "mppi_robotarm_b200.controller"
+
+
+def test_exported_data_files_are_byte_identical(tmp_path):
+    """tools/export_ref_paths.py (run by build()) writes the four .txt files a fresh checkout needs for
+    `np.loadtxt('xydq_circle.txt')` (run.py:18): the same bytes as the reference's own files."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import export_ref_paths
+    for path in export_ref_paths.export(str(tmp_path)):
+        with open(path, "rb") as a, open(os.path.join(rh.REFERENCE_DIR, os.path.basename(path)), "rb") as b:
+            assert a.read() == b.read(), path
+
+
+def test_remaining_utils_helpers_match_the_reference():
+    """`from utils import *` (run.py:5) also brings Inverse_Kinemetic, Feedback_linearization and Controller
+    (utils.py:41-93; never called by run.py): same names, arguments and values here."""
+    import utils
+    _, ref_utils = rh.import_reference()
+    rng = np.random.default_rng(3)
+    for th in list(rng.uniform(0, 6.0, 20)) + [6.1, 6.2, 6.3, 6.48, 6.6, 7.0]:
+        a, b = utils.Inverse_Kinemetic(th), ref_utils.Inverse_Kinemetic(th)
+        np.testing.assert_allclose(a[0], b[0], rtol=0, atol=1e-13)
+        assert a[1] == b[1] and a[2] == b[2]
+    for _ in range(20):
+        q, dq, v, r, dr = (rng.normal(0, 1, 2) for _ in range(5))
+        np.testing.assert_allclose(utils.Feedback_linearization(q, dq, v), ref_utils.Feedback_linearization(q, dq, v),
+                                   rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(utils.Controller(q, dq, r, dr, v), ref_utils.Controller(q, dq, r, dr, v),
+                                   rtol=1e-13, atol=1e-13)

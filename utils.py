@@ -30,3 +30,25 @@ def Forward_Kinemetic(q):
     l1, l2 = _P["l1"], _P["l2"]
     x1, y1 = l1 * np.cos(q[0]), l1 * np.sin(q[0])
     return x1, y1, x1 + l2 * np.cos(q[0] + q[1]), y1 + l2 * np.sin(q[0] + q[1])
+
+
+# The three helpers run.py pulls in with `from utils import *` but never calls (utils.py:41-93): the producers of
+# the reference's data files.  Same names, arguments and return values; the arithmetic lives in refgen.py.
+def Inverse_Kinemetic(Theta):
+    """(r, XE, YE): joint target r = [q1, q2] reaching the circle point of angle Theta (utils.py:41-62)."""
+    from mppi_robotarm_b200 import refgen
+    xe, ye = refgen.circle_point(Theta)
+    q1, q2 = refgen.inverse_kinematics(xe, ye)
+    return np.array([float(q1), float(q2)]), float(xe), float(ye)
+
+
+def Feedback_linearization(q, dq, v):
+    """Computed-torque input u = M(q) v + C(q, dq) dq + G(q) (utils.py:65-84)."""
+    from mppi_robotarm_b200 import refgen
+    return refgen.computed_torque(q, dq, v, _P)
+
+
+def Controller(q, dq, r, dr, ddr):
+    """PD outer loop v = ddr - 20 (dq - dr) - 100 (q - r) (utils.py:87-93)."""
+    from mppi_robotarm_b200 import refgen
+    return refgen.pd_outer_loop(q, dq, r, dr, ddr)

@@ -43,13 +43,14 @@ class MPPIControllerForPathTracking:
             visualze_sampled_trajs=False,
             *,
             noise: str = "philox",      # "philox": in-kernel draw; "numpy": self._calc_epsilon() injected
-            seed=None,                  # Philox key; None -> drawn once from numpy's global RNG
+            seed=None,                  # Philox key; None -> drawn once from OS entropy (rank 0's draw in sharded runs)
             device=None,                # CUDA device (default: current)
             verbose: bool = True,       # print the reference's three lines per step (control.py:227-229)
             use_graph: bool = True,     # replay the step as a CUDA graph
             distributed: bool = False,  # shard the K samples over torch.distributed ranks
             process_group=None,
-            exchange: str = "nccl",     # sharded runs: "nccl" all-gather or "p2p" (fused peer-memory exchange)
+            exchange: str = "auto",     # sharded runs: "p2p" (exchange fused into the kernels, NVLink peer memory),
+                                        #  "nccl" (all-gather) or "auto" = p2p where the peer mapping works, else nccl
             sampled_traj_top_n=None,    # with visualze_sampled_trajs: return only the n best, best first
             smoother: str = "median",  # "median" (control.py:122), "average" (control.py:329-344) or "none"
             dynamics: str = "F",        # rollout model: "F" (control.py:234-263) or "F1" (control.py:265-295)
@@ -83,7 +84,9 @@ class MPPIControllerForPathTracking:
         if noise not in ("philox", "numpy"):
             raise ValueError("noise must be 'philox' or 'numpy'")
         self.noise = noise
-        self.seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
+        # (a private generator: the reference never touches numpy's global stream at construction)
+        self.seed = int(np.random.default_rng().integers(0, 2 ** 31 - 1)) if seed is None else int(seed)
+        self._seed_is_drawn = seed is None
         self.verbose = verbose
         self._device = device
         self._use_graph = use_graph
@@ -110,6 +113,16 @@ class MPPIControllerForPathTracking:
 
     def _engine(self) -> MppiEngine:
         if self._engine_obj is None:
+            if self._distributed and self._seed_is_drawn:
+                # every rank must key Philox on the SAME seed (samples are keyed on their global index, so the
+                # result does not depend on the sharding): take rank 0's draw
+                import torch
+                import torch.distributed as dist
+                dev = "cuda" if dist.get_backend(self._group) == "nccl" else "cpu"
+                t = torch.tensor([self.seed], dtype=torch.int64, device=dev)
+                dist.broadcast(t, src=dist.get_global_rank(self._group, 0) if self._group is not None else 0, group=self._group)
+                self.seed = int(t.item())
+                self._seed_is_drawn = False
             self._engine_obj = MppiEngine(
                 K=self.K, T=self.T, delta_t=self.delta_t, param_lambda=self.param_lambda,
                 param_gamma=self.param_gamma, sigma=self.Sigma, stage_cost_weight=self.stage_cost_weight,

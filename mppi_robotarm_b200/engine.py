@@ -29,6 +29,27 @@ class ShardSpec:
         return k_offset, K_local
 
 
+def noise_factor(sigma: np.ndarray) -> np.ndarray:
+    """Lower-triangular L with L L^T = Sigma for the in-kernel draw eps = L z.  The reference draws with
+    np.random.multivariate_normal (control.py:163), which accepts any symmetric positive SEMI-definite Sigma
+    (SVD factor) and only warns otherwise: a positive definite Sigma gets its Cholesky factor, a semi-definite
+    one a factor from the eigen-decomposition; an asymmetric or indefinite Sigma is an error here, because the
+    noise covariance would not be the Sigma whose inverse enters the control cost (control.py:106)."""
+    sigma = np.asarray(sigma, dtype=np.float64)
+    if not np.allclose(sigma, sigma.T, rtol=1e-12, atol=1e-12 * max(1.0, float(np.max(np.abs(sigma))))):
+        raise np.linalg.LinAlgError("Sigma must be symmetric (noise covariance and control-cost weight must agree)")
+    try:
+        return np.linalg.cholesky(sigma)
+    except np.linalg.LinAlgError:
+        w, v = np.linalg.eigh(sigma)
+        if w.min() < -1e-10 * max(1.0, w.max()):
+            raise
+        a = v * np.sqrt(np.clip(w, 0.0, None))              # A A^T = Sigma; make it lower triangular by QR
+        q, r = np.linalg.qr(a.T)
+        L = r.T
+        return L * np.sign(np.where(np.diag(L) == 0, 1.0, np.diag(L)))[None, :]
+
+
 def exploit_count(K: int, exploration: float) -> int:
     """#samples with ``k < (1 - param_exploration) * K`` — the Python float comparison of
     control.py:98 evaluated once on the host (an integer threshold on the global sample index)."""
@@ -47,7 +68,7 @@ class MppiEngine:
     def __init__(self, *, K, T, delta_t, param_lambda, param_gamma, sigma, stage_cost_weight,
                  terminal_cost_weight, arm_params, ref_path, param_exploration=0.0, cost_l1=1.0, cost_l2=1.0,
                  n_env=1, seed=0, device=None, optimal_traj=True, use_graph=True, smoother="median",
-                 shard: ShardSpec | None = None, process_group=None, max_ref_rows=None, exchange="nccl",
+                 shard: ShardSpec | None = None, process_group=None, max_ref_rows=None, exchange="auto",
                  search="certified", search_stats=False, dynamics="F", joint_limit_lo=None, joint_limit_hi=None,
                  joint_limit_weight=0.0, resident_state=False, exchange_timeout_ms=None):
         import torch
@@ -68,7 +89,7 @@ class MppiEngine:
         self.k_offset, self.K_local = k_offset, K_local
         sigma = np.asarray(sigma, dtype=np.float64)
         sig_inv = np.linalg.inv(sigma)                       # LinAlgError on a singular Sigma (control.py:106)
-        chol = np.linalg.cholesky(sigma)                     # LinAlgError unless symmetric positive definite
+        chol = noise_factor(sigma)                           # factor of the in-kernel draw (unused with injected noise)
         ref = np.ascontiguousarray(np.asarray(ref_path, dtype=np.float64)[:, 0:4])
         cfg = _cabi.MppiConfig()
         cfg.abi_version = _cabi.ABI_VERSION
@@ -156,15 +177,34 @@ class MppiEngine:
         self._dist_graph = None
         self.use_graph = bool(use_graph)
         self._symm = None
-        if exchange not in ("nccl", "p2p"):
-            raise ValueError("exchange must be 'nccl' or 'p2p'")
-        self.exchange = exchange if self.shard.world > 1 else "nccl"
+        if exchange not in ("auto", "nccl", "p2p"):
+            raise ValueError("exchange must be 'auto' (p2p where the peer mapping works, else nccl), 'nccl' or 'p2p'")
+        self.exchange = exchange if self.shard.world > 1 else "none"
         self.set_ref_path(ref)
-        if self.exchange == "p2p":
+        if self.exchange == "auto":
+            self.exchange = "p2p" if self._try_peer_exchange() else "nccl"
+        elif self.exchange == "p2p":
             self._setup_peer_exchange()
+        if self.exchange == "p2p":
             if exchange_timeout_ms is not None:
                 _cabi.check(self.lib.mppi_set_exchange_timeout(self.handle, float(exchange_timeout_ms)), self.handle,
                             "mppi_set_exchange_timeout")
+
+    def _try_peer_exchange(self) -> bool:
+        """exchange="auto": map the peer buffers if every rank can; all ranks take the same decision."""
+        torch = self.torch
+        import torch.distributed as dist
+        try:
+            self._setup_peer_exchange()
+            ok = 1
+        except Exception:                                   # noqa: BLE001 (no symmetric memory / no peer access)
+            ok = 0
+        flag = torch.tensor([ok], device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            self._symm = None
+            return False
+        return True
 
     def _setup_peer_exchange(self):
         """Map one exchange buffer per rank into every rank's address space (torch symmetric memory over

@@ -220,7 +220,7 @@ def test_resident_controller_state_equals_host_driven_steps(paths):
     ref = cases.ref_path_for(paths, "xydq_circle.txt")
     traj1 = paths["trajectory1"]
     for B, K, T in ((4, 256, 16), (320, 64, 24)):
-        rows = np.array(([0, 400, 1000, 1990] * (B // 4))[:B])
+        rows = np.array(([0, 400, 1000, 1999] * (B // 4))[:B])       # (1999: the last waypoint — that environment is at the end)
         X = np.array([[traj1[r, 0], traj1[r, 1], 0.0, 0.0] for r in rows])
         kw = cases.run_py_kwargs(ref, K, T)
         bat = BatchedMPPIController(B, **kw, seed=21, visualize_optimal_traj=True)

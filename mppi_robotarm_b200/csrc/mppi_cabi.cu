@@ -8,6 +8,7 @@
 #include <math.h>
 #include <new>
 #include <mutex>
+#include <nvtx3/nvToolsExt.h>        // header-only: ranges show up in Nsight Systems / ncu --nvtx, cost nothing otherwise
 
 #include "../../include/mppi_b200.h"
 #define MPPI_MAX_T_INTERNAL MPPI_MAX_T
@@ -21,6 +22,13 @@ constexpr int kNumTimers = 6;        // prepare, rollout, softmin, wsum, reduce,
 char g_create_error[512] = "";
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// NVTX range around the host-side enqueue of one stage of the step (the kernels of a graph replay inherit the
+// names of their nodes; these ranges name the stages of plain launches and of the capture)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct Workspace {
     size_t bytes;
@@ -67,6 +75,7 @@ struct MppiHandle {
     uint64_t capture_kernels;  // kernels enqueued while capture mode was on (= per replay)
     cudaEvent_t const_ev;      // recorded after this handle's last reader of the constant-bank window
     uint64_t step_scratch;     // source of the step-counter upload of a resident handle
+    bool pdl;                  // programmatic dependent launch of the rollout and weight-sum kernels
     char err[512];
 };
 
@@ -302,10 +311,14 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
             CU(h, cudaMemcpyAsync(ws + h->ws.off_in, h->host, h->in_bytes, cudaMemcpyHostToDevice, s));
     }
     if (timed) CU(h, cudaEventRecord(h->tev[0], s));
-    mppi_prepare_sm100a<<<dc.n_env, 32, 0, s>>>(dc, dio, ref, step_blocks, pull,
-                                                (unsigned long long*)(ws + h->ws.off_seq));
+    {
+        NvtxRange r("mppi.prepare");
+        mppi_prepare_sm100a<<<dc.n_env, 32, 0, s>>>(dc, dio, ref, step_blocks, pull,
+                                                    (unsigned long long*)(ws + h->ws.off_seq));
+    }
     if (timed) CU(h, cudaEventRecord(h->tev[1], s));
     {
+        NvtxRange r("mppi.rollout");
         dim3 grid(dc.g_roll, dc.n_env);
         const bool ph = noise_mode == MPPI_NOISE_PHILOX;
         if (h->const_window) {
@@ -322,9 +335,18 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
         const bool cert = certified_kernels(&h->cfg), jl = h->cfg.joint_limit_weight > 0.0;
         unsigned long long* stats = (unsigned long long*)(ws + h->ws.off_stats);
         const float* eps_arg = ph ? nullptr : eps_dev;
+        // Programmatic dependent launch: the rollout CTAs are scheduled while the prepare kernel still runs and wait
+        // (griddepcontrol.wait) just before they read the step block — the launch latency leaves the critical path.
+        // (Not with the constant-bank window: the copy node sits between the two kernels.)
+        cudaLaunchAttribute pdl_attr[1];
+        pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = grid; lc.blockDim = dim3(kRollThreads); lc.dynamicSmemBytes = h->roll_smem; lc.stream = s;
+        lc.attrs = pdl_attr; lc.numAttrs = (h->pdl && !h->const_window && !timed) ? 1 : 0;
 #define MPPI_ROLL(NOISE, CW, NS_, DYN, CERT) do { \
-        if (CERT && DYN == 0 && jl) mppi_rollout_sm100a<NOISE, false, NS_, 0, true, true><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, eps_arg, S, bmin, stats); \
-        else mppi_rollout_sm100a<NOISE, CW, NS_, DYN, CERT><<<grid, kRollThreads, h->roll_smem, s>>>(dc, step_ctr, step_blocks, eps_arg, S, bmin, stats); } while (0)
+        if (CERT && DYN == 0 && jl) CU(h, cudaLaunchKernelEx(&lc, mppi_rollout_sm100a<NOISE, false, NS_, 0, true, true>, dc, step_ctr, (const char*)step_blocks, eps_arg, S, bmin, stats)); \
+        else CU(h, cudaLaunchKernelEx(&lc, mppi_rollout_sm100a<NOISE, CW, NS_, DYN, CERT>, dc, step_ctr, (const char*)step_blocks, eps_arg, S, bmin, stats)); } while (0)
 #define MPPI_ROLL_NS(NOISE, CW, DYN, CERT) do { if (ns2) MPPI_ROLL(NOISE, CW, 2, DYN, CERT); else MPPI_ROLL(NOISE, CW, 1, DYN, CERT); } while (0)
 #define MPPI_ROLL_NOISE(CW, DYN, CERT) do { if (ph) MPPI_ROLL_NS(0, CW, DYN, CERT); else MPPI_ROLL_NS(1, CW, DYN, CERT); } while (0)
         if (f1) MPPI_ROLL_NOISE(false, 1, true);
@@ -337,6 +359,7 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
 #undef MPPI_ROLL
     }
     if (timed) CU(h, cudaEventRecord(h->tev[2], s));
+    NvtxRange r_w(use_px ? "mppi.weights+sum+exchange" : "mppi.weights+sum");
     if (noise_mode == MPPI_NOISE_PHILOX) {
         // fused: soft-min weights + weighted sum + this GPU's partial triple
         // 4096 samples per block for large K; small K is latency bound: up to 64 blocks of >= 512 samples
@@ -345,10 +368,15 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
         if (g < g_small) g = g_small;
         if (g > dc.g_wsum) g = dc.g_wsum;
         const size_t sm = (size_t)(kWsumThreads / 32) * ((dc.T + 1) / 2) * sizeof(float4);
-        mppi_softmin_wsum_philox_sm100a<<<dim3(g, dc.n_env), kWsumThreads, sm, s>>>(
-            dc, step_ctr, S, bmin, w, (double*)(ws + h->ws.off_eta_fused), v_part,
-            (unsigned int*)(ws + h->ws.off_tickets), rho, partial_dev, use_px ? h->px : PeerExchange{},
-            dio, o.fuse_finalize ? 1 : 0);
+        cudaLaunchAttribute pdl_attr[1];
+        pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(g, dc.n_env); lc.blockDim = dim3(kWsumThreads); lc.dynamicSmemBytes = sm; lc.stream = s;
+        lc.attrs = pdl_attr; lc.numAttrs = (h->pdl && !timed) ? 1 : 0;      // (timed: an event record sits in between)
+        CU(h, cudaLaunchKernelEx(&lc, mppi_softmin_wsum_philox_sm100a, dc, step_ctr, (const float*)S, (const float*)bmin, w,
+                                 (double*)(ws + h->ws.off_eta_fused), v_part, (unsigned int*)(ws + h->ws.off_tickets), rho,
+                                 partial_dev, use_px ? h->px : PeerExchange{}, dio, o.fuse_finalize ? 1 : 0));
         if (timed) { CU(h, cudaEventRecord(h->tev[3], s)); CU(h, cudaEventRecord(h->tev[4], s)); }
         h->launches += 3;
     } else {
@@ -373,6 +401,7 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
 int enqueue_combine(MppiHandle* h, const double* gathered_dev, int world, cudaStream_t s, const StepOpts& o) {
     const bool timed = o.timed, record_done = o.record_done && !o.capturing, copy_outputs = o.host_io, use_px = o.use_px;
     if (world < 1 || world > 64) return fail(h, MPPI_ERR_INVALID, "%s", "world must be in [1, 64]");
+    NvtxRange r("mppi.combine+update");
     if (!o.fuse_finalize) {      // (fused: the last block of the weight-sum kernel has done this already)
         mppi_finalize_sm100a<<<h->dc.n_env, 256, 0, s>>>(h->dc, copy_outputs ? h->dio : h->dio_dev, gathered_dev, world,
                                                          use_px ? h->px : PeerExchange{});
@@ -509,6 +538,7 @@ int mppi_create(const MppiConfig* c, void* workspace, size_t workspace_bytes, vo
             cudaGetLastError();
         }
     }
+    h->pdl = getenv("MPPI_NO_PDL") == nullptr;
     h->px.world = 0;
     h->px.timeout_ns = 3000000000ull;
     h->px.seq = (const unsigned long long*)(h->dev + h->ws.off_seq);

@@ -51,6 +51,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Programmatic dependent launch (PTX griddepcontrol): `wait` blocks until the kernel this one depends on has
+// completed and its memory is visible (a no-op for a normal launch); `launch_dependents` lets the next kernel's
+// CTAs be scheduled early (they still wait before touching our results).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -358,6 +364,7 @@ __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, 
                                                           char* __restrict__ step_blocks, int pull,
                                                           unsigned long long* __restrict__ seq) {
     __shared__ double srow[kWindowPad][2];        // local window rows for the certificate construction
+    pdl_launch_dependents();                      // the rollout CTAs may be scheduled now (they wait before reading)
     const int e = blockIdx.x, lane = threadIdx.x, T = cfg.T;
     if (e == 0 && lane == 0) *seq += 1ull;        // step sequence number, read by every later kernel of the step
     const bool zx = io.host_in != nullptr && (pull & 1), zc = io.host_in != nullptr && (pull & 2);
@@ -584,8 +591,10 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
     if (tid == 0) {
         mbar_init(&bar, 1);
         mbar_expect_tx(&bar, (uint32_t)cfg.step_block_bytes);
-        tma_load_1d(smem, step_blocks + (size_t)e * cfg.step_block_bytes, (uint32_t)cfg.step_block_bytes, &bar);
     }
+    pdl_wait();                                   // the prepare kernel's step block (and step counter) are complete
+    if (tid == 0)
+        tma_load_1d(smem, step_blocks + (size_t)e * cfg.step_block_bytes, (uint32_t)cfg.step_block_bytes, &bar);
     __syncthreads();
     mbar_wait(&bar, 0);
     const StepBlockView sb = view_step_block(smem);
@@ -963,6 +972,7 @@ mppi_softmin_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ct
     __shared__ bool is_last;
     const int e = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_pairs = (cfg.T + 1) >> 1;
+    pdl_wait();                                   // the rollout kernel's costs and block minima are complete
     // rho = min over the rollout kernel's block minima
     float m = INFINITY;
     for (int i = tid; i < cfg.g_roll; i += kWsumThreads) m = fminf(m, block_min[(size_t)e * cfg.g_roll + i]);

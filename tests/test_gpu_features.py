@@ -518,6 +518,43 @@ def test_device_closed_loop_equals_host_driven_loop(paths):
     dev.close(); host.close()
 
 
+def test_device_closed_loop_ticks_against_the_oracle_loop(paths):
+    """The ticks of the device-resident loop themselves against the FP64 oracle: the noise the kernels will
+    draw at ticks 0..24 is exported first, then the oracle controller (restated control.py:67-152) and the oracle
+    plant (utils.py:14-29, run.py:53-55) run the same 25 ticks on the CPU with that noise.  Applied controls
+    within the north_star bound (1e-4 relative) while the states still agree, joints within 1e-4 rad over the
+    25 ticks, waypoint indices equal."""
+    from control import MPPIControllerForPathTracking
+    ref = cases.ref_path_for(paths, "xydq_circle.txt")
+    K, T, n, dt = 512, 30, 25, 0.003
+    kw = cases.run_py_kwargs(ref, K, T)
+    dev = MPPIControllerForPathTracking(**kw, seed=77, verbose=False)
+    eng = dev._engine()
+    eps = [eng.philox_noise(step=t)[0].cpu().numpy().astype(np.float64) for t in range(n)]
+    # start from tick 200 of the reference's recorded run (a tracking state, not the rest at the path's first rows)
+    with np.load(cases.HERE + "/closed_loop_c1.npz") as z:
+        x0, p0, prev = z["state"][200].copy(), int(z["prev_idx"][200, 0]), z["u_new"][199].copy()
+    u_start = np.concatenate([prev[1:], prev[-1:]], axis=0)
+    dev.u_prev[...] = u_start
+    dev.prev_waypoints_idx = p0
+    out = dev.run_closed_loop(x0, n, dt)
+    c = mo.OracleMPPI(**kw)
+    c.u_prev = u_start.copy()
+    c.prev_waypoints_idx = p0
+    q, dq = x0[0:2].copy(), x0[2:4].copy()
+    worst_u = worst_q = 0.0
+    for t in range(n):
+        o = mo.step_vectorized(c, np.concatenate([q, dq]), eps[t])
+        u = o["u0"]                                        # the control run.py applies (post-shift, quirk Q2)
+        q, dq = mo.plant_step(q, dq, u, dt)
+        worst_u = max(worst_u, float(np.max(np.abs(out["u"][t] - u)) / np.max(np.abs(o["u_new"]))))
+        worst_q = max(worst_q, float(np.max(np.abs(out["state"][t, 0:2] - q))))
+        assert int(out["waypoint_idx"][t]) == o["prev_idx_after"], t
+    print(f"device loop vs oracle loop, {n} ticks: worst control error {worst_u:.2e} (relative), worst joint error {worst_q:.2e} rad")
+    assert worst_u <= 1e-4 and worst_q <= 1e-4, (worst_u, worst_q)
+    dev.close()
+
+
 def test_device_closed_loop_stops_at_the_end_of_the_path(paths, capsys):
     from control import MPPIControllerForPathTracking
     ref = cases.ref_path_for(paths, "xydq_circle.txt")

@@ -285,18 +285,28 @@ __device__ __forceinline__ void warp_win_cert(const double (*srow)[2], int lane,
     const double wmin = kCertMinLateral * reach, wt = kCertOffsetLateral * reach;
     const double bmax = (fabs(nux) + fabs(nuy)) * domw;
     double lo = -bmax, hi = bmax;
-    if (valid) {
+    {
         auto row = [&](int j, double& x, double& y) { x = srow[j][0]; y = srow[j][1]; };
-        const RowGeom g = cert_row_geom(row, lane, n, nux, nuy, margin, wt);
-        rec.tx = (float)g.tx; rec.ty = (float)g.ty;
-        double push, rlo, rhi;
-        if (lane == 0) rec.kL = kCertHuge;
-        else if (cert_role_form(g.L, g.b, wmin, wt, push, rlo, rhi)) {
-            rec.kL = (float)(g.k - push - cert_delta(g.tx, g.ty, g.k - push, domw)); lo = fmax(lo, rlo); hi = fmin(hi, rhi);
+        RowGeom g, gp;
+        bool again = false;
+        if (valid) {
+            g = cert_row_geom<false>(row, lane, n, nux, nuy, margin, wt);
+            gp = g;
+            again = (lane > 0 && !cert_role_plain(g.L, g.b, wmin)) || (lane < n - 1 && !cert_role_plain(g.U, g.b, wmin));
         }
-        if (lane == n - 1) rec.kU = -kCertHuge;
-        else if (cert_role_form(g.U, g.b, wmin, wt, push, rlo, rhi)) {
-            rec.kU = (float)(g.k + push + cert_delta(g.tx, g.ty, g.k + push, domw)); lo = fmax(lo, rlo); hi = fmin(hi, rhi);
+        // rows closer together than the FP32 margin (a path that starts from rest): thresholds pushed off the row
+        if (__any_sync(0xffffffffu, again) && again) gp = cert_row_geom<true>(row, lane, n, nux, nuy, margin, wt);
+        if (valid) {
+            rec.tx = (float)g.tx; rec.ty = (float)g.ty;
+            double push, rlo, rhi;
+            if (lane == 0) rec.kL = kCertHuge;
+            else if (cert_role_form(g.L, gp.L, g.b, wmin, wt, push, rlo, rhi)) {
+                rec.kL = (float)(g.k - push - cert_delta(g.tx, g.ty, g.k - push, domw)); lo = fmax(lo, rlo); hi = fmin(hi, rhi);
+            }
+            if (lane == n - 1) rec.kU = -kCertHuge;
+            else if (cert_role_form(g.U, gp.U, g.b, wmin, wt, push, rlo, rhi)) {
+                rec.kU = (float)(g.k + push + cert_delta(g.tx, g.ty, g.k + push, domw)); lo = fmax(lo, rlo); hi = fmin(hi, rhi);
+            }
         }
     }
     // ---- index estimate: Kasa circle fit on centred chord coordinates, quadratic fit of the index on w ----

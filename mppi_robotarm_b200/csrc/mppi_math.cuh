@@ -82,9 +82,12 @@ MPPI_HD double rsqrt64_(double x) {
     r = r * fma(-0.5 * x * r, r, 1.5);
     return r * fma(-0.5 * x * r, r, 1.5);
 }
+// FP32-accurate reciprocal (relative error < 2e-7) for the certificate's pair loop, whose results are widened by 1e-6
+MPPI_HD double rcp32_(double x) { return (double)__frcp_rn((float)x); }
 #else
 MPPI_HD double rcp64_(double x) { return 1.0 / x; }
 MPPI_HD double rsqrt64_(double x) { return 1.0 / sqrt(x); }
+MPPI_HD double rcp32_(double x) { return 1.0 / x; }
 #endif
 
 // ---- sin & cos of one angle, ~1 ulp, no slow path --------------------------------------------
@@ -414,8 +417,10 @@ constexpr double kCertOffsetLateral = 0.25;            // lateral half-width of 
 constexpr double kCertMaxOffset = 0.25;                // give up when the threshold would be > 25 cm from the row
 
 // Row a of `n` local rows against every other row.  nu = window normal (already rounded to FP32 and widened
-// back); `row(j, x, y)` fetches row j; wt = lateral half-width of the pushed form.
-template <class RowFn>
+// back); `row(j, x, y)` fetches row j; wt = lateral half-width of the pushed form.  PUSH = false computes only
+// the bounds of the threshold-at-the-row form (the common case; the caller asks again with PUSH = true for rows
+// whose roles that form cannot serve).  Bounds carry the 2e-7 relative error of rcp32_: the caller widens.
+template <bool PUSH, class RowFn>
 MPPI_HD RowGeom cert_row_geom(RowFn row, int a, int n, double nux, double nuy, double margin, double wt) {
     RowGeom g;
     double ax, ay, px, py, qx, qy;
@@ -446,29 +451,38 @@ MPPI_HD RowGeom cert_row_geom(RowFn row, int a, int n, double nux, double nuy, d
         if (!(along > 0.0)) { r.ok = false; continue; }
         const double f0 = gx * gx + gy * gy + 2.0 * (gx * (v0x - ax) + gy * (v0y - ay));
         const double sl = 2.0 * (gx * v1x + gy * v1y);
-        if (sl > 0.0) { const double bnd = (margin - f0) * rcp64_(sl); r.lo = bnd > r.lo ? bnd : r.lo; }
-        else if (sl < 0.0) { const double bnd = (margin - f0) * rcp64_(sl); r.hi = bnd < r.hi ? bnd : r.hi; }
-        else if (!(f0 >= margin)) r.lo = 1e300;
-        const double need = (margin - (f0 + sl * g.b - fabs(sl) * wt)) * 0.5 * rcp64_(along);
-        r.fneed = need > r.fneed ? need : r.fneed;
+        if (!PUSH) {
+            const double bnd = (margin - f0) * rcp32_(sl);
+            if (sl > 0.0) r.lo = bnd > r.lo ? bnd : r.lo;
+            else if (sl < 0.0) r.hi = bnd < r.hi ? bnd : r.hi;
+            else if (!(f0 >= margin)) r.lo = 1e300;
+        } else {
+            const double need = (margin - (f0 + sl * g.b - fabs(sl) * wt)) * 0.5 * rcp32_(along);
+            r.fneed = need > r.fneed ? need : r.fneed;
+        }
     }
     return g;
 }
 // Decide the form of one role: threshold at the row (push = 0, the role's own lateral bounds), pushed by
 // `push` (bounds b +- wt), or off.  Returns false when the role is off.
-MPPI_HD bool cert_role_form(const RowRole& r, double b, double wmin, double wt, double& push, double& lo, double& hi) {
-    push = 0.0; lo = r.lo; hi = r.hi;
-    if (!r.ok) return false;
-    if (r.lo <= b - wmin && r.hi >= b + wmin) return true;
-    if (!(r.fneed <= kCertMaxOffset)) return false;
-    push = r.fneed * (1.0 + 1e-9) + 1e-12; lo = b - wt; hi = b + wt;
+MPPI_HD bool cert_role_plain(const RowRole& r, double b, double wmin) {
+    return r.ok && r.lo <= b - wmin && r.hi >= b + wmin;
+}
+// `plain` = the role as computed with PUSH = false, `pushed` = with PUSH = true (only read when plain fails)
+MPPI_HD bool cert_role_form(const RowRole& plain, const RowRole& pushed, double b, double wmin, double wt,
+                            double& push, double& lo, double& hi) {
+    push = 0.0; lo = plain.lo; hi = plain.hi;
+    if (!plain.ok) return false;
+    if (cert_role_plain(plain, b, wmin)) return true;
+    if (!(pushed.fneed <= kCertMaxOffset)) return false;
+    push = pushed.fneed * (1.0 + 1e-6) + 1e-12; lo = b - wt; hi = b + wt;
     return true;
 }
 
 // [blo, bhi] as the FP32 test will see it: moved inwards by the rounding of b = fma(nx, x, ny * y), of the
-// float conversion, and by 1e-9 relative for the approximate reciprocals of the device construction.
+// float conversion, and by 1e-6 relative for the FP32-accurate reciprocals of the device construction.
 MPPI_HD void cert_store_range(WinCert& c, double nux, double nuy, double blo, double bhi, double bmax) {
-    const double eb = (8.0 * kCertU + 1e-9) * bmax + 1e-30;
+    const double eb = (8.0 * kCertU + 1e-6) * bmax + 1e-30;
     c.nx = (float)nux; c.ny = (float)nuy;
     c.blo = (float)(blo + eb); c.bhi = (float)(bhi - eb);
 }
@@ -633,17 +647,20 @@ MPPI_HD void make_win_cert(const double (*rows)[2], int n_valid, double reach, d
     double blo = -bmax, bhi = bmax;
     double sj[kWindow], bj[kWindow];
     for (int a = 0; a < n_valid; ++a) {
-        const RowGeom g = cert_row_geom(row, a, n_valid, nux, nuy, margin, wt);
+        const RowGeom g = cert_row_geom<false>(row, a, n_valid, nux, nuy, margin, wt);
+        RowGeom gp = g;
+        if ((a > 0 && !cert_role_plain(g.L, g.b, wmin)) || (a < n_valid - 1 && !cert_role_plain(g.U, g.b, wmin)))
+            gp = cert_row_geom<true>(row, a, n_valid, nux, nuy, margin, wt);
         RowRec& r = tab[a];
         r.tx = (float)g.tx; r.ty = (float)g.ty;
         double push, lo, hi;
         if (a == 0) r.kL = kCertHuge;                        // no rows below row 0
-        else if (cert_role_form(g.L, g.b, wmin, wt, push, lo, hi)) {
+        else if (cert_role_form(g.L, gp.L, g.b, wmin, wt, push, lo, hi)) {
             r.kL = (float)(g.k - push - cert_delta(g.tx, g.ty, g.k - push, domw));
             blo = lo > blo ? lo : blo; bhi = hi < bhi ? hi : bhi;
         }
         if (a == n_valid - 1) r.kU = -kCertHuge;             // no rows above the last one
-        else if (cert_role_form(g.U, g.b, wmin, wt, push, lo, hi)) {
+        else if (cert_role_form(g.U, gp.U, g.b, wmin, wt, push, lo, hi)) {
             r.kU = (float)(g.k + push + cert_delta(g.tx, g.ty, g.k + push, domw));
             blo = lo > blo ? lo : blo; bhi = hi < bhi ? hi : bhi;
         }

@@ -182,7 +182,10 @@ class MppiEngine:
         self.exchange = exchange if self.shard.world > 1 else "none"
         self.set_ref_path(ref)
         if self.exchange == "auto":
-            self.exchange = "p2p" if self._try_peer_exchange() else "nccl"
+            import torch.distributed as dist
+            # (a shard without a process group — partials gathered by the caller — has nobody to map buffers with)
+            live = dist.is_available() and dist.is_initialized()
+            self.exchange = "p2p" if live and self._try_peer_exchange() else "nccl"
         elif self.exchange == "p2p":
             self._setup_peer_exchange()
         if self.exchange == "p2p":

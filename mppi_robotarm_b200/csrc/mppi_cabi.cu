@@ -19,6 +19,7 @@ using namespace mppi;
 namespace {
 
 constexpr int kNumTimers = 6;        // prepare, rollout, softmin, wsum, reduce, finalize
+constexpr int kWinTableMaxRows = 131072;   // 320 MB of window tables at most
 char g_create_error[512] = "";
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -33,7 +34,7 @@ struct NvtxRange {
 struct Workspace {
     size_t bytes;
     size_t off_ref, off_step_blocks, off_in, off_out, off_S, off_w, off_block_min, off_eta_part,
-        off_rho, off_v_part, off_partial, off_loop, off_eta_fused, off_tickets, off_seq, off_stats;
+        off_rho, off_v_part, off_partial, off_loop, off_eta_fused, off_tickets, off_seq, off_stats, off_win_table;
 };
 
 }  // namespace
@@ -193,6 +194,9 @@ void carve(const MppiConfig* c, int sm, Workspace* w) {
     w->off_tickets = take(E * sizeof(unsigned int));
     w->off_seq = take(2 * sizeof(unsigned long long));       // [0] step sequence number, [1] exchange status
     w->off_stats = take(4 * sizeof(unsigned long long));     // warp-lookups: [0] answered by an end test, [1] all, [2] by a certified triple
+    // window tables + certificates of every window start of the path (2.4 KB per waypoint), built by
+    // mppi_set_ref_path(); paths beyond kWinTableMaxRows build the window on the spot in every step instead
+    w->off_win_table = take(c->max_ref_rows <= kWinTableMaxRows ? (size_t)c->max_ref_rows * kWinBytes : 0);
     w->bytes = off;
 }
 
@@ -314,7 +318,8 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
     {
         NvtxRange r("mppi.prepare");
         mppi_prepare_sm100a<<<dc.n_env, 32, 0, s>>>(dc, dio, ref, step_blocks, pull,
-                                                    (unsigned long long*)(ws + h->ws.off_seq));
+                                                    (unsigned long long*)(ws + h->ws.off_seq),
+                                                    h->cfg.max_ref_rows <= kWinTableMaxRows ? ws + h->ws.off_win_table : nullptr);
     }
     if (timed) CU(h, cudaEventRecord(h->tev[1], s));
     {
@@ -585,6 +590,14 @@ int mppi_set_ref_path(MppiHandle* h, const double* ref, int32_t n_rows) {
     CU(h, cudaMemcpy(h->dev + h->ws.off_ref, ref, (size_t)n_rows * 4 * sizeof(double), cudaMemcpyHostToDevice));
     h->n_ref_rows = n_rows;
     h->dc.n_ref_rows = n_rows;
+    if (h->cfg.max_ref_rows <= kWinTableMaxRows) {
+        // everything of a step block that depends only on (path, window start): built here, once, for every start
+        mppi_window_table_sm100a<<<n_rows, 32>>>(h->dc, (const double*)(h->dev + h->ws.off_ref), n_rows,
+                                                  h->dev + h->ws.off_win_table);
+        CU(h, cudaGetLastError());
+        CU(h, cudaDeviceSynchronize());
+        h->launches += 1;
+    }
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
     if (h->tick_exec) { cudaGraphExecDestroy(h->tick_exec); h->tick_exec = nullptr; }
     if (h->sharded_exec) { cudaGraphExecDestroy(h->sharded_exec); h->sharded_exec = nullptr; }

@@ -360,6 +360,57 @@ __device__ __forceinline__ void warp_win_cert(const double (*srow)[2], int lane,
     c.jhi = (fabs(q0) < 1e6 && fabs(q1) < 1e30 && fabs(q2) < 1e30) ? (float)(n - 2) : 0.f;
 }
 
+// Bytes of a step block that depend only on the path and the window start p (everything between the header
+// and the step controls): built once per path for every p (mppi_window_table_sm100a) and copied by the prepare
+// kernel, or built on the spot when the path is too long for a table.
+constexpr int kWinBytes = kStepBlockFixed - 64;
+static_assert(kWinBytes % 16 == 0, "window part is copied in 16-byte words");
+
+// One warp: `row` = this lane's path row p + lane (x, y, dq1, dq2; anything for lanes beyond the path end),
+// (ox, oy) = row p.  Writes the window tables, the lookup certificate and the far-field wedges through sb.
+__device__ __forceinline__ void write_window_tables(const double4& row, double ox, double oy, int lane, int p, int n,
+                                                    const DevCfg& cfg, double (*srow)[2], const StepBlockView& sb) {
+    // window row `lane` in coordinates local to row p (make_window_row on the preloaded rows)
+    WinEntry w; RefRow r;
+    if (lane < kWindow && p + lane < n) {
+        const double rx = row.x - ox, ry = row.y - oy;
+        w.a = (float)(-2.0 * rx); w.b = (float)(-2.0 * ry); w.c = (float)(rx * rx + ry * ry); w.pad = 0.f;
+        r.rx = (float)rx; r.ry = (float)ry; r.rd1 = (float)row.z; r.rd2 = (float)row.w;
+    } else {                   // beyond the end of the path (control.py:208-209) or table padding
+        w.a = 0.f; w.b = 0.f; w.c = kSentinel; w.pad = 0.f;
+        r.rx = 0.f; r.ry = 0.f; r.rd1 = 0.f; r.rd2 = 0.f;
+    }
+    // the rollouts subtract the FP32 origin from the FP32 end-effector; rows are relative to
+    // the FP64 origin — the difference (<= 6e-8) is common to all candidates of a lookup
+    sb.win[lane] = w; sb.rows[lane] = r;
+    {   // lookup certificate of the window (make_win_cert of mppi_math.cuh, one lane per row)
+        const int nv = min(kWindow, n - p);
+        if (lane < kWindow) { srow[lane][0] = row.x - ox; srow[lane][1] = row.y - oy; }
+        __syncwarp();
+        WinCert c; RowRec rec; EndWedges wed;
+        warp_win_cert(srow, lane, nv, cfg.cost_l1 + cfg.cost_l2, ox, oy, !(cfg.flags & 16), c, rec, wed);   // 16: MPPI_FLAG_FULL_SEARCH
+        rec.a = w.a; rec.b = w.b; rec.c = w.c; rec.pad = 0.f;
+        sb.rec[lane] = rec;
+        if (lane == 0) { *sb.cert = c; *sb.wed = wed; }
+    }
+    // the same a/b coefficients once more, laid out as candidate pairs
+    const float a1 = __shfl_down_sync(0xffffffffu, w.a, 1), b1 = __shfl_down_sync(0xffffffffu, w.b, 1);
+    if ((lane & 1) == 0) sb.pairs[lane >> 1] = make_float4(w.a, a1, w.b, b1);
+}
+
+// Window part of the step block for EVERY window start p of the path (one warp per p), run by
+// mppi_set_ref_path(): table[p] = bytes [64, kStepBlockFixed) of the step block of a controller at waypoint p.
+__global__ void __launch_bounds__(32) mppi_window_table_sm100a(DevCfg cfg, const double* __restrict__ ref, int n,
+                                                               char* __restrict__ table) {
+    __shared__ double srow[kWindowPad][2];
+    const int p = blockIdx.x, lane = threadIdx.x;
+    const double4* ref4 = (const double4*)ref;
+    const double4 row = ref4[min(p + lane, n - 1)];
+    const double ox = __shfl_sync(0xffffffffu, row.x, 0), oy = __shfl_sync(0xffffffffu, row.y, 0);
+    const StepBlockView sb = view_step_block(table + (size_t)p * kWinBytes - 64);    // (header and controls not touched)
+    write_window_tables(row, ox, oy, lane, p, n, cfg, srow, sb);
+}
+
 // ================================================================================================
 // 1. prepare: one warp per environment
 // ================================================================================================
@@ -372,7 +423,8 @@ __device__ __forceinline__ void warp_win_cert(const double (*srow)[2], int lane,
 // state on the device between steps: the step counter then advances here.
 __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, const double* __restrict__ ref,
                                                           char* __restrict__ step_blocks, int pull,
-                                                          unsigned long long* __restrict__ seq) {
+                                                          unsigned long long* __restrict__ seq,
+                                                          const char* __restrict__ win_table) {
     __shared__ double srow[kWindowPad][2];        // local window rows for the certificate construction
     pdl_launch_dependents();                      // the rollout CTAs may be scheduled now (they wait before reading)
     const int e = blockIdx.x, lane = threadIdx.x, T = cfg.T;
@@ -453,33 +505,18 @@ __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, 
         *sb.hd = h;
         out_store(io, io.new_idx + e, p);
     }
-    {
-        // window row `lane` in coordinates local to row p (make_window_row on the preloaded rows)
-        WinEntry w; RefRow r;
-        if (lane < kWindow && p + lane < n) {
-            const double rx = row.x - ox, ry = row.y - oy;
-            w.a = (float)(-2.0 * rx); w.b = (float)(-2.0 * ry); w.c = (float)(rx * rx + ry * ry); w.pad = 0.f;
-            r.rx = (float)rx; r.ry = (float)ry; r.rd1 = (float)row.z; r.rd2 = (float)row.w;
-        } else {                   // beyond the end of the path (control.py:208-209) or table padding
-            w.a = 0.f; w.b = 0.f; w.c = kSentinel; w.pad = 0.f;
-            r.rx = 0.f; r.ry = 0.f; r.rd1 = 0.f; r.rd2 = 0.f;
+    if (win_table != nullptr) {
+        // everything of the step block that depends only on the window start was built when the path was set:
+        // copy the 2.4 KB of window p (five independent 16-byte loads per lane)
+        const uint4* src = (const uint4*)(win_table + (size_t)p * kWinBytes);
+        uint4* dst = (uint4*)((char*)sb.hd + 64);
+#pragma unroll
+        for (int i = 0; i < (kWinBytes / 16 + 31) / 32; ++i) {
+            const int k = lane + 32 * i;
+            if (k < kWinBytes / 16) dst[k] = __ldg(src + k);
         }
-        // the rollouts subtract the FP32 origin from the FP32 end-effector; rows are relative to
-        // the FP64 origin — the difference (<= 6e-8) is common to all candidates of a lookup
-        sb.win[lane] = w; sb.rows[lane] = r;
-        {   // lookup certificate of the window (make_win_cert of mppi_math.cuh, one lane per row)
-            const int nv = min(kWindow, n - p);
-            if (lane < kWindow) { srow[lane][0] = row.x - ox; srow[lane][1] = row.y - oy; }
-            __syncwarp();
-            WinCert c; RowRec rec; EndWedges wed;
-            warp_win_cert(srow, lane, nv, cfg.cost_l1 + cfg.cost_l2, ox, oy, !(cfg.flags & 16), c, rec, wed);   // 16: MPPI_FLAG_FULL_SEARCH
-            rec.a = w.a; rec.b = w.b; rec.c = w.c; rec.pad = 0.f;
-            sb.rec[lane] = rec;
-            if (lane == 0) { *sb.cert = c; *sb.wed = wed; }
-        }
-        // the same a/b coefficients once more, laid out as candidate pairs
-        const float a1 = __shfl_down_sync(0xffffffffu, w.a, 1), b1 = __shfl_down_sync(0xffffffffu, w.b, 1);
-        if ((lane & 1) == 0) sb.pairs[lane >> 1] = make_float4(w.a, a1, w.b, b1);
+    } else {
+        write_window_tables(row, ox, oy, lane, p, n, cfg, srow, sb);
     }
 #pragma unroll
     for (int i = 0; i < kTS; ++i) {

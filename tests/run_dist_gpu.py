@@ -27,7 +27,7 @@ def main():
     kw = cases.run_py_kwargs(ref, K, T, param_lambda=3000.0)
     results = {}
     for label, graph, exch in (("eager", False, "nccl"), ("graph", True, "nccl"), ("p2p", True, "p2p"),
-                               ("p2p_eager", False, "p2p")):
+                               ("p2p_eager", False, "p2p"), ("auto", True, "auto")):
         c = MPPIControllerForPathTracking(**kw, seed=77, verbose=False, distributed=True, use_graph=graph, exchange=exch)
         x = np.array(cases.X0)
         seq = []
@@ -35,6 +35,10 @@ def main():
             u0, useq, opt, _ = c.calc_control_input(x)
             seq.append((u0.copy(), useq.copy(), opt.copy(), c.prev_waypoints_idx))
         results[label] = seq
+        if label == "auto":
+            assert c._engine().exchange in ("p2p", "nccl")
+            if rank == 0:
+                print(f"exchange='auto' resolved to {c._engine().exchange!r}")
         # every rank must hold bit-identical controller state
         mine = torch.from_numpy(c.u_prev.copy()).cuda()
         allu = [torch.zeros_like(mine) for _ in range(world)]
@@ -42,7 +46,7 @@ def main():
         for other in allu:
             assert torch.equal(other, allu[0]), "ranks diverged"
         c.close()
-    for other in ("graph", "p2p", "p2p_eager"):           # same partials, same combine: bit-identical
+    for other in ("graph", "p2p", "p2p_eager", "auto"):   # same partials, same combine: bit-identical
         for a, b in zip(results["eager"], results[other]):
             for xa, xb in zip(a[:3], b[:3]):
                 np.testing.assert_array_equal(xa, xb)

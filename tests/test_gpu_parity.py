@@ -263,22 +263,34 @@ def test_joint_limit_cost_against_the_oracle(paths):
     kernels.  Weight 0, or limits that are never reached: the very same floats as without the option."""
     from control import MPPIControllerForPathTracking
     ref = cases.ref_path_for(paths, "xydq_circle.txt")
-    lim = dict(joint_limit_lo=(1.10, -1.30), joint_limit_hi=(1.20, -1.20), joint_limit_weight=3.0)
+    with np.load(cases.HERE + "/closed_loop_c1.npz") as z:
+        x0, p0, prev = z["state"][500].copy(), int(z["prev_idx"][500, 0]), z["u_new"][499].copy()
+    # a box of +-0.02 rad around the current joint angles: most rollouts leave it within the horizon
+    lim = dict(joint_limit_lo=(x0[0] - 0.02, x0[1] - 0.02), joint_limit_hi=(x0[0] + 0.02, x0[1] + 0.02),
+               joint_limit_weight=3.0)
     for K, T in ((2048, 30), (300000, 10)):
         kw = cases.run_py_kwargs(ref, K, T, visualize_optimal_traj=False)
+        u = np.concatenate([prev[1:], np.repeat(prev[-1:], 30, axis=0)], axis=0)[:T]
         eps = mo.injected_noise(9, K, T, kw["sigma"])
         c = mo.OracleMPPI(**kw, **lim)
-        o = mo.step_vectorized(c, cases.X0, eps.astype(np.float64))
+        c.u_prev = u.copy(); c.prev_waypoints_idx = p0
+        o = mo.step_vectorized(c, x0, eps.astype(np.float64))
         ctrl = MPPIControllerForPathTracking(**kw, noise="numpy", verbose=False, **lim)
+        ctrl.u_prev = u.copy(); ctrl.prev_waypoints_idx = p0
         H.inject(ctrl, eps)
-        H.quiet_step(ctrl, cases.X0)
+        H.quiet_step(ctrl, x0)
         eng = ctrl._engine()
         S = eng.last_costs()[0][0].cpu().numpy().astype(np.float64)
-        assert H.rel_err(S, o["S"]) <= TOL_S, (K, T)
+        errS = np.abs(S - o["S"]) / np.max(np.abs(o["S"]))
+        # (same bound as the golden cases: isolated FP32 near-tie lookup flips may exceed 2e-6, by at most 20x)
+        assert int((errS > TOL_S).sum()) <= max(1, K // 64) and errS.max() <= 20 * TOL_S, (K, T, np.sort(errS)[-3:])
         assert H.rel_err(eng.out_u_new[0], o["u_new"]) <= TOL_U, (K, T)
-        plain = mo.rollout_costs(mo.OracleMPPI(**kw), np.array(cases.X0), eps.astype(np.float64), prev_idx=0)
-        assert np.mean(o["S"] > plain * (1 + 1e-6)) > 0.5          # the term really is in play
+        plain = mo.OracleMPPI(**kw)
+        plain.u_prev = u.copy()
+        Sp = mo.rollout_costs(plain, x0, eps.astype(np.float64), prev_idx=int(eng.out_new_idx[0]))
+        assert np.mean(o["S"] > Sp * (1 + 1e-6)) > 0.5          # the term really is in play
         ctrl.close()
+    lim = dict(joint_limit_lo=(1.10, -1.30), joint_limit_hi=(1.20, -1.20), joint_limit_weight=3.0)
     # Philox noise source with the term: equals the injected-noise kernels on the exported draw
     K, T = 4096, 40
     kw = cases.run_py_kwargs(ref, K, T, visualize_optimal_traj=False)

@@ -863,6 +863,12 @@ __device__ __forceinline__ unsigned long long global_ns() {
 __device__ __forceinline__ void finalize_env(const DevCfg& cfg, const DevIo& io, int e, const double* gathered, int world,
                                              const PeerExchange& px, FinalizeSmem& sm) {
     const int tid = threadIdx.x, T = cfg.T;
+#ifdef MPPI_PHASE_PRINT
+    unsigned long long fp[8]; fp[0] = global_ns();
+#define MPPI_FPHASE(i) fp[i] = global_ns()
+#else
+#define MPPI_FPHASE(i)
+#endif
     if (tid == 0) sm.timed_out = 0;
     __syncthreads();
     if (px.world > 0) {
@@ -882,6 +888,7 @@ __device__ __forceinline__ void finalize_env(const DevCfg& cfg, const DevIo& io,
         gathered = (const double*)(px.buf[px.rank] + (size_t)par * px.slot_bytes);
         world = px.world;
     }
+    MPPI_FPHASE(1);
     // A partial that did not arrive must not be combined (its slot holds an older step): the update is
     // skipped (u_new = u_prev, zero update, NaN rho / eta) and bit 0 of the status word tells the caller.
     const bool skip = sm.timed_out != 0;
@@ -914,6 +921,7 @@ __device__ __forceinline__ void finalize_env(const DevCfg& cfg, const DevIo& io,
         out_store(io, io.w_eps_raw + (size_t)e * 2 * T + c, v);
     }
     __syncthreads();
+    MPPI_FPHASE(2);
     // scipy.ndimage.median_filter(size=10, mode='reflect') per column (control.py:319-327):
     // window offsets -5..+4, output = element of rank 5 of the sorted window
     for (int c = tid; c < 2 * T; c += blockDim.x) {
@@ -951,6 +959,7 @@ __device__ __forceinline__ void finalize_env(const DevCfg& cfg, const DevIo& io,
         out_store(io, io.u_new + (size_t)e * 2 * T + c, u);
     }
     __syncthreads();
+    MPPI_FPHASE(3);
     // What calc_control_input returns as the control (control.py:148-152, quirk Q2: the first row AFTER the
     // shift), and — MPPI_FLAG_RESIDENT_STATE — the controller state of the next step, kept on the device:
     // shifted sequence (control.py:148-149) and waypoint index (control.py:230).  An environment at the end
@@ -969,6 +978,7 @@ __device__ __forceinline__ void finalize_env(const DevCfg& cfg, const DevIo& io,
     // control.py:129-134: x <- F(x, u[t-1]) for t = 0..T-1 (t = 0 wraps to the last control, Q3).
     // The recurrence is serial: one thread runs it and parks (value, compensation) pairs in shared
     // memory; all threads then convert and store the trajectory (keeps global / PCIe stores off the chain).
+    MPPI_FPHASE(4);
     if (cfg.flags & 1) {
         if (tid == 0) {
             const double* x0 = io.x0 + 4 * e;
@@ -983,14 +993,23 @@ __device__ __forceinline__ void finalize_env(const DevCfg& cfg, const DevIo& io,
             }
         }
         __syncthreads();
+        MPPI_FPHASE(5);
         double* o = io.opt_traj + (size_t)e * 4 * T;
         for (int c = tid; c < 4 * T; c += blockDim.x) {
             const int t = c >> 2, k = c & 3;
             out_store(io, o + c, (double)sm.tr[8 * t + k] - (double)sm.tr[8 * t + 4 + k]);
         }
     } else {
+        MPPI_FPHASE(5);
         for (int c = tid; c < 4 * T; c += blockDim.x) out_store(io, io.opt_traj + (size_t)e * 4 * T + c, 0.0);
     }
+#ifdef MPPI_PHASE_PRINT
+    MPPI_FPHASE(6);
+    if (tid == 0 && e == 0)
+        printf("finalize: wait %llu, combine %llu, filter+update %llu, u0/resident %llu, trajectory %llu, stores %llu ns\n",
+               fp[1] - fp[0], fp[2] - fp[1], fp[3] - fp[2], fp[4] - fp[3], fp[5] - fp[4], fp[6] - fp[5]);
+#endif
+#undef MPPI_FPHASE
 }
 
 constexpr int kPairSlots = MPPI_MAX_T_INTERNAL / 2 / 32;      // Philox calls per lane and sample (weight-sum kernel)
@@ -1019,7 +1038,14 @@ mppi_softmin_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ct
     __shared__ bool is_last;
     const int e = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_pairs = (cfg.T + 1) >> 1;
+#ifdef MPPI_PHASE_PRINT
+    unsigned long long ph[8]; ph[0] = global_ns();
+#define MPPI_PHASE(i) ph[i] = global_ns()
+#else
+#define MPPI_PHASE(i)
+#endif
     pdl_wait();                                   // the rollout kernel's costs and block minima are complete
+    MPPI_PHASE(1);
     // rho = min over the rollout kernel's block minima
     float m = INFINITY;
     for (int i = tid; i < cfg.g_roll; i += kWsumThreads) m = fminf(m, block_min[(size_t)e * cfg.g_roll + i]);
@@ -1084,6 +1110,7 @@ mppi_softmin_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ct
             }
         }
     }
+    MPPI_PHASE(2);
     eta = warp_sum(eta);
     if (lane == 0) redd[warp] = eta;
 #pragma unroll
@@ -1114,6 +1141,7 @@ mppi_softmin_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ct
     if (tid == 0) is_last = (atomicAdd(&tickets[e], 1u) == gridDim.x - 1);
     __syncthreads();
     if (!is_last) return;
+    MPPI_PHASE(3);
     __threadfence();
     double* out = partial + (size_t)e * (2 + 2 * cfg.T);
     const int G = gridDim.x;
@@ -1123,13 +1151,15 @@ mppi_softmin_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ct
         a = warp_sum(a);
         if (lane == 0) { out[0] = (double)rho; out[1] = a; tickets[e] = 0u; }
     }
-    for (int c = tid; c < 2 * cfg.T; c += kWsumThreads) {
-        double a = 0.0;
+    for (int c = tid; c < 2 * cfg.T; c += kWsumThreads) {      // (measured: 9.5 us for 256 rows; two batched / warp-split
+        double a = 0.0;                                        //  forms of this loop were slower, profiles/r2_variants.md)
         const float* src = v_part + (size_t)e * cfg.g_wsum * 2 * cfg.T + c;
         for (int b = 0; b < G; ++b) a += (double)__ldcg(src + (size_t)b * 2 * cfg.T);
         out[2 + c] = a;
     }
+    MPPI_PHASE(4);
     if (px.world > 0) px_put(px, out, cfg.n_env, e, 2 + 2 * cfg.T);   // fused exchange: triple -> every peer
+    MPPI_PHASE(5);
     // fused combine / filter / update / optimal trajectory: one kernel boundary less per control step.  With
     // the peer exchange this block then waits for the other ranks' triples (their last blocks put them the
     // same way; every rank's kernel is resident on its own GPU, so the wait cannot deadlock).
@@ -1138,6 +1168,13 @@ mppi_softmin_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ct
         __syncthreads();
         finalize_env(cfg, io, e, partial, 1, px, fin);
     }
+#ifdef MPPI_PHASE_PRINT
+    MPPI_PHASE(6);
+    if (tid == 0 && e == 0)
+        printf("wsum last block: wait %llu, scan %llu, partials+ticket %llu, reduce %llu, put %llu, finalize %llu ns (G=%d)\n",
+               ph[1] - ph[0], ph[2] - ph[1], ph[3] - ph[2], ph[4] - ph[3], ph[5] - ph[4], ph[6] - ph[5], (int)gridDim.x);
+#endif
+#undef MPPI_PHASE
 }
 
 // ================================================================================================

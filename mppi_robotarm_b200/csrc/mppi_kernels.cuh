@@ -1151,8 +1151,11 @@ mppi_softmin_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ct
         a = warp_sum(a);
         if (lane == 0) { out[0] = (double)rho; out[1] = a; tickets[e] = 0u; }
     }
-    for (int c = tid; c < 2 * cfg.T; c += kWsumThreads) {      // (measured: 9.5 us for 256 rows; two batched / warp-split
-        double a = 0.0;                                        //  forms of this loop were slower, profiles/r2_variants.md)
+    // (G x 2T floats through ONE block: ~37 ns per row, bound by the number of requests a single SM keeps in flight —
+    //  9.5 us at K = 2^20 (G = 256), 3 us at the 8-GPU shard size; unrolled / batched / warp-split forms of this loop
+    //  measured the same or worse, profiles/r2_variants.md)
+    for (int c = tid; c < 2 * cfg.T; c += kWsumThreads) {
+        double a = 0.0;
         const float* src = v_part + (size_t)e * cfg.g_wsum * 2 * cfg.T + c;
         for (int b = 0; b < G; ++b) a += (double)__ldcg(src + (size_t)b * 2 * cfg.T);
         out[2 + c] = a;

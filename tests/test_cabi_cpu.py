@@ -56,9 +56,11 @@ def test_layout_and_workspace_sizing():
     lay = _cabi.MppiIoLayout()
     c = _cfg()
     assert lib.mppi_io_layout(C.byref(c), C.byref(lay)) == 0
-    offs = [lay.off_x0, lay.off_u_prev, lay.off_prev_idx, lay.off_step, lay.off_new_idx, lay.off_rho, lay.off_eta,
-            lay.off_w_eps_raw, lay.off_w_eps_filt, lay.off_u_new, lay.off_opt_traj, lay.bytes]
-    assert offs == sorted(offs) and all(o % 8 == 0 for o in offs)
+    offs = [lay.off_x0, lay.off_u_prev, lay.off_prev_idx, lay.off_step, lay.off_new_idx, lay.off_status, lay.off_rho,
+            lay.off_eta, lay.off_u0, lay.off_w_eps_raw, lay.off_w_eps_filt, lay.off_u_new, lay.off_opt_traj, lay.bytes]
+    assert offs == sorted(offs) and len(set(offs)) == len(offs) and all(o % 8 == 0 for o in offs)
+    # the compact results of a resident handle are the contiguous head of the outputs
+    assert lay.off_w_eps_raw - lay.off_new_idx <= 256 and lay.off_u0 + 16 <= lay.off_w_eps_raw
     assert lay.off_u_prev - lay.off_x0 >= 4 * 8 and lay.bytes - lay.off_opt_traj >= 50 * 4 * 8
     ws = lib.mppi_workspace_bytes(C.byref(c))
     assert ws >= 2 * 4096 * 4 + 2000 * 32
@@ -69,7 +71,10 @@ def test_layout_and_workspace_sizing():
 @pytest.mark.parametrize("mutate, why", [
     (lambda c: setattr(c, "T", 0), "T"), (lambda c: setattr(c, "T", _cabi.MAX_T + 1), "T"),
     (lambda c: setattr(c, "K_local", 5000), "shard"), (lambda c: setattr(c, "abi_version", 99), "abi"),
-    (lambda c: setattr(c, "param_lambda", 0.0), "lambda"), (lambda c: setattr(c, "n_env", 0), "n_env")])
+    (lambda c: setattr(c, "param_lambda", 0.0), "lambda"), (lambda c: setattr(c, "n_env", 0), "n_env"),
+    (lambda c: setattr(c, "joint_limit_weight", -1.0), "joint_limit_weight"),
+    (lambda c: (setattr(c, "joint_limit_weight", 1.0), c.joint_limit_lo.__setitem__(0, 2.0), c.joint_limit_hi.__setitem__(0, 1.0)), "lo <= hi"),
+    (lambda c: (setattr(c, "joint_limit_weight", 1.0), setattr(c, "flags", c.flags | _cabi.FLAG_DYNAMICS_F1)), "_F only")])
 def test_invalid_configs_are_rejected(mutate, why):
     lib = _cabi.load()
     c = _cfg()

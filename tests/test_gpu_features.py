@@ -465,6 +465,49 @@ def test_two_handles_in_flight_do_not_share_window_state(paths):
     a.close(); b.close()
 
 
+def test_peer_exchange_timeout_skips_the_update(paths):
+    """A peer whose partial never arrives (here: rank 1 of 2 does not exist — both exchange buffers are local
+    allocations of this GPU and nobody raises rank 1's flag): after the configured timeout the step must NOT combine
+    the stale slot.  It skips the update (u_new = u_prev, zero update, NaN rho / eta), reports it in the status
+    word and through mppi_exchange_status, and leaves the handle usable: the next step reports again instead of
+    staying poisoned, and after re-configuring the exchange for a world of one the step is the single-GPU step."""
+    import ctypes as C
+    import torch
+    from mppi_robotarm_b200 import ShardSpec, _cabi
+    K, T = 2048, 20
+    eng = _engine(paths, K, T, shard=ShardSpec(0, 2), exchange="nccl")
+    lib = eng.lib
+    nbytes = int(lib.mppi_exchange_bytes(C.byref(eng.cfg), 2))
+    bufs = [torch.zeros(nbytes, dtype=torch.uint8, device=eng.device) for _ in range(2)]
+    table = (C.c_void_p * 2)(*[b.data_ptr() for b in bufs])
+    _cabi.check(lib.mppi_set_peer_exchange(eng.handle, 0, 2, table), eng.handle)
+    _cabi.check(lib.mppi_set_exchange_timeout(eng.handle, 5.0), eng.handle)
+    assert lib.mppi_set_exchange_timeout(eng.handle, 0.0) != 0
+    u = _u0(T)
+    for _ in range(2):
+        eng.write_inputs(cases.X0, u, 0)
+        _cabi.check(lib.mppi_step_sharded(eng.handle, _cabi.NOISE_PHILOX, None, eng.stream.cuda_stream), eng.handle)
+        _cabi.check(lib.mppi_wait(eng.handle), eng.handle)
+        eng.step_counter += 1
+        assert eng.out_status[0] == 1 and lib.mppi_exchange_status(eng.handle) == 1
+        np.testing.assert_array_equal(eng.out_u_new[0], u)
+        assert not np.any(eng.out_w_eps_filt) and np.isnan(eng.out_rho[0]) and np.isnan(eng.out_eta[0])
+    # a world of one (rank 0 alone, same buffers): its own put satisfies the wait
+    eng.close()
+    one = _engine(paths, K, T, seed=99)
+    solo = _engine(paths, K, T, seed=99)
+    table1 = (C.c_void_p * 1)(bufs[0].zero_().data_ptr())
+    assert int(lib.mppi_exchange_bytes(C.byref(solo.cfg), 1)) <= nbytes
+    _cabi.check(lib.mppi_set_peer_exchange(solo.handle, 0, 1, table1), solo.handle)
+    solo.write_inputs(cases.X0, u, 0)
+    _cabi.check(lib.mppi_step_sharded(solo.handle, _cabi.NOISE_PHILOX, None, solo.stream.cuda_stream), solo.handle)
+    _cabi.check(lib.mppi_wait(solo.handle), solo.handle)
+    one.step(cases.X0, u, 0, None)
+    assert solo.out_status[0] == 0 and lib.mppi_exchange_status(solo.handle) == 0
+    np.testing.assert_array_equal(solo.out_u_new, one.out_u_new)
+    one.close(); solo.close()
+
+
 def test_nccl_sharded_step_matches_single_gpu():
     """Real multi-process NCCL run (one rank per GPU); skipped on single-GPU boxes."""
     import os

@@ -31,6 +31,8 @@ def _compare_step(ctrl, g, s, kw, out, label):
     # within FP32 rounding can pick the neighbouring waypoint (far-off, zero-weight samples):
     # at most one sample in 64 may deviate more, and then by no more than 4e-5 of the largest cost
     errS = np.abs(S - g[f"S.{s}"]) / np.max(np.abs(g[f"S.{s}"]))
+    if (errS > TOL_S).any():           # (printed so that a growing number of near-tie flips shows up in the log)
+        print(f"{label}: {int((errS > TOL_S).sum())} of {S.size} costs beyond {TOL_S:g} (near-tie lookup flips), worst {errS.max():.2e}")
     assert int((errS > TOL_S).sum()) <= max(1, S.size // 64) and errS.max() <= 20 * TOL_S, (label, "S", np.sort(errS)[-3:])
     # normalised weights (control.py:297-314); a cost error dS moves a weight by ~dS/lambda relative
     wt = eng.last_costs()[1][0].cpu().numpy().astype(np.float64)

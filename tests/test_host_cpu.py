@@ -117,3 +117,19 @@ def test_refgen_tracking_run_has_the_shape_of_xydq_circle(paths):
     # same order of magnitude of joint rates and torques as the recorded file
     assert 0.3 <= np.abs(rec[:, 2:4]).max() / np.abs(ref[:, 2:4]).max() <= 3.0
     assert 0.3 <= np.abs(rec[:, 4:6]).max() / np.abs(ref[:, 4:6]).max() <= 3.0
+
+
+def test_noise_factor_handles_definite_semidefinite_and_rejects_asymmetric():
+    """Factor of the in-kernel draw eps = L z (engine.noise_factor): Cholesky for a positive definite Sigma, an
+    eigen-factor made lower triangular for a semi-definite one (np.random.multivariate_normal, control.py:163,
+    accepts those), LinAlgError for an asymmetric or indefinite matrix."""
+    from mppi_robotarm_b200.engine import noise_factor
+    for sig in (np.array([[20.0, 0.0], [0.0, 20.0]]), np.array([[20.0, 6.0], [6.0, 10.0]]),
+                np.array([[4.0, 2.0], [2.0, 1.0]]), np.array([[0.0, 0.0], [0.0, 9.0]])):
+        L = noise_factor(sig)
+        np.testing.assert_allclose(L @ L.T, sig, atol=1e-12)
+        assert L[0, 1] == 0.0 or abs(L[0, 1]) < 1e-12
+    with pytest.raises(np.linalg.LinAlgError):
+        noise_factor(np.array([[10.0, 10.0], [100.0, 100.0]]))       # the reference's (unusable) default Sigma: asymmetric
+    with pytest.raises(np.linalg.LinAlgError):
+        noise_factor(np.array([[1.0, 2.0], [2.0, 1.0]]))             # indefinite

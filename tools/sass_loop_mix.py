@@ -1,4 +1,8 @@
-"""Static view of the rollout kernel's horizon loop from `cuobjdump -sass` (no GPU needed): size of the loop body,
+"""(Round-1 tool: it recognises the loop shape of the round-1 kernels — two 30-candidate search blocks that a certified
+warp jumps over.  The round-2 kernels are described by the executed-instruction mix of the ncu capture instead,
+profiles/r2_rollout_c4_instruction_mix.txt.)
+
+Static view of the rollout kernel's horizon loop from `cuobjdump -sass` (no GPU needed): size of the loop body,
 the two search blocks the certified lookups jump over, and the opcode mix of what remains (the path a fully
 certified warp executes; the Philox block in it runs every second iteration).
 

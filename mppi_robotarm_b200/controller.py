@@ -102,6 +102,7 @@ class MPPIControllerForPathTracking:
         self.joint_limit_weight = joint_limit_weight
         self._engine_obj = None
         self._engine_ref_path = None
+        self._sigma_checked = None
         self.last = {}               # intermediates of the last step (rho, eta, raw / filtered update)
 
     # ---- engine life cycle ---------------------------------------------------------------------
@@ -155,8 +156,9 @@ class MPPIControllerForPathTracking:
         eps = None
         if self.noise == "numpy":
             eps = self._calc_epsilon(self.Sigma, self.K, self.T, self.dim_u)     # control.py:84
-        else:
+        elif self.Sigma is not self._sigma_checked:       # (the reference validates Sigma in every call, control.py:157-159)
             self._check_sigma(self.Sigma, self.dim_u)
+            self._sigma_checked = self.Sigma
 
         prev_idx = self.prev_waypoints_idx
         eng.step(x0, u, prev_idx, eps)

@@ -66,6 +66,7 @@ struct MppiHandle {
     bool have_step;            // a step has run (step blocks valid)
     bool const_window;         // single environment: window coefficients go through the constant bank
     int ns;                    // samples per thread of the rollout kernel
+    int roll_threads;          // threads per CTA of the rollout kernel
     bool zero_copy;            // kernels read / write the caller's pinned block directly (no memcpy nodes)
     DevIo dio_dev;             // same as dio but never touching the pinned block (device closed loop)
     PeerExchange px;           // peer-memory exchange (world == 0: not configured)
@@ -151,10 +152,18 @@ int pick_ns(const MppiConfig* c, int sm) {
     return best;
 }
 
+// Threads per CTA of the rollout kernel: 128, or fewer for small shards, where finer CTAs spread more evenly over
+// the SMs (MPPI_ROLL_THREADS overrides; A/B in profiles/r2_variants.md).
+int pick_roll_threads(const MppiConfig* c, int sm) {
+    if (const char* f = getenv("MPPI_ROLL_THREADS")) { const int v = atoi(f); if (v == 32 || v == 64 || v == 128) return v; }
+    (void)c; (void)sm;
+    return kRollThreads;
+}
+
 void grid_sizes(const MppiConfig* c, int sm, int* g_roll, int* g_soft, int* g_wsum) {
     const int K = c->K_local;
-    const int ns = pick_ns(c, sm);
-    int gr = (K + kRollThreads * ns - 1) / (kRollThreads * ns);
+    const int ns = pick_ns(c, sm), thr = pick_roll_threads(c, sm);
+    int gr = (K + thr * ns - 1) / (thr * ns);
     if (gr > 32768) gr = 32768;
     *g_roll = gr;
     int gs = (K + kSoftThreads * 4 - 1) / (kSoftThreads * 4);
@@ -347,7 +356,7 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
         pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
         cudaLaunchConfig_t lc = {};
-        lc.gridDim = grid; lc.blockDim = dim3(kRollThreads); lc.dynamicSmemBytes = h->roll_smem; lc.stream = s;
+        lc.gridDim = grid; lc.blockDim = dim3(h->roll_threads); lc.dynamicSmemBytes = h->roll_smem; lc.stream = s;
         lc.attrs = pdl_attr; lc.numAttrs = (h->pdl && !h->const_window && !timed) ? 1 : 0;
 #define MPPI_ROLL(NOISE, CW, NS_, DYN, CERT) do { \
         if (CERT && DYN == 0 && jl) CU(h, cudaLaunchKernelEx(&lc, mppi_rollout_sm100a<NOISE, false, NS_, 0, true, true>, dc, step_ctr, (const char*)step_blocks, eps_arg, S, bmin, stats)); \
@@ -526,6 +535,7 @@ int mppi_create(const MppiConfig* c, void* workspace, size_t workspace_bytes, vo
     h->dio.opt_traj = (double*)(dout + h->io.off_opt_traj);
     h->roll_smem = (size_t)h->dc.step_block_bytes;
     h->ns = pick_ns(c, h->sm_count);
+    h->roll_threads = pick_roll_threads(c, h->sm_count);
     h->const_window = pick_const_window(c);
     h->dio_dev = h->dio;
     h->dio_dev.host_in = nullptr; h->dio_dev.in_delta = 0; h->dio_dev.out_delta = 0;

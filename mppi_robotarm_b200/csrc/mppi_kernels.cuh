@@ -654,9 +654,11 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
 
     float tmin = INFINITY;
     const int T = cfg.T;
-    // thread handles samples kl0 + s*kRollThreads (s < NS): consecutive lanes -> consecutive samples.
+    // thread handles samples kl0 + s*blockDim.x (s < NS): consecutive lanes -> consecutive samples.  The block size
+    // is a launch parameter (128, or 64 for small shards: finer CTAs spread evenly over the SMs).
+    const int nthr = blockDim.x;
     // The trip count is decided per WARP (its first lane), because the lookups vote across the warp.
-    for (int kw0 = blockIdx.x * (kRollThreads * kNS) + (tid & ~31); kw0 < cfg.K_local; kw0 += gridDim.x * kRollThreads * kNS) {
+    for (int kw0 = blockIdx.x * (nthr * kNS) + (tid & ~31); kw0 < cfg.K_local; kw0 += gridDim.x * nthr * kNS) {
         const int kl0 = kw0 + (tid & 31);
         float um[kNS], S[kNS];
         int kl[kNS];
@@ -664,7 +666,7 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
 #pragma unroll
         for (int s = 0; s < kNS; ++s) {
             // a padding sample past the end recomputes the last one (its result is not stored)
-            kl[s] = min(kl0 + s * kRollThreads, cfg.K_local - 1);
+            kl[s] = min(kl0 + s * nthr, cfg.K_local - 1);
             um[s] = (cfg.k_offset + kl[s]) < cfg.n_exploit ? 1.0f : 0.0f;
             asm volatile("" : "+f"(um[s]));            // keep it in a register: not re-derived in every horizon step
         }
@@ -684,7 +686,7 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
         }
 #pragma unroll
         for (int s = 0; s < kNS; ++s) {
-            if (kl0 + s * kRollThreads < cfg.K_local) {
+            if (kl0 + s * nthr < cfg.K_local) {
                 S_out[(size_t)e * cfg.K_local + kl[s]] = S[s];
                 if (finite_(S[s])) tmin = fminf(tmin, S[s]);
             }
@@ -701,7 +703,7 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
     if (tid == 0) {
         float m = red[0];
 #pragma unroll
-        for (int i = 1; i < kRollThreads / 32; ++i) m = fminf(m, red[i]);
+        for (int i = 1; i < nthr / 32; ++i) m = fminf(m, red[i]);
         block_min[(size_t)e * gridDim.x + blockIdx.x] = m;
     }
 }

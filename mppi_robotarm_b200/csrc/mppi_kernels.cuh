@@ -1,17 +1,21 @@
 // mppi_kernels.cuh — sm_100a kernels of the MPPI step (included by mppi_cabi.cu only).
 //
-//   mppi_prepare_sm100a    waypoint update in FP64 + step-block tables       control.py:75, 200-232
+//   mppi_window_table_sm100a  window tables + lookup certificate of every window start (once per path)   control.py:203-215
+//   mppi_prepare_sm100a    waypoint update in FP64, header, window copy, step controls   control.py:75, 200-232
 //   mppi_rollout_sm100a    K fused rollouts, costs only                       control.py:84-109
 //   mppi_softmin_sm100a    min / exp / partial normaliser                     control.py:297-314
 //   mppi_wsum_injected_sm100a   weighted noise sum, K x (T*2) reduction       control.py:115-118
-//   mppi_softmin_wsum_philox_sm100a  the two above + reduce fused (Philox)      control.py:297-314, 115-118
+//   mppi_softmin_wsum_philox_sm100a  the two above + reduce (+ exchange, combine, filter, update) fused (Philox)
+//                                                                              control.py:297-314, 115-134
 //   mppi_reduce_sm100a     this GPU's partial (rho_g, eta_g, V_g)             (sharding)
 //   mppi_finalize_sm100a   combine, median filter, update, optimal rollout    control.py:122-134
+//   mppi_plant_sm100a      one tick of the device-resident closed loop        run.py:53-59, utils.py:14-29
 //   mppi_sampled_traj_sm100a  trajectories of all samples                     control.py:137-145
 //   mppi_philox_export_sm100a the noise tensor the kernels draw               control.py:154-164
 //
-// Data layout in HBM (per environment e): step block = 64 B header | 32 x WinEntry | 32 x RefRow |
-// T x StepCtl (contiguous, 16-byte aligned, moved into shared memory with ONE 1-D TMA bulk copy);
+// Data layout in HBM (per environment e): step block = 64 B header | 32 x WinEntry | 32 x RefRow | 16 x pair |
+// WinCert | 32 x RowRec | EndWedges | T x StepCtl (contiguous, 16-byte aligned, moved into shared memory with ONE
+// 1-D TMA bulk copy);
 // costs S[e][K_local] and weights w[e][K_local] float32; injected noise eps[e][K_local][T][2]
 // float32 (the reference's own [K,T,2] layout, control.py:84).
 #pragma once

@@ -115,10 +115,11 @@ MPPI_HD void sincos_(float x, float& s, float& c) {
     pc = fma_(pc, r2, 4.166664568298827e-2f);
     pc = fma_(pc, r2, -0.5f);
     float cr = fma_(pc, r2, 1.0f);
-    float ss = (q & 1) ? cr : sr;
-    float cc = (q & 1) ? sr : cr;
-    s = (q & 2) ? -ss : ss;
-    c = ((q + 1) & 2) ? -cc : cc;
+    const bool odd = (q & 1) != 0;
+    float ss = odd ? cr : sr;
+    float cc = odd ? sr : cr;
+    s = (q & 2) != 0 ? -ss : ss;
+    c = ((q + 1) & 2) != 0 ? -cc : cc;
 }
 
 // ---- per-controller constants (derived once on the host in FP64, rounded to FP32) -----------

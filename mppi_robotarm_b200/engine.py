@@ -103,7 +103,7 @@ class MppiEngine:
         if smoother == "average" and self.T < 10:
             raise ValueError("the moving-average smoother needs horizon_step_T >= 10 (np.convolve 'same', control.py:338)")
         if search not in ("certified", "full"):
-            raise ValueError("search must be 'certified' (end-of-window shortcut, bit-identical results) or 'full'")
+            raise ValueError("search must be 'certified' (lookups answered by per-window certificates, bit-identical results) or 'full'")
         if dynamics not in ("F", "F1"):
             raise ValueError("dynamics must be 'F' (control.py:234-263) or 'F1' (control.py:265-295)")
         cfg.flags = ((_cabi.FLAG_OPTIMAL_TRAJ if optimal_traj else 0) | (_cabi.FLAG_DEVICE_GRAPH if use_graph else 0)

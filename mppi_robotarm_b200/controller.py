@@ -103,6 +103,7 @@ class MPPIControllerForPathTracking:
         self._engine_obj = None
         self._engine_ref_path = None
         self._sigma_checked = None
+        self._zero_view = None
         self.last = {}               # intermediates of the last step (rho, eta, raw / filtered update)
 
     # ---- engine life cycle ---------------------------------------------------------------------
@@ -150,7 +151,7 @@ class MPPIControllerForPathTracking:
     # ---- the step (control.py:67-152) ------------------------------------------------------------
     def calc_control_input(self, observed_x):
         u = self.u_prev                                   # alias on purpose (control.py:70)
-        x0 = np.asarray(observed_x, dtype=np.float64).reshape(4)
+        x0 = observed_x
         eng = self._engine()
 
         eps = None
@@ -185,7 +186,9 @@ class MPPIControllerForPathTracking:
             sampled_traj_list = np.zeros((self.K, self.T, self.dim_x))
         else:   # the reference allocates K*T*4 float64 zeros every call (26 MB at K=16384, T=50): return a
                 # read-only zero view of the same shape and dtype instead
-            sampled_traj_list = np.broadcast_to(np.zeros(()), (self.K, self.T, self.dim_x))
+            if self._zero_view is None or self._zero_view.shape != (self.K, self.T, self.dim_x):
+                self._zero_view = np.broadcast_to(np.zeros(()), (self.K, self.T, self.dim_x))
+            sampled_traj_list = self._zero_view
 
         self.u_prev[:-1] = u[1:]                          # control.py:148
         self.u_prev[-1] = u[-1]                           # control.py:149

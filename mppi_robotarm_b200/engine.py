@@ -283,9 +283,14 @@ class MppiEngine:
         return self._eps_dev
 
     def write_inputs(self, x0, u_prev, prev_idx):
-        self.in_x0[...] = np.asarray(x0, dtype=np.float64).reshape(self.n_env, 4)
-        self.in_u_prev[...] = np.asarray(u_prev, dtype=np.float64).reshape(self.n_env, self.T, 2)
-        self.in_prev_idx[...] = np.asarray(prev_idx, dtype=np.int64).reshape(self.n_env)
+        if self.n_env == 1:            # the drop-in class: plain assignments (numpy converts), no temporaries
+            self.in_x0[0] = x0
+            self.in_u_prev[0] = u_prev
+            self.in_prev_idx[0] = prev_idx
+        else:
+            self.in_x0[...] = np.asarray(x0, dtype=np.float64).reshape(self.n_env, 4)
+            self.in_u_prev[...] = np.asarray(u_prev, dtype=np.float64).reshape(self.n_env, self.T, 2)
+            self.in_prev_idx[...] = np.asarray(prev_idx, dtype=np.int64).reshape(self.n_env)
         self.in_step[0] = self.step_counter
 
     def step(self, x0, u_prev, prev_idx, eps=None):

@@ -135,8 +135,30 @@ bool pick_const_window(const MppiConfig* c) {
 // (every SM sub-partition runs a whole number of warps).  Model: CTAs of 4 warps (one per sub-partition),
 // `per_sm` resident CTAs per SM; full waves cost per_sm warp-times each, the last partial wave
 // ceil(rest / SMs) warp-times; a warp-time is proportional to ns (x 1.03 for ns = 1).  Pick the cheaper.
+// ns = 0 selects the BALANCED kernel (certified kernels only): one wave of CTAs, the warp-samples dealt evenly to the
+// warps (see mppi_rollout_sm100a).  It is used while a warp's share stays small — shards of one to a few waves, where
+// the wave-by-wave kernels end in a last wave at low occupancy (MPPI_BALANCED_MAX_SHARE overrides the limit,
+// 0 switches it off; A/B on B200: profiles/r2s2_ab_balanced.txt).
+#ifndef MPPI_BALANCED_MAX_SHARE
+#define MPPI_BALANCED_MAX_SHARE 8
+#endif
+int balanced_threads(const MppiConfig* c, int sm, int* ctas_per_env);
 int pick_ns(const MppiConfig* c, int sm) {
-    if (const char* f = getenv("MPPI_NS")) { const int v = atoi(f); if (v == 1 || v == 2) return v; }
+    if (const char* f = getenv("MPPI_NS")) {
+        const int v = atoi(f); int g = 0;
+        if (v == 1 || v == 2 || (v == 0 && certified_kernels(c) && balanced_threads(c, sm, &g) > 0)) return v;
+    }
+    if (certified_kernels(c)) {
+        int max_share = MPPI_BALANCED_MAX_SHARE;
+        if (const char* f = getenv("MPPI_BALANCED_MAX_SHARE")) max_share = atoi(f);
+        int g = 0;
+        const int thr = balanced_threads(c, sm, &g);
+        if (thr > 0 && max_share > 0) {
+            const long long nws = ((long long)c->K_local + 31) / 32, warps = (long long)g * (thr / 32);
+            // more than one warp-sample for some warp (else the one-sample kernel is the same thing), at most max_share
+            if (nws > warps && nws <= warps * max_share) return 0;
+        }
+    }
     const bool cw = pick_const_window(c);
     double best_cost = 0.0; int best = 1;
     for (int ns = 1; ns <= 2; ++ns) {
@@ -152,18 +174,43 @@ int pick_ns(const MppiConfig* c, int sm) {
     return best;
 }
 
+// CTA shape of the balanced kernel: `thr` threads per CTA and *ctas_per_env CTAs per environment such that all CTAs
+// of all environments are resident at once (MPPI_ROLL_MIN_BLOCKS_CERT CTAs of 128 threads per SM, i.e. 20 warps).
+// Of 128 / 64 / 32 threads the shape that fills most warp slots wins (ties: the larger CTA).  0: does not fit.
+int balanced_threads(const MppiConfig* c, int sm, int* ctas_per_env) {
+    const long long nws = ((long long)c->K_local + 31) / 32;
+    int forced = 0;
+    if (const char* f = getenv("MPPI_ROLL_THREADS")) { const int v = atoi(f); if (v == 32 || v == 64 || v == 128) forced = v; }
+    int best_thr = 0; long long best_warps = 0; int best_g = 0;
+    for (int thr = 128; thr >= 32; thr /= 2) {
+        if (forced && thr != forced) continue;
+        const int wpb = thr / 32;
+        const long long slots = (long long)sm * MPPI_ROLL_MIN_BLOCKS_CERT * (128 / thr);
+        long long g = slots / c->n_env;
+        const long long useful = (nws + wpb - 1) / wpb;
+        if (g > useful) g = useful;
+        if (g < 1) continue;
+        const long long warps = g * wpb;                     // per environment
+        if (warps > best_warps) { best_warps = warps; best_thr = thr; best_g = (int)g; }
+    }
+    *ctas_per_env = best_g;
+    return best_thr;
+}
+
 // Threads per CTA of the rollout kernel: 128, or fewer for small shards, where finer CTAs spread more evenly over
 // the SMs (MPPI_ROLL_THREADS overrides; A/B in profiles/r2_variants.md).
 int pick_roll_threads(const MppiConfig* c, int sm) {
+    if (pick_ns(c, sm) == 0) { int g; return balanced_threads(c, sm, &g); }
     if (const char* f = getenv("MPPI_ROLL_THREADS")) { const int v = atoi(f); if (v == 32 || v == 64 || v == 128) return v; }
-    (void)c; (void)sm;
     return kRollThreads;
 }
 
 void grid_sizes(const MppiConfig* c, int sm, int* g_roll, int* g_soft, int* g_wsum) {
     const int K = c->K_local;
     const int ns = pick_ns(c, sm), thr = pick_roll_threads(c, sm);
-    int gr = (K + thr * ns - 1) / (thr * ns);
+    int gr;
+    if (ns == 0) balanced_threads(c, sm, &gr);
+    else gr = (K + thr * ns - 1) / (thr * ns);
     if (gr > 32768) gr = 32768;
     *g_roll = gr;
     int gs = (K + kSoftThreads * 4 - 1) / (kSoftThreads * 4);
@@ -201,7 +248,8 @@ void carve(const MppiConfig* c, int sm, Workspace* w) {
     w->off_loop = take(sizeof(LoopParams));
     w->off_eta_fused = take(E * g_wsum * sizeof(double));
     w->off_tickets = take(E * sizeof(unsigned int));
-    w->off_seq = take(2 * sizeof(unsigned long long));       // [0] step sequence number, [1] exchange status
+    // [0] step sequence number, [1] exchange status, then one 32-bit minimum-cost key per environment
+    w->off_seq = take(2 * sizeof(unsigned long long) + E * sizeof(unsigned int));
     w->off_stats = take(4 * sizeof(unsigned long long));     // warp-lookups: [0] answered by an end test, [1] all, [2] by a certified triple
     // window tables + certificates of every window start of the path (2.4 KB per waypoint), built by
     // mppi_set_ref_path(); paths beyond kWinTableMaxRows build the window on the spot in every step instead
@@ -348,6 +396,7 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
         const bool ns2 = h->ns == 2, f1 = (dc.flags & MPPI_FLAG_DYNAMICS_F1) != 0;
         const bool cert = certified_kernels(&h->cfg), jl = h->cfg.joint_limit_weight > 0.0;
         unsigned long long* stats = (unsigned long long*)(ws + h->ws.off_stats);
+        unsigned int* rho_key = (unsigned int*)(ws + h->ws.off_seq + 2 * sizeof(unsigned long long));
         const float* eps_arg = ph ? nullptr : eps_dev;
         // Programmatic dependent launch: the rollout CTAs are scheduled while the prepare kernel still runs and wait
         // (griddepcontrol.wait) just before they read the step block — the launch latency leaves the critical path.
@@ -359,9 +408,9 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
         lc.gridDim = grid; lc.blockDim = dim3(h->roll_threads); lc.dynamicSmemBytes = h->roll_smem; lc.stream = s;
         lc.attrs = pdl_attr; lc.numAttrs = (h->pdl && !h->const_window && !timed) ? 1 : 0;
 #define MPPI_ROLL(NOISE, CW, NS_, DYN, CERT) do { \
-        if (CERT && DYN == 0 && jl) CU(h, cudaLaunchKernelEx(&lc, mppi_rollout_sm100a<NOISE, false, NS_, 0, true, true>, dc, step_ctr, (const char*)step_blocks, eps_arg, S, bmin, stats)); \
-        else CU(h, cudaLaunchKernelEx(&lc, mppi_rollout_sm100a<NOISE, CW, NS_, DYN, CERT>, dc, step_ctr, (const char*)step_blocks, eps_arg, S, bmin, stats)); } while (0)
-#define MPPI_ROLL_NS(NOISE, CW, DYN, CERT) do { if (ns2) MPPI_ROLL(NOISE, CW, 2, DYN, CERT); else MPPI_ROLL(NOISE, CW, 1, DYN, CERT); } while (0)
+        if (CERT && DYN == 0 && jl) CU(h, cudaLaunchKernelEx(&lc, mppi_rollout_sm100a<NOISE, false, NS_, 0, true, true>, dc, step_ctr, (const char*)step_blocks, eps_arg, S, bmin, stats, rho_key)); \
+        else CU(h, cudaLaunchKernelEx(&lc, mppi_rollout_sm100a<NOISE, CW, NS_, DYN, CERT>, dc, step_ctr, (const char*)step_blocks, eps_arg, S, bmin, stats, rho_key)); } while (0)
+#define MPPI_ROLL_NS(NOISE, CW, DYN, CERT) do { if (ns2) MPPI_ROLL(NOISE, CW, 2, DYN, CERT); else if (CERT && h->ns == 0) MPPI_ROLL(NOISE, false, 0, DYN, true); else MPPI_ROLL(NOISE, CW, 1, DYN, CERT); } while (0)
 #define MPPI_ROLL_NOISE(CW, DYN, CERT) do { if (ph) MPPI_ROLL_NS(0, CW, DYN, CERT); else MPPI_ROLL_NS(1, CW, DYN, CERT); } while (0)
         if (f1) MPPI_ROLL_NOISE(false, 1, true);
         else if (cert) MPPI_ROLL_NOISE(false, 0, true);
@@ -376,11 +425,13 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
     NvtxRange r_w(use_px ? "mppi.weights+sum+exchange" : "mppi.weights+sum");
     if (noise_mode == MPPI_NOISE_PHILOX) {
         // fused: soft-min weights + weighted sum + this GPU's partial triple
-        // 4096 samples per block for large K; small K is latency bound: up to 64 blocks of >= 512 samples
-        int g = (dc.K_local + 4095) / 4096;
+        // 2048 samples per block for large K (rows of blocks without a non-zero weight are never read back, so many
+        // blocks cost nothing); small K is latency bound: up to 64 blocks of >= 512 samples
+        int g = (dc.K_local + kWsumSamplesPerBlock - 1) / kWsumSamplesPerBlock;
         const int g_small = (dc.K_local + 511) / 512 < 64 ? (dc.K_local + 511) / 512 : 64;
         if (g < g_small) g = g_small;
         if (g > dc.g_wsum) g = dc.g_wsum;
+        if (g > kWsumMaxBlocks) g = kWsumMaxBlocks;
         const size_t sm = (size_t)(kWsumThreads / 32) * ((dc.T + 1) / 2) * sizeof(float4);
         cudaLaunchAttribute pdl_attr[1];
         pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -388,7 +439,8 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
         cudaLaunchConfig_t lc = {};
         lc.gridDim = dim3(g, dc.n_env); lc.blockDim = dim3(kWsumThreads); lc.dynamicSmemBytes = sm; lc.stream = s;
         lc.attrs = pdl_attr; lc.numAttrs = (h->pdl && !timed) ? 1 : 0;      // (timed: an event record sits in between)
-        CU(h, cudaLaunchKernelEx(&lc, mppi_softmin_wsum_philox_sm100a, dc, step_ctr, (const float*)S, (const float*)bmin, w,
+        CU(h, cudaLaunchKernelEx(&lc, mppi_softmin_wsum_philox_sm100a, dc, step_ctr, (const float*)S,
+                                 (const unsigned int*)(ws + h->ws.off_seq + 2 * sizeof(unsigned long long)), w,
                                  (double*)(ws + h->ws.off_eta_fused), v_part, (unsigned int*)(ws + h->ws.off_tickets), rho,
                                  partial_dev, use_px ? h->px : PeerExchange{}, dio, o.fuse_finalize ? 1 : 0));
         if (timed) { CU(h, cudaEventRecord(h->tev[3], s)); CU(h, cudaEventRecord(h->tev[4], s)); }

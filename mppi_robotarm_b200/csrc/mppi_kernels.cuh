@@ -61,6 +61,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 
+// Order-preserving map float -> uint32 (radix-sort key): the rollout CTAs fold their minima into ONE word per
+// environment with atomicMin (min is order-independent, so the result is deterministic); 0xffffffff = "no finite cost".
+__device__ __forceinline__ unsigned int min_key(float v) {
+    const unsigned int b = __float_as_uint(v);
+    return b ^ ((unsigned int)((int)b >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float min_key_decode(unsigned int k) {
+    if (k == 0xffffffffu) return INFINITY;
+    return __uint_as_float(k ^ (((k >> 31) - 1u) | 0x80000000u));
+}
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -433,6 +443,7 @@ __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, 
     pdl_launch_dependents();                      // the rollout CTAs may be scheduled now (they wait before reading)
     const int e = blockIdx.x, lane = threadIdx.x, T = cfg.T;
     if (e == 0 && lane == 0) *seq += 1ull;        // step sequence number, read by every later kernel of the step
+    if (lane == 0) ((unsigned int*)(seq + 2))[e] = 0xffffffffu;   // this step's minimum cost: no finite cost seen yet
     const bool zx = io.host_in != nullptr && (pull & 1), zc = io.host_in != nullptr && (pull & 2);
     const ptrdiff_t back = zc ? io.in_delta : 0;  // zero-copy: read the pinned block instead of the mirror
     const double* sx = (const double*)((const char*)(io.x0 + 4 * e) - (zx ? io.in_delta : 0));
@@ -628,12 +639,58 @@ __device__ __forceinline__ void win_load(WinTable& w, const StepBlockView& sb) {
 __device__ __forceinline__ void win_load(WinRegs& w, const StepBlockView& sb) { w.load(sb.win); }
 __device__ __forceinline__ void win_load(WinConst& w, const StepBlockView& sb) { w.load(sb.win); }
 
+// One pass of NS samples per thread: sample s of the lane is k0 + s * stride (a padding sample past the end recomputes
+// the last one; its result is not stored).  Returns the smallest finite cost of the lane's samples.
+template <int NOISE, int NS, int DYN, bool JL, class Win>
+__device__ __forceinline__ float roll_pass(const DevCfg& cfg, const uint64_t* __restrict__ step_ctr, int e, int k0, int stride,
+                                           const StepHeader& hd, const Win& win, const WinCert& cert, const StepBlockView& sb,
+                                           const float* __restrict__ eps, float* __restrict__ S_out, LookupStats& hits) {
+    float um[NS], S[NS];
+    int kl[NS];
+    const int T = cfg.T;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        kl[s] = min(k0 + s * stride, cfg.K_local - 1);
+        um[s] = (cfg.k_offset + kl[s]) < cfg.n_exploit ? 1.0f : 0.0f;
+        asm volatile("" : "+f"(um[s]));            // keep it in a register: not re-derived in every horizon step
+    }
+    if (NOISE == 0) {
+        PhiloxNoise nz[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            nz[s].nc = cfg.noise; nz[s].nc.step = (uint32_t)(*step_ctr); nz[s].env = (uint32_t)e;
+            nz[s].k = (uint32_t)(cfg.k_offset + kl[s]);
+        }
+        rollout_cost_n<NS, DYN, JL>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
+    } else {
+        InjectedNoise nz[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) nz[s].row = (const float2*)eps + ((size_t)e * cfg.K_local + kl[s]) * T;
+        rollout_cost_n<NS, DYN, JL>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
+    }
+    float tmin = INFINITY;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        if (k0 + s * stride < cfg.K_local) {
+            S_out[(size_t)e * cfg.K_local + kl[s]] = S[s];
+            if (finite_(S[s])) tmin = fminf(tmin, S[s]);
+        }
+    }
+    return tmin;
+}
+
+// kNS = 2 / 1: samples per thread, grid = ceil(K / (threads * kNS)) CTAs per environment (the hardware hands CTAs out
+// wave after wave).  kNS = 0, "balanced": ONE wave of CTAs; the warp-samples (32 consecutive samples) of the
+// environment are dealt evenly to the warps of its CTAs, and each warp runs its share as passes of two samples per
+// thread plus, for an odd share, one pass of one.  For shards of one to a few waves this replaces a last wave at
+// low occupancy (a 131 072-sample shard is 1.38 waves of the one-sample kernel) by warps that all finish together.
+// Which lanes share a warp changes, results do not (the lookups return the same row on every path).
 template <int NOISE, bool CONSTWIN, int kNS, int DYN = 0, bool CERT = true, bool JL = false>
 __global__ void __launch_bounds__(kRollThreads, CERT ? (kNS == 1 ? MPPI_ROLL_MIN_BLOCKS_CERT_NS1 : MPPI_ROLL_MIN_BLOCKS_CERT)
                                                      : (CONSTWIN ? MPPI_ROLL_MIN_BLOCKS_CONST : (kNS == 1 ? 3 : 2)))
 mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const char* __restrict__ step_blocks,
                     const float* __restrict__ eps, float* __restrict__ S_out, float* __restrict__ block_min,
-                    unsigned long long* __restrict__ search_stats) {
+                    unsigned long long* __restrict__ search_stats, unsigned int* __restrict__ rho_key) {
     extern __shared__ __align__(128) unsigned char smem_roll[];
     unsigned char* smem = smem_roll;
     __shared__ uint64_t bar;
@@ -658,42 +715,26 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
 
     float tmin = INFINITY;
     const int T = cfg.T;
-    // thread handles samples kl0 + s*blockDim.x (s < NS): consecutive lanes -> consecutive samples.  The block size
-    // is a launch parameter (128, or 64 for small shards: finer CTAs spread evenly over the SMs).
+    // The block size is a launch parameter (128, or less for small shards: finer CTAs spread evenly over the SMs).
     const int nthr = blockDim.x;
-    // The trip count is decided per WARP (its first lane), because the lookups vote across the warp.
-    for (int kw0 = blockIdx.x * (nthr * kNS) + (tid & ~31); kw0 < cfg.K_local; kw0 += gridDim.x * nthr * kNS) {
-        const int kl0 = kw0 + (tid & 31);
-        float um[kNS], S[kNS];
-        int kl[kNS];
-        lookups += kNS * T;
-#pragma unroll
-        for (int s = 0; s < kNS; ++s) {
-            // a padding sample past the end recomputes the last one (its result is not stored)
-            kl[s] = min(kl0 + s * nthr, cfg.K_local - 1);
-            um[s] = (cfg.k_offset + kl[s]) < cfg.n_exploit ? 1.0f : 0.0f;
-            asm volatile("" : "+f"(um[s]));            // keep it in a register: not re-derived in every horizon step
-        }
-        if (NOISE == 0) {
-            PhiloxNoise nz[kNS];
-#pragma unroll
-            for (int s = 0; s < kNS; ++s) {
-                nz[s].nc = cfg.noise; nz[s].nc.step = (uint32_t)(*step_ctr); nz[s].env = (uint32_t)e;
-                nz[s].k = (uint32_t)(cfg.k_offset + kl[s]);
-            }
-            rollout_cost_n<kNS, DYN, JL>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
-        } else {
-            InjectedNoise nz[kNS];
-#pragma unroll
-            for (int s = 0; s < kNS; ++s) nz[s].row = (const float2*)eps + ((size_t)e * cfg.K_local + kl[s]) * T;
-            rollout_cost_n<kNS, DYN, JL>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
-        }
-#pragma unroll
-        for (int s = 0; s < kNS; ++s) {
-            if (kl0 + s * nthr < cfg.K_local) {
-                S_out[(size_t)e * cfg.K_local + kl[s]] = S[s];
-                if (finite_(S[s])) tmin = fminf(tmin, S[s]);
-            }
+    if (kNS == 0) {
+        // balanced: warp w of the environment's gridDim.x * (nthr / 32) warps takes warp-samples [b0, b1)
+        const int nws = (cfg.K_local + 31) >> 5, wpb = nthr >> 5;
+        const long long nwarps = (long long)gridDim.x * wpb, w = (long long)blockIdx.x * wpb + (tid >> 5);
+        int ws = (int)(w * nws / nwarps);
+        int cnt = (int)((w + 1) * nws / nwarps) - ws;
+        lookups = cnt * T;
+        for (; cnt >= 2; cnt -= 2, ws += 2)
+            tmin = fminf(tmin, roll_pass<NOISE, 2, DYN, JL>(cfg, step_ctr, e, 32 * ws + (tid & 31), 32, hd, win, cert, sb, eps, S_out, hits));
+        if (cnt)
+            tmin = fminf(tmin, roll_pass<NOISE, 1, DYN, JL>(cfg, step_ctr, e, 32 * ws + (tid & 31), 32, hd, win, cert, sb, eps, S_out, hits));
+    } else {
+        constexpr int NS = kNS == 0 ? 1 : kNS;
+        // thread handles samples kl0 + s*blockDim.x (s < NS): consecutive lanes -> consecutive samples.
+        // The trip count is decided per WARP (its first lane), because the lookups vote across the warp.
+        for (int kw0 = blockIdx.x * (nthr * NS) + (tid & ~31); kw0 < cfg.K_local; kw0 += gridDim.x * nthr * NS) {
+            lookups += NS * T;
+            tmin = fminf(tmin, roll_pass<NOISE, NS, DYN, JL>(cfg, step_ctr, e, kw0 + (tid & 31), nthr, hd, win, cert, sb, eps, S_out, hits));
         }
     }
     tmin = warp_min(tmin);
@@ -709,6 +750,7 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
 #pragma unroll
         for (int i = 1; i < nthr / 32; ++i) m = fminf(m, red[i]);
         block_min[(size_t)e * gridDim.x + blockIdx.x] = m;
+        if (finite_(m)) atomicMin(rho_key + e, min_key(m));     // what the fused weight-sum kernel reads (one word, not g_roll)
     }
 }
 
@@ -852,6 +894,7 @@ struct FinalizeSmem {
     double raw[2 * MPPI_MAX_T_INTERNAL];
     double unew[2 * MPPI_MAX_T_INTERNAL];
     __align__(16) float tr[8 * MPPI_MAX_T_INTERNAL];    // optimal trajectory: (value, compensation) per state and step
+    __align__(8) float unf[2 * MPPI_MAX_T_INTERNAL];    // the updated sequence rounded to FP32 (inputs of that recurrence)
     double scale[64];
     double eta_s;
     int timed_out;
@@ -961,6 +1004,7 @@ __device__ __forceinline__ void finalize_env(const DevCfg& cfg, const DevIo& io,
         }
         const double u = io.u_prev[(size_t)e * 2 * T + c] + med;        // control.py:126
         sm.unew[c] = u;
+        sm.unf[c] = (float)u;      // (converted here, by all threads: an FP64->FP32 conversion stalls the serial chain below)
         out_store(io, io.w_eps_filt + (size_t)e * 2 * T + c, med);
         out_store(io, io.u_new + (size_t)e * 2 * T + c, u);
     }
@@ -991,8 +1035,9 @@ __device__ __forceinline__ void finalize_env(const DevCfg& cfg, const DevIo& io,
             ArmState st; arm_init(st, (float)x0[0], (float)x0[1], (float)x0[2], (float)x0[3]);
             for (int t = 0; t < T; ++t) {
                 const int tc = t == 0 ? T - 1 : t - 1;
-                if (cfg.flags & 32) arm_step<1>(st, cfg.arm, (float)sm.unew[2 * tc], (float)sm.unew[2 * tc + 1]);   // MPPI_FLAG_DYNAMICS_F1
-                else arm_step<0>(st, cfg.arm, (float)sm.unew[2 * tc], (float)sm.unew[2 * tc + 1]);
+                const float2 v = *(const float2*)(sm.unf + 2 * tc);
+                if (cfg.flags & 32) arm_step<1>(st, cfg.arm, v.x, v.y);   // MPPI_FLAG_DYNAMICS_F1
+                else arm_step<0>(st, cfg.arm, v.x, v.y);
                 float4* o = (float4*)(sm.tr + 8 * t);
                 o[0] = make_float4(st.q1, st.q2, st.d1, st.d2);
                 o[1] = make_float4(st.kq1, st.kq2, st.kd1, st.kd2);
@@ -1019,6 +1064,11 @@ __device__ __forceinline__ void finalize_env(const DevCfg& cfg, const DevIo& io,
 }
 
 constexpr int kPairSlots = MPPI_MAX_T_INTERNAL / 2 / 32;      // Philox calls per lane and sample (weight-sum kernel)
+#ifndef MPPI_WSUM_SAMPLES_PER_BLOCK
+#define MPPI_WSUM_SAMPLES_PER_BLOCK 2048                      // two batches of four cost loads per thread; 512 blocks at K = 2^20 are one wave (64 registers: 4 blocks per SM)
+#endif
+constexpr int kWsumSamplesPerBlock = MPPI_WSUM_SAMPLES_PER_BLOCK;
+constexpr int kWsumMaxBlocks = 4 * MPPI_MAX_T_INTERNAL;                        // blocks per environment of the fused weight-sum kernel (host: <= 8 per SM)
 
 // ================================================================================================
 // 4b. Philox mode, fused: soft-min weights + weighted noise sum + this GPU's partial triple in ONE
@@ -1031,17 +1081,23 @@ constexpr int kPairSlots = MPPI_MAX_T_INTERNAL / 2 / 32;      // Philox calls pe
 // ================================================================================================
 __global__ void __launch_bounds__(kWsumThreads)
 mppi_softmin_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const float* __restrict__ S,
-                                const float* __restrict__ block_min, float* __restrict__ w,
+                                const unsigned int* __restrict__ rho_key, float* __restrict__ w,
                                 double* __restrict__ eta_part, float* __restrict__ v_part,
                                 unsigned int* __restrict__ tickets, float* __restrict__ rho_out,
                                 double* __restrict__ partial, PeerExchange px, DevIo io, int fuse_finalize) {
     __shared__ FinalizeSmem fin;                              // (used by the last block only)
     extern __shared__ __align__(16) unsigned char smem_wsum[];
     float4* sh = (float4*)smem_wsum;                          // [warps][pairs]
-    __shared__ float redf[kWsumThreads / 32];
     __shared__ double redd[kWsumThreads / 32];
-    __shared__ float rho_s;
     __shared__ bool is_last;
+    __shared__ int n_live;
+    // scratch of the last block's cross-block sum, laid over arrays the final stage only fills afterwards:
+    // eta partials of this environment's blocks, and the blocks with a non-zero weight in block order
+    static_assert(offsetof(FinalizeSmem, unew) == offsetof(FinalizeSmem, raw) + sizeof(fin.raw), "raw and unew are adjacent");
+    static_assert(kWsumMaxBlocks * sizeof(double) <= sizeof(fin.raw) + sizeof(fin.unew), "eta partials fit");
+    static_assert(kWsumMaxBlocks * sizeof(unsigned short) <= sizeof(fin.tr), "row list fits");
+    double* eta_s = fin.raw;
+    unsigned short* live_rows = (unsigned short*)fin.tr;
     const int e = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_pairs = (cfg.T + 1) >> 1;
 #ifdef MPPI_PHASE_PRINT
@@ -1053,20 +1109,9 @@ mppi_softmin_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ct
     pdl_wait();                                   // the rollout kernel's costs and block minima are complete
     MPPI_PHASE(1);
     // rho = min over the rollout kernel's block minima
-    float m = INFINITY;
-    for (int i = tid; i < cfg.g_roll; i += kWsumThreads) m = fminf(m, block_min[(size_t)e * cfg.g_roll + i]);
-    m = warp_min(m);
-    if (lane == 0) redf[warp] = m;
-    __syncthreads();
-    if (tid == 0) {
-        float r = redf[0];
-#pragma unroll
-        for (int i = 1; i < kWsumThreads / 32; ++i) r = fminf(r, redf[i]);
-        rho_s = r;
-        if (blockIdx.x == 0) rho_out[e] = r;
-    }
-    __syncthreads();
-    const float rho = rho_s;
+    // rho = min S: the rollout CTAs folded their minima into one key per environment
+    const float rho = min_key_decode(__ldcg(rho_key + e));
+    if (tid == 0 && blockIdx.x == 0) rho_out[e] = rho;
     const float nil = (float)(-cfg.inv_lambda);
     NoiseCfg nc = cfg.noise; nc.step = (uint32_t)(*step_ctr);
     const float* Se = S + (size_t)e * cfg.K_local;
@@ -1151,20 +1196,37 @@ mppi_softmin_wsum_philox_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ct
     __threadfence();
     double* out = partial + (size_t)e * (2 + 2 * cfg.T);
     const int G = gridDim.x;
+    // Rows of blocks without a single non-zero weight (eta partial exactly 0: weights are >= 0) hold +0.0 in every
+    // column; adding them changes nothing, so only the other rows are read — in block order, like before.  With the
+    // reference's lambda the weights are winner-take-all: a handful of the G rows.
+    for (int i = tid; i < G; i += kWsumThreads) eta_s[i] = __ldcg(eta_part + (size_t)e * G + i);   // (all loads in flight at once)
+    __syncthreads();
     if (warp == 0) {
         double a = 0.0;
-        for (int i = lane; i < G; i += 32) a += __ldcg(eta_part + (size_t)e * G + i);
+        int n = 0;
+        for (int base = 0; base < G; base += 32) {
+            const int i = base + lane;
+            const double ep = i < G ? eta_s[i] : 0.0;
+            a += ep;
+            const unsigned mk = __ballot_sync(0xffffffffu, ep != 0.0);
+            if (ep != 0.0) live_rows[n + __popc(mk & ((1u << lane) - 1u))] = (unsigned short)i;
+            n += __popc(mk);
+        }
         a = warp_sum(a);
-        if (lane == 0) { out[0] = (double)rho; out[1] = a; tickets[e] = 0u; }
+        if (lane == 0) { out[0] = (double)rho; out[1] = a; tickets[e] = 0u; n_live = n; }
     }
-    // (G x 2T floats through ONE block: ~37 ns per row, bound by the number of requests a single SM keeps in flight —
-    //  9.5 us at K = 2^20 (G = 256), 3 us at the 8-GPU shard size; unrolled / batched / warp-split forms of this loop
-    //  measured the same or worse, profiles/r2_variants.md)
-    for (int c = tid; c < 2 * cfg.T; c += kWsumThreads) {
-        double a = 0.0;
-        const float* src = v_part + (size_t)e * cfg.g_wsum * 2 * cfg.T + c;
-        for (int b = 0; b < G; ++b) a += (double)__ldcg(src + (size_t)b * 2 * cfg.T);
-        out[2 + c] = a;
+    __syncthreads();
+    // (a row costs ~37 ns through ONE block — bound by the number of requests a single SM keeps in flight: 9.5 us for
+    //  all G = 256 rows at K = 2^20; unrolled / batched / warp-split forms of this loop measured the same or worse,
+    //  profiles/r2_variants.md)
+    {
+        const int nl = n_live;
+        for (int c = tid; c < 2 * cfg.T; c += kWsumThreads) {
+            double a = 0.0;
+            const float* src = v_part + (size_t)e * cfg.g_wsum * 2 * cfg.T + c;
+            for (int b = 0; b < nl; ++b) a += (double)__ldcg(src + (size_t)live_rows[b] * 2 * cfg.T);
+            out[2 + c] = a;
+        }
     }
     MPPI_PHASE(4);
     if (px.world > 0) px_put(px, out, cfg.n_env, e, 2 + 2 * cfg.T);   // fused exchange: triple -> every peer

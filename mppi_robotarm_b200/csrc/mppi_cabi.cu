@@ -135,30 +135,8 @@ bool pick_const_window(const MppiConfig* c) {
 // (every SM sub-partition runs a whole number of warps).  Model: CTAs of 4 warps (one per sub-partition),
 // `per_sm` resident CTAs per SM; full waves cost per_sm warp-times each, the last partial wave
 // ceil(rest / SMs) warp-times; a warp-time is proportional to ns (x 1.03 for ns = 1).  Pick the cheaper.
-// ns = 0 selects the BALANCED kernel (certified kernels only): one wave of CTAs, the warp-samples dealt evenly to the
-// warps (see mppi_rollout_sm100a).  It is used while a warp's share stays small — shards of one to a few waves, where
-// the wave-by-wave kernels end in a last wave at low occupancy (MPPI_BALANCED_MAX_SHARE overrides the limit,
-// 0 switches it off; A/B on B200: profiles/r2s2_ab_balanced.txt).
-#ifndef MPPI_BALANCED_MAX_SHARE
-#define MPPI_BALANCED_MAX_SHARE 8
-#endif
-int balanced_threads(const MppiConfig* c, int sm, int* ctas_per_env);
 int pick_ns(const MppiConfig* c, int sm) {
-    if (const char* f = getenv("MPPI_NS")) {
-        const int v = atoi(f); int g = 0;
-        if (v == 1 || v == 2 || (v == 0 && certified_kernels(c) && balanced_threads(c, sm, &g) > 0)) return v;
-    }
-    if (certified_kernels(c)) {
-        int max_share = MPPI_BALANCED_MAX_SHARE;
-        if (const char* f = getenv("MPPI_BALANCED_MAX_SHARE")) max_share = atoi(f);
-        int g = 0;
-        const int thr = balanced_threads(c, sm, &g);
-        if (thr > 0 && max_share > 0) {
-            const long long nws = ((long long)c->K_local + 31) / 32, warps = (long long)g * (thr / 32);
-            // more than one warp-sample for some warp (else the one-sample kernel is the same thing), at most max_share
-            if (nws > warps && nws <= warps * max_share) return 0;
-        }
-    }
+    if (const char* f = getenv("MPPI_NS")) { const int v = atoi(f); if (v == 1 || v == 2) return v; }
     const bool cw = pick_const_window(c);
     double best_cost = 0.0; int best = 1;
     for (int ns = 1; ns <= 2; ++ns) {
@@ -174,43 +152,18 @@ int pick_ns(const MppiConfig* c, int sm) {
     return best;
 }
 
-// CTA shape of the balanced kernel: `thr` threads per CTA and *ctas_per_env CTAs per environment such that all CTAs
-// of all environments are resident at once (MPPI_ROLL_MIN_BLOCKS_CERT CTAs of 128 threads per SM, i.e. 20 warps).
-// Of 128 / 64 / 32 threads the shape that fills most warp slots wins (ties: the larger CTA).  0: does not fit.
-int balanced_threads(const MppiConfig* c, int sm, int* ctas_per_env) {
-    const long long nws = ((long long)c->K_local + 31) / 32;
-    int forced = 0;
-    if (const char* f = getenv("MPPI_ROLL_THREADS")) { const int v = atoi(f); if (v == 32 || v == 64 || v == 128) forced = v; }
-    int best_thr = 0; long long best_warps = 0; int best_g = 0;
-    for (int thr = 128; thr >= 32; thr /= 2) {
-        if (forced && thr != forced) continue;
-        const int wpb = thr / 32;
-        const long long slots = (long long)sm * MPPI_ROLL_MIN_BLOCKS_CERT * (128 / thr);
-        long long g = slots / c->n_env;
-        const long long useful = (nws + wpb - 1) / wpb;
-        if (g > useful) g = useful;
-        if (g < 1) continue;
-        const long long warps = g * wpb;                     // per environment
-        if (warps > best_warps) { best_warps = warps; best_thr = thr; best_g = (int)g; }
-    }
-    *ctas_per_env = best_g;
-    return best_thr;
-}
-
 // Threads per CTA of the rollout kernel: 128, or fewer for small shards, where finer CTAs spread more evenly over
 // the SMs (MPPI_ROLL_THREADS overrides; A/B in profiles/r2_variants.md).
 int pick_roll_threads(const MppiConfig* c, int sm) {
-    if (pick_ns(c, sm) == 0) { int g; return balanced_threads(c, sm, &g); }
     if (const char* f = getenv("MPPI_ROLL_THREADS")) { const int v = atoi(f); if (v == 32 || v == 64 || v == 128) return v; }
+    (void)c; (void)sm;
     return kRollThreads;
 }
 
 void grid_sizes(const MppiConfig* c, int sm, int* g_roll, int* g_soft, int* g_wsum) {
     const int K = c->K_local;
     const int ns = pick_ns(c, sm), thr = pick_roll_threads(c, sm);
-    int gr;
-    if (ns == 0) balanced_threads(c, sm, &gr);
-    else gr = (K + thr * ns - 1) / (thr * ns);
+    int gr = (K + thr * ns - 1) / (thr * ns);
     if (gr > 32768) gr = 32768;
     *g_roll = gr;
     int gs = (K + kSoftThreads * 4 - 1) / (kSoftThreads * 4);
@@ -410,7 +363,7 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
 #define MPPI_ROLL(NOISE, CW, NS_, DYN, CERT) do { \
         if (CERT && DYN == 0 && jl) CU(h, cudaLaunchKernelEx(&lc, mppi_rollout_sm100a<NOISE, false, NS_, 0, true, true>, dc, step_ctr, (const char*)step_blocks, eps_arg, S, bmin, stats, rho_key)); \
         else CU(h, cudaLaunchKernelEx(&lc, mppi_rollout_sm100a<NOISE, CW, NS_, DYN, CERT>, dc, step_ctr, (const char*)step_blocks, eps_arg, S, bmin, stats, rho_key)); } while (0)
-#define MPPI_ROLL_NS(NOISE, CW, DYN, CERT) do { if (ns2) MPPI_ROLL(NOISE, CW, 2, DYN, CERT); else if (CERT && h->ns == 0) MPPI_ROLL(NOISE, false, 0, DYN, true); else MPPI_ROLL(NOISE, CW, 1, DYN, CERT); } while (0)
+#define MPPI_ROLL_NS(NOISE, CW, DYN, CERT) do { if (ns2) MPPI_ROLL(NOISE, CW, 2, DYN, CERT); else MPPI_ROLL(NOISE, CW, 1, DYN, CERT); } while (0)
 #define MPPI_ROLL_NOISE(CW, DYN, CERT) do { if (ph) MPPI_ROLL_NS(0, CW, DYN, CERT); else MPPI_ROLL_NS(1, CW, DYN, CERT); } while (0)
         if (f1) MPPI_ROLL_NOISE(false, 1, true);
         else if (cert) MPPI_ROLL_NOISE(false, 0, true);

@@ -460,6 +460,14 @@ __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, 
     const uint64_t stp = (zc && lane == 0 && e == 0) ? *(const uint64_t*)((const char*)io.step - back) : 0;
     const int n = cfg.n_ref_rows;
     p = max(0, min(p, n - 1));
+    if (win_table != nullptr) {
+        // the new window starts at p .. p+29, almost always within a few rows of p: pull the tables of p .. p+3 into
+        // L2 now (76 lines of 128 B), so that the copy below — at the end of the kernel's latency chain — hits
+        for (int ln = lane; ln < (4 * kWinBytes + 127) / 128; ln += 32) {
+            const char* a = win_table + (size_t)p * kWinBytes + (size_t)ln * 128;
+            if (a < win_table + (size_t)n * kWinBytes) asm volatile("prefetch.global.L2 [%0];" :: "l"(a));
+        }
+    }
     // ---- (2) reference rows p .. p+63 (clamped), two per lane --------------------------------------
     const double4* ref4 = (const double4*)ref;
     const double4 r_lo = ref4[min(p + lane, n - 1)];
@@ -478,9 +486,17 @@ __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, 
         for (int i = 0; i < kTS; ++i) { const int t = lane + 32 * i; if (t < T) du[t] = uu[i]; }
     }
     // control.py:206-215 in FP64: end-effector, distances to the forward window, first arg-min
+    // (the two FP64 sincos are the longest arithmetic chain of this kernel: even lanes evaluate q1, odd lanes q1 + q2,
+    //  and neighbours swap — the same function on the same arguments, half the latency)
     double s1, c1, s12, c12;
-    sincos(q1, &s1, &c1);
-    sincos(q1 + q2, &s12, &c12);
+    {
+        const bool odd = (lane & 1) != 0;
+        double sa, ca;
+        sincos(odd ? q1 + q2 : q1, &sa, &ca);
+        const double sb = __shfl_xor_sync(0xffffffffu, sa, 1), cb = __shfl_xor_sync(0xffffffffu, ca, 1);
+        s1 = odd ? sb : sa; c1 = odd ? cb : ca;
+        s12 = odd ? sa : sb; c12 = odd ? ca : cb;
+    }
     const double x = cfg.cost_l1 * c1 + cfg.cost_l2 * c12;
     const double y = cfg.cost_l1 * s1 + cfg.cost_l2 * s12;
     double d = 1.0e300;
@@ -639,52 +655,6 @@ __device__ __forceinline__ void win_load(WinTable& w, const StepBlockView& sb) {
 __device__ __forceinline__ void win_load(WinRegs& w, const StepBlockView& sb) { w.load(sb.win); }
 __device__ __forceinline__ void win_load(WinConst& w, const StepBlockView& sb) { w.load(sb.win); }
 
-// One pass of NS samples per thread: sample s of the lane is k0 + s * stride (a padding sample past the end recomputes
-// the last one; its result is not stored).  Returns the smallest finite cost of the lane's samples.
-template <int NOISE, int NS, int DYN, bool JL, class Win>
-__device__ __forceinline__ float roll_pass(const DevCfg& cfg, const uint64_t* __restrict__ step_ctr, int e, int k0, int stride,
-                                           const StepHeader& hd, const Win& win, const WinCert& cert, const StepBlockView& sb,
-                                           const float* __restrict__ eps, float* __restrict__ S_out, LookupStats& hits) {
-    float um[NS], S[NS];
-    int kl[NS];
-    const int T = cfg.T;
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-        kl[s] = min(k0 + s * stride, cfg.K_local - 1);
-        um[s] = (cfg.k_offset + kl[s]) < cfg.n_exploit ? 1.0f : 0.0f;
-        asm volatile("" : "+f"(um[s]));            // keep it in a register: not re-derived in every horizon step
-    }
-    if (NOISE == 0) {
-        PhiloxNoise nz[NS];
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            nz[s].nc = cfg.noise; nz[s].nc.step = (uint32_t)(*step_ctr); nz[s].env = (uint32_t)e;
-            nz[s].k = (uint32_t)(cfg.k_offset + kl[s]);
-        }
-        rollout_cost_n<NS, DYN, JL>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
-    } else {
-        InjectedNoise nz[NS];
-#pragma unroll
-        for (int s = 0; s < NS; ++s) nz[s].row = (const float2*)eps + ((size_t)e * cfg.K_local + kl[s]) * T;
-        rollout_cost_n<NS, DYN, JL>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
-    }
-    float tmin = INFINITY;
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-        if (k0 + s * stride < cfg.K_local) {
-            S_out[(size_t)e * cfg.K_local + kl[s]] = S[s];
-            if (finite_(S[s])) tmin = fminf(tmin, S[s]);
-        }
-    }
-    return tmin;
-}
-
-// kNS = 2 / 1: samples per thread, grid = ceil(K / (threads * kNS)) CTAs per environment (the hardware hands CTAs out
-// wave after wave).  kNS = 0, "balanced": ONE wave of CTAs; the warp-samples (32 consecutive samples) of the
-// environment are dealt evenly to the warps of its CTAs, and each warp runs its share as passes of two samples per
-// thread plus, for an odd share, one pass of one.  For shards of one to a few waves this replaces a last wave at
-// low occupancy (a 131 072-sample shard is 1.38 waves of the one-sample kernel) by warps that all finish together.
-// Which lanes share a warp changes, results do not (the lookups return the same row on every path).
 template <int NOISE, bool CONSTWIN, int kNS, int DYN = 0, bool CERT = true, bool JL = false>
 __global__ void __launch_bounds__(kRollThreads, CERT ? (kNS == 1 ? MPPI_ROLL_MIN_BLOCKS_CERT_NS1 : MPPI_ROLL_MIN_BLOCKS_CERT)
                                                      : (CONSTWIN ? MPPI_ROLL_MIN_BLOCKS_CONST : (kNS == 1 ? 3 : 2)))
@@ -715,26 +685,42 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
 
     float tmin = INFINITY;
     const int T = cfg.T;
-    // The block size is a launch parameter (128, or less for small shards: finer CTAs spread evenly over the SMs).
+    // thread handles samples kl0 + s*blockDim.x (s < NS): consecutive lanes -> consecutive samples.  The block size
+    // is a launch parameter (128, or 64 for small shards: finer CTAs spread evenly over the SMs).
     const int nthr = blockDim.x;
-    if (kNS == 0) {
-        // balanced: warp w of the environment's gridDim.x * (nthr / 32) warps takes warp-samples [b0, b1)
-        const int nws = (cfg.K_local + 31) >> 5, wpb = nthr >> 5;
-        const long long nwarps = (long long)gridDim.x * wpb, w = (long long)blockIdx.x * wpb + (tid >> 5);
-        int ws = (int)(w * nws / nwarps);
-        int cnt = (int)((w + 1) * nws / nwarps) - ws;
-        lookups = cnt * T;
-        for (; cnt >= 2; cnt -= 2, ws += 2)
-            tmin = fminf(tmin, roll_pass<NOISE, 2, DYN, JL>(cfg, step_ctr, e, 32 * ws + (tid & 31), 32, hd, win, cert, sb, eps, S_out, hits));
-        if (cnt)
-            tmin = fminf(tmin, roll_pass<NOISE, 1, DYN, JL>(cfg, step_ctr, e, 32 * ws + (tid & 31), 32, hd, win, cert, sb, eps, S_out, hits));
-    } else {
-        constexpr int NS = kNS == 0 ? 1 : kNS;
-        // thread handles samples kl0 + s*blockDim.x (s < NS): consecutive lanes -> consecutive samples.
-        // The trip count is decided per WARP (its first lane), because the lookups vote across the warp.
-        for (int kw0 = blockIdx.x * (nthr * NS) + (tid & ~31); kw0 < cfg.K_local; kw0 += gridDim.x * nthr * NS) {
-            lookups += NS * T;
-            tmin = fminf(tmin, roll_pass<NOISE, NS, DYN, JL>(cfg, step_ctr, e, kw0 + (tid & 31), nthr, hd, win, cert, sb, eps, S_out, hits));
+    // The trip count is decided per WARP (its first lane), because the lookups vote across the warp.
+    for (int kw0 = blockIdx.x * (nthr * kNS) + (tid & ~31); kw0 < cfg.K_local; kw0 += gridDim.x * nthr * kNS) {
+        const int kl0 = kw0 + (tid & 31);
+        float um[kNS], S[kNS];
+        int kl[kNS];
+        lookups += kNS * T;
+#pragma unroll
+        for (int s = 0; s < kNS; ++s) {
+            // a padding sample past the end recomputes the last one (its result is not stored)
+            kl[s] = min(kl0 + s * nthr, cfg.K_local - 1);
+            um[s] = (cfg.k_offset + kl[s]) < cfg.n_exploit ? 1.0f : 0.0f;
+            asm volatile("" : "+f"(um[s]));            // keep it in a register: not re-derived in every horizon step
+        }
+        if (NOISE == 0) {
+            PhiloxNoise nz[kNS];
+#pragma unroll
+            for (int s = 0; s < kNS; ++s) {
+                nz[s].nc = cfg.noise; nz[s].nc.step = (uint32_t)(*step_ctr); nz[s].env = (uint32_t)e;
+                nz[s].k = (uint32_t)(cfg.k_offset + kl[s]);
+            }
+            rollout_cost_n<kNS, DYN, JL>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
+        } else {
+            InjectedNoise nz[kNS];
+#pragma unroll
+            for (int s = 0; s < kNS; ++s) nz[s].row = (const float2*)eps + ((size_t)e * cfg.K_local + kl[s]) * T;
+            rollout_cost_n<kNS, DYN, JL>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
+        }
+#pragma unroll
+        for (int s = 0; s < kNS; ++s) {
+            if (kl0 + s * nthr < cfg.K_local) {
+                S_out[(size_t)e * cfg.K_local + kl[s]] = S[s];
+                if (finite_(S[s])) tmin = fminf(tmin, S[s]);
+            }
         }
     }
     tmin = warp_min(tmin);
@@ -894,7 +880,6 @@ struct FinalizeSmem {
     double raw[2 * MPPI_MAX_T_INTERNAL];
     double unew[2 * MPPI_MAX_T_INTERNAL];
     __align__(16) float tr[8 * MPPI_MAX_T_INTERNAL];    // optimal trajectory: (value, compensation) per state and step
-    __align__(8) float unf[2 * MPPI_MAX_T_INTERNAL];    // the updated sequence rounded to FP32 (inputs of that recurrence)
     double scale[64];
     double eta_s;
     int timed_out;
@@ -943,20 +928,24 @@ __device__ __forceinline__ void finalize_env(const DevCfg& cfg, const DevIo& io,
     const bool skip = sm.timed_out != 0;
     const size_t stride_rank = (size_t)cfg.n_env * (2 + 2 * T);
     const double* g0 = gathered + (size_t)e * (2 + 2 * T);
-    if (tid == 0) {
-        double rho = g0[0];
-        for (int g = 1; g < world; ++g) rho = fmin(rho, g0[g * stride_rank]);
-        double eta = 0.0;
-        for (int g = 0; g < world; ++g) {
-            // a shard with no finite cost reports rho_g = +inf and eta_g = 0
-            const double sg = exp(-(g0[g * stride_rank] - rho) * cfg.inv_lambda);
-            sm.scale[g] = sg;
-            eta += sg * g0[g * stride_rank + 1];
+    if (tid < 32) {
+        // one lane per rank: its minimum, and its rescaling factor (an FP64 exp each — side by side, not one after the
+        // other); lane 0 then adds the weight sums in rank order
+        double rho = __longlong_as_double(0x7ff0000000000000ll);
+        for (int g = tid; g < world; g += 32) rho = fmin(rho, g0[g * stride_rank]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rho = fmin(rho, __shfl_xor_sync(0xffffffffu, rho, o));
+        // a shard with no finite cost reports rho_g = +inf and eta_g = 0
+        for (int g = tid; g < world; g += 32) sm.scale[g] = exp(-(g0[g * stride_rank] - rho) * cfg.inv_lambda);
+        __syncwarp();
+        if (tid == 0) {
+            double eta = 0.0;
+            for (int g = 0; g < world; ++g) eta += sm.scale[g] * g0[g * stride_rank + 1];
+            sm.eta_s = eta;
+            const double nan = __longlong_as_double(0x7ff8000000000000ll);
+            out_store(io, io.rho + e, skip ? nan : rho); out_store(io, io.eta + e, skip ? nan : eta);
+            out_store(io, io.status + e, skip ? 1 : 0);
         }
-        sm.eta_s = eta;
-        const double nan = __longlong_as_double(0x7ff8000000000000ll);
-        out_store(io, io.rho + e, skip ? nan : rho); out_store(io, io.eta + e, skip ? nan : eta);
-        out_store(io, io.status + e, skip ? 1 : 0);
     }
     __syncthreads();
     for (int c = tid; c < 2 * T; c += blockDim.x) {
@@ -1004,7 +993,6 @@ __device__ __forceinline__ void finalize_env(const DevCfg& cfg, const DevIo& io,
         }
         const double u = io.u_prev[(size_t)e * 2 * T + c] + med;        // control.py:126
         sm.unew[c] = u;
-        sm.unf[c] = (float)u;      // (converted here, by all threads: an FP64->FP32 conversion stalls the serial chain below)
         out_store(io, io.w_eps_filt + (size_t)e * 2 * T + c, med);
         out_store(io, io.u_new + (size_t)e * 2 * T + c, u);
     }
@@ -1035,9 +1023,8 @@ __device__ __forceinline__ void finalize_env(const DevCfg& cfg, const DevIo& io,
             ArmState st; arm_init(st, (float)x0[0], (float)x0[1], (float)x0[2], (float)x0[3]);
             for (int t = 0; t < T; ++t) {
                 const int tc = t == 0 ? T - 1 : t - 1;
-                const float2 v = *(const float2*)(sm.unf + 2 * tc);
-                if (cfg.flags & 32) arm_step<1>(st, cfg.arm, v.x, v.y);   // MPPI_FLAG_DYNAMICS_F1
-                else arm_step<0>(st, cfg.arm, v.x, v.y);
+                if (cfg.flags & 32) arm_step<1>(st, cfg.arm, (float)sm.unew[2 * tc], (float)sm.unew[2 * tc + 1]);   // MPPI_FLAG_DYNAMICS_F1
+                else arm_step<0>(st, cfg.arm, (float)sm.unew[2 * tc], (float)sm.unew[2 * tc + 1]);
                 float4* o = (float4*)(sm.tr + 8 * t);
                 o[0] = make_float4(st.q1, st.q2, st.d1, st.d2);
                 o[1] = make_float4(st.kq1, st.kq2, st.kd1, st.kd2);

@@ -852,67 +852,3 @@ def test_device_built_certificates_are_sound(paths, emul):
         eng.close()
     assert n_armed > 40 and n_certified > 500000
 
-
-# ---------------------------------------------------------------------------------------------
-# Balanced rollout kernel (one wave of CTAs, warp-samples dealt evenly to the warps)
-# ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("K,T,s,noise", [
-    (100003, 12, 500, "philox"),       # 3126 warp-samples on 2960 warps: one or two each, partial last warp
-    (300000, 8, 1000, "philox"),       # three or four each: passes of two samples per thread plus a pass of one
-    (5000, 30, 100, "injected"),       # fewer warp-samples than warp slots: the grid shrinks to one each
-    (131072, 10, 0, "injected"),       # the 8-GPU shard size, arm at rest (far-field wedges), noise read from HBM
-])
-def test_balanced_rollout_kernel_is_bit_identical(paths, monkeypatch, K, T, s, noise):
-    """MPPI_NS=0 deals the samples to the warps differently (which lanes share a warp, and hence the warp votes
-    of the lookups, change); costs, weights and the update must be the very same floats as with one or two
-    samples per thread handed out wave by wave."""
-    with np.load(cases.HERE + "/closed_loop_c1.npz") as z:
-        cl = {k: z[k] for k in z.files}
-    x0, u, p = _tracking_state(cl, s, T) if s else (cases.X0, _u0(T), 0)
-    out = {}
-    for ns in ("0", "1", "2"):
-        monkeypatch.setenv("MPPI_NS", ns)
-        eng = _engine(paths, K, T, search_stats=True)
-        eps = eng.philox_noise(step=0) if noise == "injected" else None
-        eng.step(x0, u, p, eps)
-        S, w = (t[0].cpu().numpy().copy() for t in eng.last_costs())
-        out[ns] = (S, w, eng.out_u_new[0].copy(), eng.out_opt_traj[0].copy(), float(eng.out_rho[0]), float(eng.out_eta[0]),
-                   eng.search_stats()["lookups"])
-        eng.close()
-    monkeypatch.delenv("MPPI_NS")
-    for ns in ("1", "2"):
-        for i in range(4):
-            assert np.array_equal(out["0"][i], out[ns][i]), f"output {i}: balanced kernel vs MPPI_NS={ns}"
-        assert out["0"][4] == out[ns][4] and out["0"][5] == out[ns][5]
-    assert np.all(np.isfinite(out["0"][0])) and out["0"][6] > 0
-
-
-def test_balanced_rollout_kernel_batched_environments(paths, monkeypatch):
-    """Several environments share the wave: each gets its own CTAs (own step block), 1-, 2- or 4-warp CTAs."""
-    from mppi_robotarm_b200.batched import BatchedMPPIController
-    with np.load(cases.HERE + "/closed_loop_c1.npz") as z:
-        cl = {k: z[k] for k in z.files}
-    ref = cases.ref_path_for(paths, "xydq_circle.txt")
-    T, K, steps = 16, 40000, (0, 100, 500, 1000, 1499, 700, 300)
-    kw = cases.run_py_kwargs(ref, K, T)
-    kw.pop("visualize_optimal_traj", None); kw.pop("visualze_sampled_trajs", None)
-    res = {}
-    for ns, thr in (("1", "128"), ("0", "128"), ("0", "64"), ("0", "32")):
-        monkeypatch.setenv("MPPI_NS", ns)
-        monkeypatch.setenv("MPPI_ROLL_THREADS", thr)
-        b = BatchedMPPIController(len(steps), **kw, seed=4)
-        xs, us, ps = [], [], []
-        for s in steps:
-            x0, u, p = _tracking_state(cl, s, T) if s else (cases.X0, _u0(T), 0)
-            xs.append(x0); us.append(u); ps.append(p)
-        b.u_prev[...] = np.array(us)
-        b.prev_waypoints_idx[...] = ps
-        b.calc_control_input(np.array(xs))
-        b.engine.download_state()
-        res[(ns, thr)] = (b.engine.last_costs()[0].cpu().numpy().copy(), b.engine.out_u_new.copy(), b.engine.out_rho.copy())
-        b.close()
-    monkeypatch.delenv("MPPI_NS"); monkeypatch.delenv("MPPI_ROLL_THREADS")
-    base = res[("1", "128")]
-    for key, val in res.items():
-        for i in range(3):
-            assert np.array_equal(base[i], val[i]), f"output {i} differs for MPPI_NS, threads = {key}"

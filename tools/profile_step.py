@@ -37,6 +37,9 @@ def main():
     if a.timing:                                   # first launches carry module load and graph set-up: keep them out
         for _ in range(3):
             eng.step(x0, u, p0, eps)
+        eng.set_timing(True)                       # (the timed path launches the final stage as its own kernel: warm that too)
+        for _ in range(2):
+            eng.step(x0, u, p0, eps)
         eng.search_stats(reset=True)
     eng.set_timing(a.timing)
     for _ in range(a.steps):

@@ -109,6 +109,8 @@ bool valid_cfg(const MppiConfig* c, const char** why) {
     if (c->max_ref_rows < 2) { *why = "max_ref_rows < 2"; return false; }
     if (!(c->param_lambda > 0.0)) { *why = "param_lambda must be > 0"; return false; }
     if (!(c->joint_limit_weight >= 0.0)) { *why = "joint_limit_weight must be >= 0"; return false; }
+    for (int i = 0; i < 4; ++i)        // the stage cost is evaluated on residuals scaled by sqrt(weight)
+        if (!(c->stage_cost_weight[i] >= 0.0) || !(c->stage_cost_weight[i] < 1e30)) { *why = "stage_cost_weight entries must be finite and >= 0"; return false; }
     if (c->joint_limit_weight > 0.0) {
         if (!(c->joint_limit_lo[0] <= c->joint_limit_hi[0]) || !(c->joint_limit_lo[1] <= c->joint_limit_hi[1])) {
             *why = "joint limits need lo <= hi"; return false;
@@ -232,11 +234,13 @@ void fill_dev_cfg(MppiHandle* h) {
     d.arm.G1a = (float)((m1 * lc1 + m2 * l1) * g);
     d.arm.G1b = (float)(m2 * lc2 * g);
     d.arm.dt = (float)c.delta_t;
+    d.arm.dtfix = arm_dtfix(c.delta_t);
     d.arm.L1 = (float)c.cost_l1; d.arm.L2 = (float)c.cost_l2;
     d.cost.s0 = (float)(c.stage_cost_weight[0] * 1e4); d.cost.s1 = (float)(c.stage_cost_weight[1] * 1e4);
     d.cost.s2 = (float)(c.stage_cost_weight[2] * 1e4); d.cost.s3 = (float)(c.stage_cost_weight[3] * 1e4);
     d.cost.t0 = (float)(c.terminal_cost_weight[0] * 1e4); d.cost.t1 = (float)(c.terminal_cost_weight[1] * 1e4);
     d.cost.t2 = (float)(c.terminal_cost_weight[2] * 1e4); d.cost.t3 = (float)(c.terminal_cost_weight[3] * 1e4);
+    cost_roots(d.cost);
     {   // joint limits: +-inf would turn into NaN in (q - hi)^2 * 0; clamp the bounds to a huge finite value
         auto lim = [](double v) { return (float)(v > 1e30 ? 1e30 : (v < -1e30 ? -1e30 : v)); };
         d.cost.jw = (float)(c.joint_limit_weight * 1e4);

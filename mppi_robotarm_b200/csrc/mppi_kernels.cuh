@@ -109,10 +109,10 @@ struct LoopParams {
 };
 
 struct StepBlockView {          // pointers into one environment's step block (global or shared)
-    StepHeader* hd; WinEntry* win; RefRow* rows; float4* pairs; WinCert* cert; RowRec* rec; EndWedges* wed; StepCtl* ctl;
+    StepHeader* hd; WinEntry* win; RefRow* rows; float4* pairs; WinCert* cert; RowRec* rec; EndWedges* wed; RefRow* srows; StepCtl* ctl;
 };
-// header + win + rows + pairs + certificate + row records + end wedges
-constexpr int kStepBlockFixed = 64 + 32 * kWindowPad + 16 * (kWindowPad / 2) + 64 + 32 * kWindowPad + 64;
+// header + win + rows + pairs + certificate + row records + end wedges + pre-scaled rows of the stage cost
+constexpr int kStepBlockFixed = 64 + 32 * kWindowPad + 16 * (kWindowPad / 2) + 64 + 32 * kWindowPad + 64 + 16 * kWindowPad;
 __host__ __device__ __forceinline__ StepBlockView view_step_block(void* base) {
     char* b = (char*)base;
     StepBlockView v;
@@ -123,6 +123,7 @@ __host__ __device__ __forceinline__ StepBlockView view_step_block(void* base) {
     v.cert = (WinCert*)(b + 64 + 32 * kWindowPad + 16 * (kWindowPad / 2));   // lookup certificate of the window
     v.rec = (RowRec*)(b + 64 + 32 * kWindowPad + 16 * (kWindowPad / 2) + 64);   // (a, b, c) + certificate of each row
     v.wed = (EndWedges*)(b + 64 + 32 * kWindowPad + 16 * (kWindowPad / 2) + 64 + 32 * kWindowPad);   // far-field wedges of the end rows
+    v.srows = (RefRow*)(b + kStepBlockFixed - 16 * kWindowPad);   // -sqrt(weight) * waypoint: stage_cost() of mppi_math.cuh
     v.ctl = (StepCtl*)(b + kStepBlockFixed);
     return v;
 }
@@ -397,6 +398,7 @@ __device__ __forceinline__ void write_window_tables(const double4& row, double o
     // the rollouts subtract the FP32 origin from the FP32 end-effector; rows are relative to
     // the FP64 origin — the difference (<= 6e-8) is common to all candidates of a lookup
     sb.win[lane] = w; sb.rows[lane] = r;
+    sb.srows[lane] = (lane < kWindow && p + lane < n) ? stage_row(cfg.cost, row.x - ox, row.y - oy, row.z, row.w) : r;
     {   // lookup certificate of the window (make_win_cert of mppi_math.cuh, one lane per row)
         const int nv = min(kWindow, n - p);
         if (lane < kWindow) { srow[lane][0] = row.x - ox; srow[lane][1] = row.y - oy; }
@@ -532,7 +534,8 @@ __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, 
         h.ox = (float)ox; h.oy = (float)oy;
         h.win_start = p; h.n_valid = min(kWindow, n - p);
         h.status = (p >= n - 1) ? 1 : 0;                     // control.py:76
-        for (int i = 0; i < 7; ++i) h.pad[i] = 0;
+        h.a1 = angle_fix(q1); h.a12 = angle_fix(q1 + q2);
+        for (int i = 0; i < 5; ++i) h.pad[i] = 0;
         *sb.hd = h;
         out_store(io, io.new_idx + e, p);
     }
@@ -708,12 +711,12 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
                 nz[s].nc = cfg.noise; nz[s].nc.step = (uint32_t)(*step_ctr); nz[s].env = (uint32_t)e;
                 nz[s].k = (uint32_t)(cfg.k_offset + kl[s]);
             }
-            rollout_cost_n<kNS, DYN, JL>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
+            rollout_cost_n<kNS, DYN, JL>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.srows, sb.ctl, T, um, nz, S, hits);
         } else {
             InjectedNoise nz[kNS];
 #pragma unroll
             for (int s = 0; s < kNS; ++s) nz[s].row = (const float2*)eps + ((size_t)e * cfg.K_local + kl[s]) * T;
-            rollout_cost_n<kNS, DYN, JL>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.ctl, T, um, nz, S, hits);
+            rollout_cost_n<kNS, DYN, JL>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.srows, sb.ctl, T, um, nz, S, hits);
         }
 #pragma unroll
         for (int s = 0; s < kNS; ++s) {
@@ -1020,7 +1023,8 @@ __device__ __forceinline__ void finalize_env(const DevCfg& cfg, const DevIo& io,
     if (cfg.flags & 1) {
         if (tid == 0) {
             const double* x0 = io.x0 + 4 * e;
-            ArmState st; arm_init(st, (float)x0[0], (float)x0[1], (float)x0[2], (float)x0[3]);
+            ArmState st;
+            arm_init(st, (float)x0[0], (float)x0[1], (float)x0[2], (float)x0[3], angle_fix(x0[0]), angle_fix(x0[0] + x0[1]));
             for (int t = 0; t < T; ++t) {
                 const int tc = t == 0 ? T - 1 : t - 1;
                 if (cfg.flags & 32) arm_step<1>(st, cfg.arm, (float)sm.unew[2 * tc], (float)sm.unew[2 * tc + 1]);   // MPPI_FLAG_DYNAMICS_F1
@@ -1306,7 +1310,7 @@ mppi_sampled_traj_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, cons
     const int kg = cfg.k_offset + kl, T = cfg.T;
     const float um = kg < cfg.n_exploit ? 1.0f : 0.0f;
     NoiseCfg nc = cfg.noise; nc.step = (uint32_t)(*step_ctr);
-    ArmState st; arm_init(st, hd.q1, hd.q2, hd.d1, hd.d2);
+    ArmState st; arm_init(st, hd.q1, hd.q2, hd.d1, hd.d2, hd.a1, hd.a12);
     float4* out = (float4*)traj + ((size_t)e * n_rows + row) * T;
     for (int t = 0; t < T; ++t) {
         const int tc = t == 0 ? T - 1 : t - 1;

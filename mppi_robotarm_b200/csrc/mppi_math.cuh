@@ -58,6 +58,7 @@ MPPI_HD float rcp_(float a) {             // MUFU.RCP + one Newton step (<1 ulp)
 }
 MPPI_HD int f2i(float a) { return __float_as_int(a); }
 MPPI_HD float i2f(int a) { return __int_as_float(a); }
+MPPI_HD int32_t f2i_rn_(float a) { return __float2int_rn(a); }     // F2I: nearest-even, saturating, NaN -> 0
 #else
 MPPI_HD float fma_(float a, float b, float c) { return fmaf(a, b, c); }
 MPPI_HD float mul_(float a, float b) { return a * b; }
@@ -66,6 +67,12 @@ MPPI_HD float sub_(float a, float b) { return a - b; }
 MPPI_HD float rcp_(float a) { return 1.0f / a; }
 MPPI_HD int f2i(float a) { union { float f; int i; } u; u.f = a; return u.i; }
 MPPI_HD float i2f(int a) { union { float f; int i; } u; u.i = a; return u.f; }
+MPPI_HD int32_t f2i_rn_(float a) {                                  // what cvt.rni.s32.f32 returns
+    if (!(a == a)) return 0;
+    if (a >= 2147483648.0f) return 2147483647;
+    if (a <= -2147483648.0f) return (int32_t)(-2147483647 - 1);
+    return (int32_t)nearbyintf(a);                                  // (default rounding mode: nearest-even)
+}
 #endif
 
 // FP64 reciprocal / reciprocal square root.  Device: FP32 MUFU seed + two Newton steps (~1e-14 relative) —
@@ -122,6 +129,47 @@ MPPI_HD void sincos_(float x, float& s, float& c) {
     c = ((q + 1) & 2) != 0 ? -cc : cc;
 }
 
+// ---- joint angles in fixed point ----------------------------------------------------------------
+// The dynamics only ever use sin/cos of q1 and q1 + q2, so the rollouts carry those two angles as 32-bit
+// integers in units of 2 pi / 2^32 (one turn = 2^32: the integer wraps where the angle does).  The
+// integration q <- q + dq dt (control.py:258-259) becomes one F2I of dq * dt in those units and an
+// integer add: resolution 1.46e-9 rad per step, ~40x finer than an FP32 q near 1 rad — what the Kahan
+// term of a float angle buys — and the sum q1 + q2 is exact.  The range reduction of the sincos is a
+// shift and a conversion, the sign of the half turn one XOR (no quadrant selects).
+#ifndef MPPI_ANGLE_FIX
+#define MPPI_ANGLE_FIX 1
+#endif
+constexpr double kFixPerRad = 4294967296.0 / 6.283185307179586476925;     // 2^32 / (2 pi)
+MPPI_HD uint32_t angle_fix(double q) {                  // FP64 angle -> fixed point (prepare kernel, host)
+    if (!(fabs(q) < 1.0e15)) return 0u;
+    double t = q * kFixPerRad;
+    t -= 4294967296.0 * floor(t * (1.0 / 4294967296.0));                   // [0, 2^32]
+    return (uint32_t)(unsigned long long)rint(t);                          // (2^32 wraps to 0)
+}
+// sin & cos of a fixed-point angle.  k = round(a / 2^31) half turns are removed by the shift (the remainder
+// 2 (a - k 2^31) IS the signed value of a << 1), r = remainder * pi / 2^32 lies in [-pi/2, pi/2];
+// sin(a) = (-1)^k sin r, cos(a) = (-1)^k cos r with k's parity = bit 31 of a + 2^30.  Minimax polynomials
+// of degree 9 / 10 on [-pi/2, pi/2] (4.6e-9, 2.4e-10); measured max abs error of the FP32 evaluation
+// over all arguments: 1.4e-7 (sin), 2.3e-7 (cos); |s|, |c| <= 1 + 2^-23 for EVERY argument (there is
+// no argument for which the result is not finite).
+MPPI_HD void sincos_fix(uint32_t a, float& s, float& c) {
+    const int32_t ri = (int32_t)(a << 1);
+    const float r = mul_((float)ri, 7.3145906e-10f);                   // pi / 2^32
+    const uint32_t flip = (a + 0x40000000u) & 0x80000000u;
+    const float r2 = mul_(r, r);
+    float ps = fma_(r2, 2.60005481e-06f, -1.98066147e-04f);
+    ps = fma_(ps, r2, 8.33301712e-03f);
+    ps = fma_(ps, r2, -1.66666567e-01f);
+    const float sr = fma_(mul_(ps, r2), r, r);
+    float pc = fma_(r2, -2.6077106e-07f, 2.47618864e-05f);
+    pc = fma_(pc, r2, -1.38884038e-03f);
+    pc = fma_(pc, r2, 4.16666418e-02f);
+    pc = fma_(pc, r2, -0.5f);
+    const float cr = fma_(pc, r2, 1.0f);
+    s = i2f((int)((uint32_t)f2i(sr) ^ flip));
+    c = i2f((int)((uint32_t)f2i(cr) ^ flip));
+}
+
 // ---- per-controller constants (derived once on the host in FP64, rounded to FP32) -----------
 struct ArmF {
     float A0, A1;        // M11 = A0 + A1*cos q2         (control.py:241-242)
@@ -129,7 +177,9 @@ struct ArmF {
     float G1a, G1b;      // g1 = G1a*cos q1 + G1b*cos q12; g2 = G1b*cos q12   (control.py:248-249)
     float dt;            // controller integration step (control.py:240)
     float L1, L2;        // cost-side link lengths self.l1 / self.l2 (control.py:55-56)
+    float dtfix;         // dt in fixed-point angle units per rad/s: dt * 2^32 / (2 pi)
 };
+MPPI_HD float arm_dtfix(double dt) { return (float)(dt * kFixPerRad); }
 
 struct CostW {           // weights already multiplied by 1e4 (control.py:185, 198)
     float s0, s1, s2, s3;
@@ -137,7 +187,13 @@ struct CostW {           // weights already multiplied by 1e4 (control.py:185, 1
     // joint-limit stage cost (north_star item 1; not in the reference — its only limits are the commented-out
     // clamps of _g, control.py:166-172): jw * (viol(q1)^2 + viol(q2)^2), viol(q) = max(q - hi, lo - q, 0)
     float jw, lo1, hi1, lo2, hi2;
+    // square roots of s0..s3: the stage cost is evaluated on residuals that are already scaled (stage_cost below)
+    float r0, r1, r2, r3;
 };
+MPPI_HD void cost_roots(CostW& W) {
+    W.r0 = (float)sqrt((double)W.s0); W.r1 = (float)sqrt((double)W.s1);
+    W.r2 = (float)sqrt((double)W.s2); W.r3 = (float)sqrt((double)W.s3);
+}
 MPPI_HD float joint_limit_cost(const CostW& W, float q1, float q2) {
     const float v1 = fmaxf(fmaxf(sub_(q1, W.hi1), sub_(W.lo1, q1)), 0.0f);
     const float v2 = fmaxf(fmaxf(sub_(q2, W.hi2), sub_(W.lo2, q2)), 0.0f);
@@ -148,21 +204,6 @@ struct WinEntry { float a, b, c, pad; };     // d_j - |p'|^2 = c + a*x' + b*y'  
 struct RefRow { float rx, ry, rd1, rd2; };   // waypoint in local coordinates + reference joint rates
 struct StepCtl { float u1, u2, g1, g2; };    // nominal control and gamma*(u^T Sigma^-1)
 
-// Arm state carried through the horizon.  sin/cos of q1 and q1+q2 are kept from the previous step
-// (they were needed for its forward kinematics) so each step evaluates two sincos, not eight cos/sin.
-struct ArmState {
-    float q1, q2, d1, d2;
-    float s1, c1, s12, c12;
-    float kq1, kq2, kd1, kd2;      // Kahan compensation terms of the four integrators
-};
-
-MPPI_HD void arm_init(ArmState& st, float q1, float q2, float d1, float d2) {
-    st.q1 = q1; st.q2 = q2; st.d1 = d1; st.d2 = d2;
-    st.kq1 = 0.f; st.kq2 = 0.f; st.kd1 = 0.f; st.kd2 = 0.f;
-    sincos_(q1, st.s1, st.c1);
-    sincos_(add_(q1, q2), st.s12, st.c12);
-}
-
 // acc += y with the rounding error left in `comp` (y already has the old comp subtracted)
 MPPI_HD void kahan_(float& acc, float& comp, float y) {
     float t = add_(acc, y);
@@ -170,11 +211,63 @@ MPPI_HD void kahan_(float& acc, float& comp, float y) {
     acc = t;
 }
 
+// Arm state carried through the horizon.  sin/cos of q1 and q1+q2 are kept from the previous step
+// (they were needed for its forward kinematics) so each step evaluates two sincos, not eight cos/sin.
+struct ArmState {
+    float q1, q2, d1, d2;
+    float s1, c1, s12, c12;
+    float kq1, kq2, kd1, kd2;      // Kahan compensation terms of the four integrators
+    uint32_t a1, a12;              // q1 and q1 + q2 in fixed point (what the sincos are taken of)
+};
+
+// (a1, a12) = angle_fix of the FP64 q1 and q1 + q2 (the step header carries them)
+MPPI_HD void arm_init(ArmState& st, float q1, float q2, float d1, float d2, uint32_t a1, uint32_t a12) {
+    st.q1 = q1; st.q2 = q2; st.d1 = d1; st.d2 = d2;
+    st.kq1 = 0.f; st.kq2 = 0.f; st.kd1 = 0.f; st.kd2 = 0.f;
+    st.a1 = a1; st.a12 = a12;
+#if MPPI_ANGLE_FIX
+    sincos_fix(a1, st.s1, st.c1);
+    sincos_fix(a12, st.s12, st.c12);
+#else
+    sincos_(q1, st.s1, st.c1);
+    sincos_(add_(q1, q2), st.s12, st.c12);
+#endif
+}
+
+// q <- q + dq dt (control.py:258-259, with the NEW rates) and the sin/cos of the new angles.  TRACKQ: the
+// float angles are kept as well (compensated), for the kernels that output them or charge a joint-limit cost;
+// the rollouts proper only need the fixed-point pair.
+template <bool TRACKQ>
+MPPI_HD void arm_advance_angles(ArmState& st, const ArmF& A) {
+#if MPPI_ANGLE_FIX
+    const int32_t i1 = f2i_rn_(mul_(st.d1, A.dtfix));
+    const int32_t i2 = f2i_rn_(mul_(st.d2, A.dtfix));
+    st.a1 += (uint32_t)i1;
+    st.a12 += (uint32_t)i1 + (uint32_t)i2;
+    if (TRACKQ) {
+#endif
+#if (MPPI_KAHAN_MASK & 2)
+        kahan_(st.q1, st.kq1, fma_(st.d1, A.dt, -st.kq1));
+        kahan_(st.q2, st.kq2, fma_(st.d2, A.dt, -st.kq2));
+#else
+        st.q1 = fma_(st.d1, A.dt, st.q1);
+        st.q2 = fma_(st.d2, A.dt, st.q2);
+#endif
+#if MPPI_ANGLE_FIX
+    }
+    sincos_fix(st.a1, st.s1, st.c1);
+    sincos_fix(st.a12, st.s12, st.c12);
+#else
+    sincos_(st.q1, st.s1, st.c1);
+    sincos_(add_(st.q1, st.q2), st.s12, st.c12);
+#endif
+}
+
 // One integration step (control.py:241-259) under control (v1, v2).
 // DYN = 0: the arm model _F.  DYN = 1: the reference's other rollout model _F1 (control.py:265-295),
 // which forms u = M v + C dq (gravity dropped, control.py:281-284) and solves ddq = M^-1 (u - C dq):
 // ddq = v up to FP64 rounding, so the input is applied as the joint acceleration.
-template <int DYN = 0>
+template <int DYN = 0, bool TRACKQ = true>
 MPPI_HD void arm_step(ArmState& st, const ArmF& A, float v1, float v2) {
     if (DYN == 1) {
 #if (MPPI_KAHAN_MASK & 1)
@@ -183,14 +276,7 @@ MPPI_HD void arm_step(ArmState& st, const ArmF& A, float v1, float v2) {
 #else
         st.d1 = fma_(v1, A.dt, st.d1); st.d2 = fma_(v2, A.dt, st.d2);
 #endif
-#if (MPPI_KAHAN_MASK & 2)
-        kahan_(st.q1, st.kq1, fma_(st.d1, A.dt, -st.kq1));
-        kahan_(st.q2, st.kq2, fma_(st.d2, A.dt, -st.kq2));
-#else
-        st.q1 = fma_(st.d1, A.dt, st.q1); st.q2 = fma_(st.d2, A.dt, st.q2);
-#endif
-        sincos_(st.q1, st.s1, st.c1);
-        sincos_(add_(st.q1, st.q2), st.s12, st.c12);
+        arm_advance_angles<TRACKQ>(st, A);
         return;
     }
     // cos/sin of q2 = (q1+q2) - q1 by the angle-difference identity
@@ -219,15 +305,7 @@ MPPI_HD void arm_step(ArmState& st, const ArmF& A, float v1, float v2) {
     st.d2 = fma_(n2, idt, st.d2);
 #endif
     // (the rate's own compensation term times dt, ~1e-8 * dt, is far below one ulp of q and is dropped)
-#if (MPPI_KAHAN_MASK & 2)
-    kahan_(st.q1, st.kq1, fma_(st.d1, A.dt, -st.kq1));
-    kahan_(st.q2, st.kq2, fma_(st.d2, A.dt, -st.kq2));
-#else
-    st.q1 = fma_(st.d1, A.dt, st.q1);
-    st.q2 = fma_(st.d2, A.dt, st.q2);
-#endif
-    sincos_(st.q1, st.s1, st.c1);
-    sincos_(add_(st.q1, st.q2), st.s12, st.c12);
+    arm_advance_angles<TRACKQ>(st, A);
 }
 
 // End-effector in window-local coordinates: (x - ox, y - oy), origin = first row of the window.
@@ -247,6 +325,25 @@ MPPI_HD float wsq(float w0, float w1, float w2, float w3, float ex, float ey, fl
     c = fma_(mul_(w2, e1), e1, c);
     c = fma_(mul_(w3, e2), e2, c);
     return c;
+}
+
+// Stage cost (control.py:183-185) on pre-scaled rows: with r_i = sqrt(weight_i) the table holds
+// -r_i * (waypoint component) (formed in FP64, rounded once), so each weighted residual is ONE FMA
+// r_i * state + row and the cost four squares: 8 instructions instead of 12.  The terminal cost
+// (other weights, once per sample) still goes through residuals() / wsq() on the plain rows.
+#ifndef MPPI_STAGE_FOLD
+#define MPPI_STAGE_FOLD 1
+#endif
+MPPI_HD RefRow stage_row(const CostW& W, double rx, double ry, double rd1, double rd2) {
+    RefRow r;
+    r.rx = (float)(-(double)W.r0 * rx); r.ry = (float)(-(double)W.r1 * ry);
+    r.rd1 = (float)(-(double)W.r2 * rd1); r.rd2 = (float)(-(double)W.r3 * rd2);
+    return r;
+}
+MPPI_HD float stage_cost(const CostW& W, const ArmState& st, float xl, float yl, const RefRow& sr) {
+    const float ex = fma_(W.r0, xl, sr.rx), ey = fma_(W.r1, yl, sr.ry);
+    const float e1 = fma_(W.r2, st.d1, sr.rd1), e2 = fma_(W.r3, st.d2, sr.rd2);
+    return fma_(e2, e2, fma_(e1, e1, fma_(ey, ey, mul_(ex, ex))));
 }
 
 // ---- Philox4x32-10 counter-based generator (Salmon et al., SC'11; same constants as cuRAND) ----
@@ -342,7 +439,8 @@ struct StepHeader {            // first 64 bytes of a step block (one per enviro
     int32_t win_start;         // updated prev_waypoints_idx (control.py:230)
     int32_t n_valid;           // rows of the window that exist (control.py:208-209 truncation)
     int32_t status;            // bit0: reached the end of the path (control.py:76)
-    int32_t pad[7];
+    uint32_t a1, a12;          // angle_fix of the FP64 q1 and q1 + q2
+    int32_t pad[5];
 };
 static_assert(sizeof(StepHeader) == 64, "header is 64 bytes");
 
@@ -721,6 +819,27 @@ MPPI_HD bool cert_in_box(const CertEnds& c, float xl, float yl, float& b) {
     b = fma_(c.nx, xl, mul_(c.ny, yl));
     return (fmaxf(fabsf(xl), fabsf(yl)) <= c.dom) & (b >= c.blo) & (b <= c.bhi);      // false for NaN
 }
+// The rollouts' form.  Their query is fk_local() of sin / cos values that sincos_fix bounds by 1 + 2^-23 for
+// every argument, so |x'| <= (L1 + L2)(1 + 2^-23) + |ox| < dom = 1.01 (L1 + L2) + max(|ox|, |oy|) + 0.01 (and the
+// same for y') holds by construction and is never NaN: the domain test of the certificate is implied.
+#ifndef MPPI_CERT_DOM_TEST
+#define MPPI_CERT_DOM_TEST (!MPPI_ANGLE_FIX)
+#endif
+MPPI_HD bool cert_in_box_fk(const CertEnds& c, float xl, float yl, float& b) {
+#if MPPI_CERT_DOM_TEST
+    return cert_in_box(c, xl, yl, b);
+#else
+    b = fma_(c.nx, xl, mul_(c.ny, yl));
+    return (b >= c.blo) & (b <= c.bhi);
+#endif
+}
+MPPI_HD bool cert_dom_fk(const CertEnds& c, float xl, float yl) {
+#if MPPI_CERT_DOM_TEST
+    return fmaxf(fabsf(xl), fabsf(yl)) <= c.dom;
+#else
+    return true;
+#endif
+}
 MPPI_HD int cert_guess(const WinCert& c, float xl, float yl, float b) {
     const float s = fma_(c.sx, xl, fma_(c.sy, yl, c.s0));
 #if defined(__CUDA_ARCH__)
@@ -854,13 +973,13 @@ MPPI_HD int nearest_wp(const WinTable& win, const WinCert& c, float xl, float yl
     if (md.far) {                              // a sample that left the lateral box usually stays out: wedges first
         float wl, wf;
         wedge_test(*win.wed, xl, yl, wl, wf);
-        const bool dom_ok = fmaxf(fabsf(xl), fabsf(yl)) <= e.dom;
+        const bool dom_ok = cert_dom_fk(e, xl, yl);
         if (MPPI_ALL_LANES(dom_ok & (wl >= 0.0f))) return e.last;
         if (MPPI_ALL_LANES(dom_ok & (wf >= 0.0f))) return 0;
         md.far = false;
     }
     float b;
-    const bool in = cert_in_box(e, xl, yl, b);
+    const bool in = cert_in_box_fk(e, xl, yl, b);
     if (MPPI_ALL_LANES(in & (fma_(e.lx, xl, fma_(e.ly, yl, e.lk)) >= 0.0f))) return e.last;
     if (MPPI_ALL_LANES(in & (fma_(e.fx, xl, fma_(e.fy, yl, e.fk)) <= 0.0f))) return 0;
     if (c.jhi >= 1.0f) {
@@ -871,7 +990,7 @@ MPPI_HD int nearest_wp(const WinTable& win, const WinCert& c, float xl, float yl
     // far field: the wedges of the two end rows (samples that left the lateral box)
     float wl, wf;
     wedge_test(*win.wed, xl, yl, wl, wf);
-    const bool dom_ok = fmaxf(fabsf(xl), fabsf(yl)) <= e.dom;
+    const bool dom_ok = cert_dom_fk(e, xl, yl);
     if (MPPI_ALL_LANES(dom_ok & (wl >= 0.0f))) { md.far = true; return e.last; }
     if (MPPI_ALL_LANES(dom_ok & (wf >= 0.0f))) { md.far = true; return 0; }
     ++st.scan;
@@ -890,17 +1009,18 @@ MPPI_HD int nearest_wp(const Win& win, const WinCert&, float xl, float yl, Looku
 // JL: the stage cost carries the joint-limit term (a template flag: the default kernels do not contain it)
 template <int NS, int DYN = 0, bool JL = false, class Win, class Noise>
 MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
-                            const Win& win, const WinCert& cert, const RefRow* rows, const StepCtl* ctl,
+                            const Win& win, const WinCert& cert, const RefRow* rows, const RefRow* srows, const StepCtl* ctl,
                             int T, const float (&um)[NS], Noise (&noise)[NS], float (&S_out)[NS], LookupStats& hits) {
     ArmState st[NS];
     LookupMode md[NS];
-    float S[NS], kS[NS], ex[NS], ey[NS], e1[NS], e2[NS];
+    float S[NS], kS[NS], xl[NS], yl[NS];
+    int j[NS];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int s = 0; s < NS; ++s) {
-        arm_init(st[s], hd.q1, hd.q2, hd.d1, hd.d2);
-        S[s] = 0.f; kS[s] = 0.f; ex[s] = 0.f; ey[s] = 0.f; e1[s] = 0.f; e2[s] = 0.f;
+        arm_init(st[s], hd.q1, hd.q2, hd.d1, hd.d2, hd.a1, hd.a12);
+        S[s] = 0.f; kS[s] = 0.f; xl[s] = 0.f; yl[s] = 0.f; j[s] = 0;
         md[s].far = false;
     }
 #if defined(__CUDA_ARCH__)
@@ -908,8 +1028,7 @@ MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
 #endif
     for (int t = 0; t < T; ++t) {
         const StepCtl c = ctl[t];
-        float v1[NS], v2[NS], xl[NS], yl[NS];
-        int j[NS];
+        float v1[NS], v2[NS];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -922,7 +1041,7 @@ MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int s = 0; s < NS; ++s) arm_step<DYN>(st[s], A, v1[s], v2[s]);
+        for (int s = 0; s < NS; ++s) arm_step<DYN, JL>(st[s], A, v1[s], v2[s]);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -934,9 +1053,13 @@ MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
 #pragma unroll
 #endif
         for (int s = 0; s < NS; ++s) {
-            const RefRow r = rows[j[s]];
-            residuals(st[s], xl[s], yl[s], r, ex[s], ey[s], e1[s], e2[s]);
-            float cst = wsq(W.s0, W.s1, W.s2, W.s3, ex[s], ey[s], e1[s], e2[s]);
+#if MPPI_STAGE_FOLD
+            float cst = stage_cost(W, st[s], xl[s], yl[s], srows[j[s]]);
+#else
+            float ex, ey, e1, e2;
+            residuals(st[s], xl[s], yl[s], rows[j[s]], ex, ey, e1, e2);
+            float cst = wsq(W.s0, W.s1, W.s2, W.s3, ex, ey, e1, e2);
+#endif
             cst = fma_(c.g1, v1[s], fma_(c.g2, v2[s], cst));   // + gamma * u^T Sigma^-1 v  (control.py:106)
             if (JL) cst = add_(cst, joint_limit_cost(W, st[s].q1, st[s].q2));
 #if (MPPI_KAHAN_MASK & 4)
@@ -950,18 +1073,21 @@ MPPI_HD void rollout_cost_n(const StepHeader& hd, const ArmF& A, const CostW& W,
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int s = 0; s < NS; ++s)
-        S_out[s] = add_(S[s], sub_(wsq(W.t0, W.t1, W.t2, W.t3, ex[s], ey[s], e1[s], e2[s]), kS[s]));
+    for (int s = 0; s < NS; ++s) {
+        float ex = 0.f, ey = 0.f, e1 = 0.f, e2 = 0.f;
+        if (T > 0) residuals(st[s], xl[s], yl[s], rows[j[s]], ex, ey, e1, e2);
+        S_out[s] = add_(S[s], sub_(wsq(W.t0, W.t1, W.t2, W.t3, ex, ey, e1, e2), kS[s]));
+    }
 }
 
 template <int DYN = 0, bool JL = false, class Win, class Noise>
 MPPI_HD float rollout_cost(const StepHeader& hd, const ArmF& A, const CostW& W,
-                           const Win& win, const WinCert& cert, const RefRow* rows, const StepCtl* ctl,
+                           const Win& win, const WinCert& cert, const RefRow* rows, const RefRow* srows, const StepCtl* ctl,
                            int T, float um, Noise& noise, LookupStats& hits) {
     const float ums[1] = { um };
     float out[1];
     Noise (&nz)[1] = reinterpret_cast<Noise (&)[1]>(noise);
-    rollout_cost_n<1, DYN, JL>(hd, A, W, win, cert, rows, ctl, T, ums, nz, out, hits);
+    rollout_cost_n<1, DYN, JL>(hd, A, W, win, cert, rows, srows, ctl, T, ums, nz, out, hits);
     return out[0];
 }
 
@@ -990,6 +1116,15 @@ MPPI_HD void make_window_row(const double* ref, int n_rows, int p, int j, WinEnt
         w.a = 0.f; w.b = 0.f; w.c = kSentinel; w.pad = 0.f;
         r.rx = 0.f; r.ry = 0.f; r.rd1 = 0.f; r.rd2 = 0.f;
     }
+}
+
+// The same plus the pre-scaled row of the stage cost.
+MPPI_HD void make_window_row(const double* ref, int n_rows, int p, int j, const CostW& W, WinEntry& w, RefRow& r, RefRow& sr) {
+    make_window_row(ref, n_rows, p, j, w, r);
+    const int row = p + j;
+    if (j < kWindow && row < n_rows)
+        sr = stage_row(W, ref[4 * row + 0] - ref[4 * p + 0], ref[4 * row + 1] - ref[4 * p + 1], ref[4 * row + 2], ref[4 * row + 3]);
+    else sr = r;
 }
 
 // Nominal control of horizon step t and the row vector gamma * u_t^T Sigma^-1 (control.py:106).

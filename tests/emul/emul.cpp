@@ -10,10 +10,10 @@ using namespace mppi;
 // the tables the prepare kernel builds for the window starting at row p (serial form)
 struct Tables {
     WinRegs regs; WinTable win; WinCert cert; EndWedges wed;
-    RefRow rows[kWindowPad]; WinEntry tab[kWindowPad]; RowRec rec[kWindowPad];
+    RefRow rows[kWindowPad]; RefRow srows[kWindowPad]; WinEntry tab[kWindowPad]; RowRec rec[kWindowPad];
 };
-static void build_tables(const double* ref, int n_rows, int p, double reach, bool use_cert, Tables& tb) {
-    for (int j = 0; j < kWindowPad; ++j) make_window_row(ref, n_rows, p, j, tb.tab[j], tb.rows[j]);
+static void build_tables(const double* ref, int n_rows, int p, double reach, bool use_cert, Tables& tb, const CostW& W = CostW{}) {
+    for (int j = 0; j < kWindowPad; ++j) make_window_row(ref, n_rows, p, j, W, tb.tab[j], tb.rows[j], tb.srows[j]);
     tb.regs.load(tb.tab);
     double lrows[kWindow][2];
     int n_valid = 0;
@@ -49,7 +49,11 @@ int emul_rollout_costs(const double* ref, int n_rows, int prev_idx, const double
     StepHeader hd{};
     hd.q1 = (float)x0[0]; hd.q2 = (float)x0[1]; hd.d1 = (float)x0[2]; hd.d2 = (float)x0[3];
     hd.ox = (float)ref[4 * p]; hd.oy = (float)ref[4 * p + 1]; hd.win_start = p;
-    Tables tb; build_tables(ref, n_rows, p, cl1 + cl2, use_cert != 0, tb);
+    hd.a1 = angle_fix(x0[0]); hd.a12 = angle_fix(x0[0] + x0[1]);
+    CostW W{ (float)(ws[0] * 1e4), (float)(ws[1] * 1e4), (float)(ws[2] * 1e4), (float)(ws[3] * 1e4),
+             (float)(wt[0] * 1e4), (float)(wt[1] * 1e4), (float)(wt[2] * 1e4), (float)(wt[3] * 1e4) };
+    cost_roots(W);
+    Tables tb; build_tables(ref, n_rows, p, cl1 + cl2, use_cert != 0, tb, W);
     const RefRow* rows = tb.rows;
     long long hits_total = 0;
     std::vector<StepCtl> ctl(T);
@@ -60,21 +64,18 @@ int emul_rollout_costs(const double* ref, int n_rows, int prev_idx, const double
     A.A1 = (float)(2 * m2 * l1 * lc2);
     A.M22 = (float)(m2 * lc2 * lc2 + l2); A.B1 = (float)(m2 * l1 * lc2);
     A.G1a = (float)((m1 * lc1 + m2 * l1) * g); A.G1b = (float)(m2 * lc2 * g);
-    A.dt = (float)dt; A.L1 = (float)cl1; A.L2 = (float)cl2;
-    // the device copy of ox/oy is FP32; fk_local subtracts exactly that value
-    CostW W{ (float)(ws[0] * 1e4), (float)(ws[1] * 1e4), (float)(ws[2] * 1e4), (float)(ws[3] * 1e4),
-             (float)(wt[0] * 1e4), (float)(wt[1] * 1e4), (float)(wt[2] * 1e4), (float)(wt[3] * 1e4) };
+    A.dt = (float)dt; A.dtfix = arm_dtfix(dt); A.L1 = (float)cl1; A.L2 = (float)cl2;
     long long tri_total = 0;
     for (int k = 0; k < K; ++k) {
         EpsArray n{ eps + (size_t)k * T * 2, T };
         LookupStats hits{0, 0};
         const float um = k < n_exploit ? 1.f : 0.f;
         if (use_cert == 2)      // the kernels without the certificate: register tournament
-            S_out[k] = dynamics_f1 ? rollout_cost<1>(hd, A, W, tb.regs, tb.cert, rows, ctl.data(), T, um, n, hits)
-                                   : rollout_cost<0>(hd, A, W, tb.regs, tb.cert, rows, ctl.data(), T, um, n, hits);
+            S_out[k] = dynamics_f1 ? rollout_cost<1>(hd, A, W, tb.regs, tb.cert, rows, tb.srows, ctl.data(), T, um, n, hits)
+                                   : rollout_cost<0>(hd, A, W, tb.regs, tb.cert, rows, tb.srows, ctl.data(), T, um, n, hits);
         else
-            S_out[k] = dynamics_f1 ? rollout_cost<1>(hd, A, W, tb.win, tb.cert, rows, ctl.data(), T, um, n, hits)
-                                   : rollout_cost<0>(hd, A, W, tb.win, tb.cert, rows, ctl.data(), T, um, n, hits);
+            S_out[k] = dynamics_f1 ? rollout_cost<1>(hd, A, W, tb.win, tb.cert, rows, tb.srows, ctl.data(), T, um, n, hits)
+                                   : rollout_cost<0>(hd, A, W, tb.win, tb.cert, rows, tb.srows, ctl.data(), T, um, n, hits);
         hits_total += T - hits.tri - hits.scan; tri_total += hits.tri;
     }
     if (hits_out) { hits_out[0] = hits_total; hits_out[1] = tri_total; }
@@ -110,6 +111,8 @@ void emul_cert_probe_given(const double* ref, int n_rows, int p, const float* ce
 }
 
 void emul_sincos(const float* x, int n, float* s, float* c) { for (int i = 0; i < n; ++i) sincos_(x[i], s[i], c[i]); }
+// sin / cos as the rollouts take them: of the fixed-point image of an FP64 angle
+void emul_sincos_fix(const double* x, int n, float* s, float* c) { for (int i = 0; i < n; ++i) sincos_fix(angle_fix(x[i]), s[i], c[i]); }
 
 void emul_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
     U4 r = philox4x32_10(U4{c0, c1, c2, c3}, philox_expand_key(k0, k1)); out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;

@@ -396,6 +396,15 @@ def test_reference_run_py_runs_unchanged_on_the_gpu(tmp_path, monkeypatch, capsy
         assert out[3].shape == (100, 30, 4)                   # run.py asks for the sampled trajectories
         return out
     monkeypatch.setattr(control.MPPIControllerForPathTracking, "calc_control_input", counted)
+    # run.py leaves the noise unseeded, and about one stream in twenty keeps the arm at waypoint 0 for 50 ticks (the
+    # oracle loop does the same on those streams): fix the Philox key to one on which the FP64 oracle loop is at
+    # waypoint 20 after 20 ticks and at 62 after 50
+    real_init = control.MPPIControllerForPathTracking.__init__
+
+    def seeded(self, *a, **k):
+        k.setdefault("seed", 4)
+        real_init(self, *a, **k)
+    monkeypatch.setattr(control.MPPIControllerForPathTracking, "__init__", seeded)
     with pytest.raises(_Enough):
         runpy.run_path(os.path.join(src, "run.py"), run_name="__main__")
     text = capsys.readouterr().out

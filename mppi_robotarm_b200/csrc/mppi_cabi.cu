@@ -138,16 +138,16 @@ bool pick_const_window(const MppiConfig* c) {
 // `per_sm` resident CTAs per SM; full waves cost per_sm warp-times each, the last partial wave
 // ceil(rest / SMs) warp-times; a warp-time is proportional to ns (x 1.03 for ns = 1).  Pick the cheaper.
 int pick_ns(const MppiConfig* c, int sm) {
-    if (const char* f = getenv("MPPI_NS")) { const int v = atoi(f); if (v == 1 || v == 2) return v; }
+    if (const char* f = getenv("MPPI_NS")) { const int v = atoi(f); if (v == 1 || v == kNsWide) return v; }
     const bool cw = pick_const_window(c);
     double best_cost = 0.0; int best = 1;
-    for (int ns = 1; ns <= 2; ++ns) {
+    for (int ns = 1; ns <= kNsWide; ns += kNsWide - 1) {
         const int per_sm = certified_kernels(c) ? (ns == 1 ? MPPI_ROLL_MIN_BLOCKS_CERT_NS1 : MPPI_ROLL_MIN_BLOCKS_CERT)
                                                 : (cw ? MPPI_ROLL_MIN_BLOCKS_CONST : (ns == 1 ? 3 : 2));
         const long long ctas = (((long long)c->K_local + 128 * ns - 1) / (128 * ns)) * c->n_env;
         const long long slots = (long long)sm * per_sm;
         const long long full = ctas / slots, rest = ctas % slots;
-        const double warp_time = ns == 1 ? 1.03 : 2.0;
+        const double warp_time = ns == 1 ? 1.03 : (double)ns;
         const double cost = (double)(full * per_sm + (rest + sm - 1) / sm) * warp_time;
         if (ns == 1 || cost < best_cost) { best_cost = cost; best = ns; }
     }
@@ -350,7 +350,7 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
         // kernel specialisations: noise source x samples per thread x { certified lookups x rollout model,
         // plain searches x window policy }.  MPPI_FLAG_FULL_SEARCH selects the kernels compiled without the
         // certificate; the _F1 model exists in the certified shape only (prepare then never arms the certificate).
-        const bool ns2 = h->ns == 2, f1 = (dc.flags & MPPI_FLAG_DYNAMICS_F1) != 0;
+        const bool ns2 = h->ns != 1, f1 = (dc.flags & MPPI_FLAG_DYNAMICS_F1) != 0;
         const bool cert = certified_kernels(&h->cfg), jl = h->cfg.joint_limit_weight > 0.0;
         unsigned long long* stats = (unsigned long long*)(ws + h->ws.off_stats);
         unsigned int* rho_key = (unsigned int*)(ws + h->ws.off_seq + 2 * sizeof(unsigned long long));
@@ -367,7 +367,7 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
 #define MPPI_ROLL(NOISE, CW, NS_, DYN, CERT) do { \
         if (CERT && DYN == 0 && jl) CU(h, cudaLaunchKernelEx(&lc, mppi_rollout_sm100a<NOISE, false, NS_, 0, true, true>, dc, step_ctr, (const char*)step_blocks, eps_arg, S, bmin, stats, rho_key)); \
         else CU(h, cudaLaunchKernelEx(&lc, mppi_rollout_sm100a<NOISE, CW, NS_, DYN, CERT>, dc, step_ctr, (const char*)step_blocks, eps_arg, S, bmin, stats, rho_key)); } while (0)
-#define MPPI_ROLL_NS(NOISE, CW, DYN, CERT) do { if (ns2) MPPI_ROLL(NOISE, CW, 2, DYN, CERT); else MPPI_ROLL(NOISE, CW, 1, DYN, CERT); } while (0)
+#define MPPI_ROLL_NS(NOISE, CW, DYN, CERT) do { if (ns2) MPPI_ROLL(NOISE, CW, kNsWide, DYN, CERT); else MPPI_ROLL(NOISE, CW, 1, DYN, CERT); } while (0)
 #define MPPI_ROLL_NOISE(CW, DYN, CERT) do { if (ph) MPPI_ROLL_NS(0, CW, DYN, CERT); else MPPI_ROLL_NS(1, CW, DYN, CERT); } while (0)
         if (f1) MPPI_ROLL_NOISE(false, 1, true);
         else if (cert) MPPI_ROLL_NOISE(false, 0, true);

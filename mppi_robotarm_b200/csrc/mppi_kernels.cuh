@@ -643,11 +643,16 @@ struct WinConst {
 #endif
 
 #ifndef MPPI_ROLL_MIN_BLOCKS_CERT
-#define MPPI_ROLL_MIN_BLOCKS_CERT 5      // <= 102 registers: 20 warps per SM (A/B on B200: profiles/r2_variants.md)
+#define MPPI_ROLL_MIN_BLOCKS_CERT 4      // <= 128 registers, no spills, per-step constants stay in registers (A/B on B200: profiles/r2s3_variants.md; 5 CTAs/SM was the choice while the float angles and their compensation terms were live)
 #endif
 #ifndef MPPI_ROLL_MIN_BLOCKS_CERT_NS1
 #define MPPI_ROLL_MIN_BLOCKS_CERT_NS1 5  // the one-sample-per-thread kernel (small shards, latency runs)
 #endif
+
+#ifndef MPPI_NS_WIDE
+#define MPPI_NS_WIDE 2                   // samples per thread of the throughput kernels
+#endif
+constexpr int kNsWide = MPPI_NS_WIDE;
 
 // Window policy per kernel family.  CERT: certified lookups, the table stays in shared memory (any number of
 // environments).  Otherwise plain searches with the coefficients in the constant bank (CONSTWIN) or in registers.

@@ -152,10 +152,19 @@ MPPI_HD uint32_t angle_fix(double q) {                  // FP64 angle -> fixed p
 // of degree 9 / 10 on [-pi/2, pi/2] (4.6e-9, 2.4e-10); measured max abs error of the FP32 evaluation
 // over all arguments: 1.4e-7 (sin), 2.3e-7 (cos); |s|, |c| <= 1 + 2^-23 for EVERY argument (there is
 // no argument for which the result is not finite).
+MPPI_HD float flip_sign_(float v, uint32_t m) {       // v with its sign flipped where bit 31 of m is set: ONE LOP3
+#if defined(__CUDA_ARCH__)
+    uint32_t o;
+    asm("lop3.b32 %0, %1, %2, %3, 0x6A;" : "=r"(o) : "r"(m), "r"(0x80000000u), "r"(__float_as_uint(v)));   // (m & mask) ^ v
+    return __uint_as_float(o);
+#else
+    return i2f((int)((uint32_t)f2i(v) ^ (m & 0x80000000u)));
+#endif
+}
 MPPI_HD void sincos_fix(uint32_t a, float& s, float& c) {
     const int32_t ri = (int32_t)(a << 1);
     const float r = mul_((float)ri, 7.3145906e-10f);                   // pi / 2^32
-    const uint32_t flip = (a + 0x40000000u) & 0x80000000u;
+    const uint32_t flip_src = a + 0x40000000u;                         // bit 31: odd number of half turns
     const float r2 = mul_(r, r);
     float ps = fma_(r2, 2.60005481e-06f, -1.98066147e-04f);
     ps = fma_(ps, r2, 8.33301712e-03f);
@@ -166,8 +175,8 @@ MPPI_HD void sincos_fix(uint32_t a, float& s, float& c) {
     pc = fma_(pc, r2, 4.16666418e-02f);
     pc = fma_(pc, r2, -0.5f);
     const float cr = fma_(pc, r2, 1.0f);
-    s = i2f((int)((uint32_t)f2i(sr) ^ flip));
-    c = i2f((int)((uint32_t)f2i(cr) ^ flip));
+    s = flip_sign_(sr, flip_src);
+    c = flip_sign_(cr, flip_src);
 }
 
 // ---- per-controller constants (derived once on the host in FP64, rounded to FP32) -----------
@@ -285,12 +294,13 @@ MPPI_HD void arm_step(ArmState& st, const ArmF& A, float v1, float v2) {
     float M11 = fma_(A.A1, c2, A.A0);
     float M12 = fma_(A.B1, c2, A.M22);
     float h = mul_(A.B1, s2);
-    float g2 = mul_(A.G1b, st.c12);
-    float g1 = fma_(A.G1a, st.c1, g2);
+    // v - G: g2 = G1b cos q12, g1 = G1a cos q1 + g2 (control.py:248-249), subtracted by FMAs
+    float w2 = fma_(-A.G1b, st.c12, v2);
+    float w1 = fma_(-A.G1a, st.c1, fma_(-A.G1b, st.c12, v1));
     // v - C dq - G with C dq = [-h d2 (2 d1 + d2), h d1^2]
     float tt = fma_(2.0f, st.d1, st.d2);
-    float b1 = fma_(mul_(h, st.d2), tt, sub_(v1, g1));
-    float b2 = fma_(-mul_(h, st.d1), st.d1, sub_(v2, g2));
+    float b1 = fma_(mul_(h, st.d2), tt, w1);
+    float b2 = fma_(-mul_(h, st.d1), st.d1, w2);
     float det = fma_(M11, A.M22, -mul_(M12, M12));
     float idt = mul_(rcp_(det), A.dt);
     float n1 = fma_(A.M22, b1, -mul_(M12, b2));

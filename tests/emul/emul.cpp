@@ -30,7 +30,11 @@ struct EpsArray {
     void operator()(int t, float& a, float& b) const { a = e[2 * t]; b = e[2 * t + 1]; }
 };
 
+static int g_ns = 1;      // samples per rollout_cost_n call (emul_set_ns)
+
 extern "C" {
+
+void emul_set_ns(int ns) { g_ns = ns == 2 ? 2 : 1; }
 
 // S[K] for injected noise eps[K][T][2]; mirrors prepare + rollout kernels.  Returns new window start.
 int emul_rollout_costs(const double* ref, int n_rows, int prev_idx, const double* x0, const double* u_prev,
@@ -67,8 +71,18 @@ int emul_rollout_costs(const double* ref, int n_rows, int prev_idx, const double
     A.dt = (float)dt; A.dtfix = arm_dtfix(dt); A.L1 = (float)cl1; A.L2 = (float)cl2;
     long long tri_total = 0;
     for (int k = 0; k < K; ++k) {
-        EpsArray n{ eps + (size_t)k * T * 2, T };
         LookupStats hits{0, 0};
+        if (g_ns == 2 && use_cert != 2 && !dynamics_f1 && k + 1 < K) {     // two samples per "thread", like the throughput kernels
+            EpsArray n2[2] = { { eps + (size_t)k * T * 2, T }, { eps + (size_t)(k + 1) * T * 2, T } };
+            const float um2[2] = { k < n_exploit ? 1.f : 0.f, k + 1 < n_exploit ? 1.f : 0.f };
+            float out2[2];
+            rollout_cost_n<2, 0, false>(hd, A, W, tb.win, tb.cert, rows, tb.srows, ctl.data(), T, um2, n2, out2, hits);
+            S_out[k] = out2[0]; S_out[k + 1] = out2[1];
+            hits_total += 2 * T - hits.tri - hits.scan; tri_total += hits.tri;
+            ++k;
+            continue;
+        }
+        EpsArray n{ eps + (size_t)k * T * 2, T };
         const float um = k < n_exploit ? 1.f : 0.f;
         if (use_cert == 2)      // the kernels without the certificate: register tournament
             S_out[k] = dynamics_f1 ? rollout_cost<1>(hd, A, W, tb.regs, tb.cert, rows, tb.srows, ctl.data(), T, um, n, hits)

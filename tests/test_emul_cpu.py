@@ -220,6 +220,13 @@ def test_certified_rollout_costs_are_bit_identical(emul, paths):
         S_off, p_off = emul_costs(emul, c, cl["state"][s], eps, int(cl["prev_idx"][s, 0]), u=u, use_cert=0, hits=hits)
         S_reg, _ = emul_costs(emul, c, cl["state"][s], eps, int(cl["prev_idx"][s, 0]), u=u, use_cert=2, hits=hits)
         assert p_on == p_off and np.array_equal(S_on, S_off) and np.array_equal(S_on, S_reg)
+        # two samples per call, in lockstep like the throughput kernels
+        emul.emul_set_ns(2)
+        try:
+            S_two, _ = emul_costs(emul, c, cl["state"][s], eps, int(cl["prev_idx"][s, 0]), u=u, use_cert=1)
+        finally:
+            emul.emul_set_ns(1)
+        assert np.array_equal(S_on, S_two)
         assert hits[1] == (0, 0)
         assert hits[0][0] + hits[0][1] > 0.995 * K * T, (s, T, hits)
         if T >= 64:

@@ -26,7 +26,7 @@ def main():
         info = []
         blocks = res.stderr.split("Compiling entry function")
         for blk in blocks:
-            m = re.search(r"mppi_rollout_sm100aILi0ELb0ELi([12])ELi0ELb1E", blk)
+            m = re.search(r"mppi_rollout_sm100aILi0ELb0ELi([1-4])ELi0ELb1E", blk)
             if m:
                 regs = re.search(r"Used (\d+) registers", blk).group(1)
                 sp = re.search(r"(\d+) bytes spill stores", blk).group(1)

@@ -39,6 +39,9 @@ struct Workspace {
 
 }  // namespace
 
+// launch layout of the rollout kernel (pick_layout): samples per thread, and for the flat mixed layout the CTA counts
+struct RollLayout { int ns; int n_wide, n_narrow; bool flat; };
+
 struct MppiHandle {
     MppiConfig cfg;
     DevCfg dc;
@@ -67,6 +70,7 @@ struct MppiHandle {
     bool const_window;         // single environment: window coefficients go through the constant bank
     int ns;                    // samples per thread of the rollout kernel
     int roll_threads;          // threads per CTA of the rollout kernel
+    RollLayout layout;         // launch layout of the rollout kernel
     bool zero_copy;            // kernels read / write the caller's pinned block directly (no memcpy nodes)
     DevIo dio_dev;             // same as dio but never touching the pinned block (device closed loop)
     PeerExchange px;           // peer-memory exchange (world == 0: not configured)
@@ -132,13 +136,16 @@ bool pick_const_window(const MppiConfig* c) {
            getenv("MPPI_NO_CONST_WINDOW") == nullptr;
 }
 
-// Samples per thread of the rollout kernel.  Two samples per thread cost ~3 % fewer instructions per
-// sample, but a warp is then twice as long, and the kernel lasts as long as the busiest scheduler
-// (every SM sub-partition runs a whole number of warps).  Model: CTAs of 4 warps (one per sub-partition),
-// `per_sm` resident CTAs per SM; full waves cost per_sm warp-times each, the last partial wave
-// ceil(rest / SMs) warp-times; a warp-time is proportional to ns (x 1.03 for ns = 1).  Pick the cheaper.
-int pick_ns(const MppiConfig* c, int sm) {
-    if (const char* f = getenv("MPPI_NS")) { const int v = atoi(f); if (v == 1 || v == kNsWide) return v; }
+// Layout of the rollout launch (kernels: mppi_kernels.cuh, section 2).
+//  * Kernels without certified lookups: uniform layouts; one or kNsWide samples per thread by a wave model — CTAs
+//    of 4 warps (one per sub-partition), `per_sm` resident CTAs per SM; full waves cost per_sm warp-times each, the
+//    last partial wave ceil(rest / SMs) warp-times; a warp-time is proportional to ns (x 1.03 for ns = 1).
+//  * Certified kernels: work is counted in units of 128 samples (U over all environments).  U <= one wave of
+//    one-sample CTAs: the one-sample kernel (a lone one-sample warp is the shortest pass there is).  Otherwise the
+//    flat mixed layout of the two-sample kernel: full waves of two-sample CTAs, and a LAST wave that is exactly full —
+//    R units left for S slots: R <= S one-sample CTAs, else (R - S) two-sample + (2S - R) one-sample CTAs.
+//    Measured on B200 (profiles/r2s3_layout_sweep.txt): 98304 samples 82.8 -> 74.3 us, 196608 samples 137.4 -> 128.7 us.
+int pick_ns_uniform(const MppiConfig* c, int sm) {
     const bool cw = pick_const_window(c);
     double best_cost = 0.0; int best = 1;
     for (int ns = 1; ns <= kNsWide; ns += kNsWide - 1) {
@@ -153,6 +160,33 @@ int pick_ns(const MppiConfig* c, int sm) {
     }
     return best;
 }
+RollLayout pick_layout(const MppiConfig* c, int sm) {
+    RollLayout L = { 1, 0, 0, false };
+    int forced = 0;
+    if (const char* f = getenv("MPPI_NS")) { const int v = atoi(f); if (v == 1 || v == kNsWide) forced = v; }
+    if (!certified_kernels(c) || kNsWide != 2) {
+        L.ns = forced ? forced : pick_ns_uniform(c, sm);
+        if (L.ns != 1 && certified_kernels(c)) {       // (the certified wide kernel only knows the flat layout)
+            const long long upe = ((long long)c->K_local + 127) / 128, U = upe * c->n_env;
+            if (c->n_env == 1 || c->K_local % (128 * kNsWide) == 0) { L.flat = true; L.n_wide = (int)(U / kNsWide); L.n_narrow = (int)(U % kNsWide); }
+            else L.ns = 1;
+        }
+        return L;
+    }
+    const long long upe = ((long long)c->K_local + 127) / 128, U = upe * c->n_env;
+    const bool flat_ok = (c->n_env == 1 || c->K_local % 256 == 0) && U < (1ll << 30);
+    const long long S = (long long)sm * MPPI_ROLL_MIN_BLOCKS_CERT, Sn = (long long)sm * MPPI_ROLL_MIN_BLOCKS_CERT_NS1;
+    // one wave of one-sample CTAs, or (measured, 131072 samples: 92.9 us against 95.2 mixed) a shard whose mixed single
+    // wave would be mostly two-sample CTAs: the one-sample kernel
+    if (forced == 1 || !flat_ok || (!forced && (U <= Sn || (U <= 2 * S && 2 * U > 3 * S)))) return L;
+    L.ns = 2; L.flat = true;
+    if (forced == 2 || getenv("MPPI_NO_MIXED")) { L.n_wide = (int)(U / 2); L.n_narrow = (int)(U % 2); return L; }
+    const long long full = U / (2 * S), R = U % (2 * S);
+    if (R == 0) { L.n_wide = (int)(U / 2); L.n_narrow = 0; }
+    else if (R <= S) { L.n_wide = (int)(full * S); L.n_narrow = (int)R; }
+    else { L.n_wide = (int)(full * S + (R - S)); L.n_narrow = (int)(2 * S - R); }
+    return L;
+}
 
 // Threads per CTA of the rollout kernel: 128, or fewer for small shards, where finer CTAs spread more evenly over
 // the SMs (MPPI_ROLL_THREADS overrides; A/B in profiles/r2_variants.md).
@@ -164,9 +198,11 @@ int pick_roll_threads(const MppiConfig* c, int sm) {
 
 void grid_sizes(const MppiConfig* c, int sm, int* g_roll, int* g_soft, int* g_wsum) {
     const int K = c->K_local;
-    const int ns = pick_ns(c, sm), thr = pick_roll_threads(c, sm);
-    int gr = (K + thr * ns - 1) / (thr * ns);
-    if (gr > 32768) gr = 32768;
+    const RollLayout L = pick_layout(c, sm);
+    const int thr = pick_roll_threads(c, sm);
+    // uniform layout: blocks per environment; flat layout: units of 128 samples per environment
+    int gr = L.flat ? (K + 127) / 128 : (K + thr * L.ns - 1) / (thr * L.ns);
+    if (!L.flat && gr > 32768) gr = 32768;
     *g_roll = gr;
     int gs = (K + kSoftThreads * 4 - 1) / (kSoftThreads * 4);
     const int cap = (4 * sm + c->n_env - 1) / c->n_env;
@@ -338,7 +374,10 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
     if (timed) CU(h, cudaEventRecord(h->tev[1], s));
     {
         NvtxRange r("mppi.rollout");
+        const RollLayout& L = h->layout;
         dim3 grid(dc.g_roll, dc.n_env);
+        if (L.flat) grid = dim3(L.n_wide + L.n_narrow, 1);
+        const int n_wide = L.n_wide;
         const bool ph = noise_mode == MPPI_NOISE_PHILOX;
         if (h->const_window) {
             // single environment, large K: stage this step's window coefficients in the constant bank
@@ -362,11 +401,11 @@ int enqueue_local(MppiHandle* h, int noise_mode, const float* eps_dev, double* p
         pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
         cudaLaunchConfig_t lc = {};
-        lc.gridDim = grid; lc.blockDim = dim3(h->roll_threads); lc.dynamicSmemBytes = h->roll_smem; lc.stream = s;
+        lc.gridDim = grid; lc.blockDim = dim3(L.flat ? kRollThreads : h->roll_threads); lc.dynamicSmemBytes = h->roll_smem; lc.stream = s;
         lc.attrs = pdl_attr; lc.numAttrs = (h->pdl && !h->const_window && !timed) ? 1 : 0;
 #define MPPI_ROLL(NOISE, CW, NS_, DYN, CERT) do { \
-        if (CERT && DYN == 0 && jl) CU(h, cudaLaunchKernelEx(&lc, mppi_rollout_sm100a<NOISE, false, NS_, 0, true, true>, dc, step_ctr, (const char*)step_blocks, eps_arg, S, bmin, stats, rho_key)); \
-        else CU(h, cudaLaunchKernelEx(&lc, mppi_rollout_sm100a<NOISE, CW, NS_, DYN, CERT>, dc, step_ctr, (const char*)step_blocks, eps_arg, S, bmin, stats, rho_key)); } while (0)
+        if (CERT && DYN == 0 && jl) CU(h, cudaLaunchKernelEx(&lc, mppi_rollout_sm100a<NOISE, false, NS_, 0, true, true>, dc, step_ctr, (const char*)step_blocks, eps_arg, S, bmin, stats, rho_key, n_wide)); \
+        else CU(h, cudaLaunchKernelEx(&lc, mppi_rollout_sm100a<NOISE, CW, NS_, DYN, CERT>, dc, step_ctr, (const char*)step_blocks, eps_arg, S, bmin, stats, rho_key, n_wide)); } while (0)
 #define MPPI_ROLL_NS(NOISE, CW, DYN, CERT) do { if (ns2) MPPI_ROLL(NOISE, CW, kNsWide, DYN, CERT); else MPPI_ROLL(NOISE, CW, 1, DYN, CERT); } while (0)
 #define MPPI_ROLL_NOISE(CW, DYN, CERT) do { if (ph) MPPI_ROLL_NS(0, CW, DYN, CERT); else MPPI_ROLL_NS(1, CW, DYN, CERT); } while (0)
         if (f1) MPPI_ROLL_NOISE(false, 1, true);
@@ -543,7 +582,8 @@ int mppi_create(const MppiConfig* c, void* workspace, size_t workspace_bytes, vo
     h->dio.u_new = (double*)(dout + h->io.off_u_new);
     h->dio.opt_traj = (double*)(dout + h->io.off_opt_traj);
     h->roll_smem = (size_t)h->dc.step_block_bytes;
-    h->ns = pick_ns(c, h->sm_count);
+    h->layout = pick_layout(c, h->sm_count);
+    h->ns = h->layout.ns;
     h->roll_threads = pick_roll_threads(c, h->sm_count);
     h->const_window = pick_const_window(c);
     h->dio_dev = h->dio;

@@ -663,17 +663,75 @@ __device__ __forceinline__ void win_load(WinTable& w, const StepBlockView& sb) {
 __device__ __forceinline__ void win_load(WinRegs& w, const StepBlockView& sb) { w.load(sb.win); }
 __device__ __forceinline__ void win_load(WinConst& w, const StepBlockView& sb) { w.load(sb.win); }
 
+// NS samples of one thread (kl0 + s * stride, s < NS) of environment e: noise source, rollout, cost store.
+// Returns the smallest finite cost of the thread's samples.
+template <int NS, int NOISE, int DYN, bool JL, class Win>
+__device__ __forceinline__ float roll_samples(const DevCfg& cfg, const StepHeader& hd, const Win& win, const WinCert& cert,
+                                              const StepBlockView& sb, const uint64_t* __restrict__ step_ctr,
+                                              const float* __restrict__ eps, float* __restrict__ S_out, int e, int kl0,
+                                              int stride, LookupStats& hits) {
+    float um[NS], S[NS];
+    int kl[NS];
+    const int T = cfg.T;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        // a padding sample past the end recomputes the last one (its result is not stored)
+        kl[s] = min(kl0 + s * stride, cfg.K_local - 1);
+        um[s] = (cfg.k_offset + kl[s]) < cfg.n_exploit ? 1.0f : 0.0f;
+        asm volatile("" : "+f"(um[s]));            // keep it in a register: not re-derived in every horizon step
+    }
+    if (NOISE == 0) {
+        PhiloxNoise nz[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            nz[s].nc = cfg.noise; nz[s].nc.step = (uint32_t)(*step_ctr); nz[s].env = (uint32_t)e;
+            nz[s].k = (uint32_t)(cfg.k_offset + kl[s]);
+        }
+        rollout_cost_n<NS, DYN, JL>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.srows, sb.ctl, T, um, nz, S, hits);
+    } else {
+        InjectedNoise nz[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) nz[s].row = (const float2*)eps + ((size_t)e * cfg.K_local + kl[s]) * T;
+        rollout_cost_n<NS, DYN, JL>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.srows, sb.ctl, T, um, nz, S, hits);
+    }
+    float tmin = INFINITY;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        if (kl0 + s * stride < cfg.K_local) {
+            S_out[(size_t)e * cfg.K_local + kl[s]] = S[s];
+            if (finite_(S[s])) tmin = fminf(tmin, S[s]);
+        }
+    }
+    return tmin;
+}
+
+// Two launch layouts.
+//  * Uniform (kNS = 1, and the kernels without certified lookups): grid (blocks per environment, environments), every
+//    thread takes kNS samples, grid-stride over the environment's samples.
+//  * Flat, mixed (certified kernels with kNS > 1): a 1-D grid over "units" of 128 consecutive samples, numbered through
+//    all environments (cfg.g_roll units each).  CTAs [0, n_wide) take kNS units (kNS samples per thread), the rest ONE
+//    unit (one sample per thread).  The host picks n_wide so that the LAST wave of CTAs is full: a shard of 1.0 to
+//    2.0 waves' worth of samples (131072 samples: an 8-GPU run, or 128 batched environments) runs as one wave of 432
+//    two-sample and 160 one-sample CTAs instead of 1.4 waves of one-sample CTAs.
 template <int NOISE, bool CONSTWIN, int kNS, int DYN = 0, bool CERT = true, bool JL = false>
 __global__ void __launch_bounds__(kRollThreads, CERT ? (kNS == 1 ? MPPI_ROLL_MIN_BLOCKS_CERT_NS1 : MPPI_ROLL_MIN_BLOCKS_CERT)
                                                      : (CONSTWIN ? MPPI_ROLL_MIN_BLOCKS_CONST : (kNS == 1 ? 3 : 2)))
 mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const char* __restrict__ step_blocks,
                     const float* __restrict__ eps, float* __restrict__ S_out, float* __restrict__ block_min,
-                    unsigned long long* __restrict__ search_stats, unsigned int* __restrict__ rho_key) {
+                    unsigned long long* __restrict__ search_stats, unsigned int* __restrict__ rho_key, int n_wide) {
     extern __shared__ __align__(128) unsigned char smem_roll[];
     unsigned char* smem = smem_roll;
     __shared__ uint64_t bar;
     __shared__ float red[kRollThreads / 32];
-    const int e = blockIdx.y, tid = threadIdx.x;
+    constexpr bool kFlat = CERT && kNS > 1;
+    const int tid = threadIdx.x;
+    int e = blockIdx.y, unit = 0, units = 1;          // flat layout: first unit of this CTA within its environment, and how many
+    if (kFlat) {
+        const int b = blockIdx.x;
+        const int first = b < n_wide ? b * kNS : n_wide * kNS + (b - n_wide);
+        e = first / cfg.g_roll; unit = first - e * cfg.g_roll;
+        units = b < n_wide ? kNS : 1;
+    }
     if (tid == 0) {
         mbar_init(&bar, 1);
         mbar_expect_tx(&bar, (uint32_t)cfg.step_block_bytes);
@@ -693,42 +751,23 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
 
     float tmin = INFINITY;
     const int T = cfg.T;
-    // thread handles samples kl0 + s*blockDim.x (s < NS): consecutive lanes -> consecutive samples.  The block size
-    // is a launch parameter (128, or 64 for small shards: finer CTAs spread evenly over the SMs).
+    // thread handles samples kl0 + s*blockDim.x (s < NS): consecutive lanes -> consecutive samples
     const int nthr = blockDim.x;
-    // The trip count is decided per WARP (its first lane), because the lookups vote across the warp.
-    for (int kw0 = blockIdx.x * (nthr * kNS) + (tid & ~31); kw0 < cfg.K_local; kw0 += gridDim.x * nthr * kNS) {
-        const int kl0 = kw0 + (tid & 31);
-        float um[kNS], S[kNS];
-        int kl[kNS];
-        lookups += kNS * T;
-#pragma unroll
-        for (int s = 0; s < kNS; ++s) {
-            // a padding sample past the end recomputes the last one (its result is not stored)
-            kl[s] = min(kl0 + s * nthr, cfg.K_local - 1);
-            um[s] = (cfg.k_offset + kl[s]) < cfg.n_exploit ? 1.0f : 0.0f;
-            asm volatile("" : "+f"(um[s]));            // keep it in a register: not re-derived in every horizon step
-        }
-        if (NOISE == 0) {
-            PhiloxNoise nz[kNS];
-#pragma unroll
-            for (int s = 0; s < kNS; ++s) {
-                nz[s].nc = cfg.noise; nz[s].nc.step = (uint32_t)(*step_ctr); nz[s].env = (uint32_t)e;
-                nz[s].k = (uint32_t)(cfg.k_offset + kl[s]);
-            }
-            rollout_cost_n<kNS, DYN, JL>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.srows, sb.ctl, T, um, nz, S, hits);
+    if (kFlat) {
+        const int kl0 = unit * kRollThreads + tid;
+        if (units == kNS) {
+            lookups = kNS * T;
+            tmin = roll_samples<kNS, NOISE, DYN, JL>(cfg, hd, win, cert, sb, step_ctr, eps, S_out, e, kl0, kRollThreads, hits);
         } else {
-            InjectedNoise nz[kNS];
-#pragma unroll
-            for (int s = 0; s < kNS; ++s) nz[s].row = (const float2*)eps + ((size_t)e * cfg.K_local + kl[s]) * T;
-            rollout_cost_n<kNS, DYN, JL>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.srows, sb.ctl, T, um, nz, S, hits);
+            lookups = T;
+            tmin = roll_samples<1, NOISE, DYN, JL>(cfg, hd, win, cert, sb, step_ctr, eps, S_out, e, kl0, kRollThreads, hits);
         }
-#pragma unroll
-        for (int s = 0; s < kNS; ++s) {
-            if (kl0 + s * nthr < cfg.K_local) {
-                S_out[(size_t)e * cfg.K_local + kl[s]] = S[s];
-                if (finite_(S[s])) tmin = fminf(tmin, S[s]);
-            }
+    } else {
+        // The trip count is decided per WARP (its first lane), because the lookups vote across the warp.
+        for (int kw0 = blockIdx.x * (nthr * kNS) + (tid & ~31); kw0 < cfg.K_local; kw0 += gridDim.x * nthr * kNS) {
+            lookups += kNS * T;
+            tmin = fminf(tmin, roll_samples<kNS, NOISE, DYN, JL>(cfg, hd, win, cert, sb, step_ctr, eps, S_out, e,
+                                                                 kw0 + (tid & 31), nthr, hits));
         }
     }
     tmin = warp_min(tmin);
@@ -743,7 +782,12 @@ mppi_rollout_sm100a(DevCfg cfg, const uint64_t* __restrict__ step_ctr, const cha
         float m = red[0];
 #pragma unroll
         for (int i = 1; i < nthr / 32; ++i) m = fminf(m, red[i]);
-        block_min[(size_t)e * gridDim.x + blockIdx.x] = m;
+        if (kFlat) {                                        // one slot per unit (read by the unfused soft-min kernel)
+            for (int i = 0; i < units; ++i)
+                if (unit + i < cfg.g_roll) block_min[(size_t)e * cfg.g_roll + unit + i] = m;
+        } else {
+            block_min[(size_t)e * gridDim.x + blockIdx.x] = m;
+        }
         if (finite_(m)) atomicMin(rho_key + e, min_key(m));     // what the fused weight-sum kernel reads (one word, not g_roll)
     }
 }
@@ -1032,8 +1076,8 @@ __device__ __forceinline__ void finalize_env(const DevCfg& cfg, const DevIo& io,
             arm_init(st, (float)x0[0], (float)x0[1], (float)x0[2], (float)x0[3], angle_fix(x0[0]), angle_fix(x0[0] + x0[1]));
             for (int t = 0; t < T; ++t) {
                 const int tc = t == 0 ? T - 1 : t - 1;
-                if (cfg.flags & 32) arm_step<1>(st, cfg.arm, (float)sm.unew[2 * tc], (float)sm.unew[2 * tc + 1]);   // MPPI_FLAG_DYNAMICS_F1
-                else arm_step<0>(st, cfg.arm, (float)sm.unew[2 * tc], (float)sm.unew[2 * tc + 1]);
+                if (cfg.flags & 32) arm_step_serial<1>(st, cfg.arm, (float)sm.unew[2 * tc], (float)sm.unew[2 * tc + 1]);   // MPPI_FLAG_DYNAMICS_F1
+                else arm_step_serial<0>(st, cfg.arm, (float)sm.unew[2 * tc], (float)sm.unew[2 * tc + 1]);
                 float4* o = (float4*)(sm.tr + 8 * t);
                 o[0] = make_float4(st.q1, st.q2, st.d1, st.d2);
                 o[1] = make_float4(st.kq1, st.kq2, st.kd1, st.kd2);

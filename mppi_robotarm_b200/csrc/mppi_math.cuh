@@ -276,8 +276,9 @@ MPPI_HD void arm_advance_angles(ArmState& st, const ArmF& A) {
 // DYN = 0: the arm model _F.  DYN = 1: the reference's other rollout model _F1 (control.py:265-295),
 // which forms u = M v + C dq (gravity dropped, control.py:281-284) and solves ddq = M^-1 (u - C dq):
 // ddq = v up to FP64 rounding, so the input is applied as the joint acceleration.
-template <int DYN = 0, bool TRACKQ = true>
-MPPI_HD void arm_step(ArmState& st, const ArmF& A, float v1, float v2) {
+// the joint rates of the step: d <- d + ddq dt
+template <int DYN>
+MPPI_HD void arm_rates(ArmState& st, const ArmF& A, float v1, float v2) {
     if (DYN == 1) {
 #if (MPPI_KAHAN_MASK & 1)
         kahan_(st.d1, st.kd1, fma_(v1, A.dt, -st.kd1));
@@ -285,7 +286,6 @@ MPPI_HD void arm_step(ArmState& st, const ArmF& A, float v1, float v2) {
 #else
         st.d1 = fma_(v1, A.dt, st.d1); st.d2 = fma_(v2, A.dt, st.d2);
 #endif
-        arm_advance_angles<TRACKQ>(st, A);
         return;
     }
     // cos/sin of q2 = (q1+q2) - q1 by the angle-difference identity
@@ -315,7 +315,45 @@ MPPI_HD void arm_step(ArmState& st, const ArmF& A, float v1, float v2) {
     st.d2 = fma_(n2, idt, st.d2);
 #endif
     // (the rate's own compensation term times dt, ~1e-8 * dt, is far below one ulp of q and is dropped)
+}
+
+template <int DYN = 0, bool TRACKQ = true>
+MPPI_HD void arm_step(ArmState& st, const ArmF& A, float v1, float v2) {
+    arm_rates<DYN>(st, A, v1, v2);
     arm_advance_angles<TRACKQ>(st, A);
+}
+
+// The same step for ONE trajectory computed by ONE thread (the optimal-trajectory rollout of the final stage,
+// control.py:129-134), where what counts is the length of the dependent chain, not the instruction count: sin / cos
+// of the new angles follow from the old ones by rotating through the step's increment e = dq dt (|e| <= 0.25 rad:
+// Taylor terms to e^5 / e^6, truncation < 2e-8) instead of F2I -> add -> I2FP -> polynomial.  The angles themselves
+// are still integrated (compensated floats for the output, fixed point for the exact fallback of a larger step).
+// Each rotation adds one rounding (~6e-8) to the unit vector: ~6e-7 after 100 steps, against a stated tolerance
+// of 2e-5 on the trajectory.
+MPPI_HD void rotate_small_(float& s, float& c, float e) {
+    const float e2 = mul_(e, e);
+    const float se = mul_(e, fma_(e2, fma_(e2, 8.3333333e-3f, -1.6666667e-1f), 1.0f));
+    const float ce = fma_(e2, fma_(e2, fma_(e2, -1.3888889e-3f, 4.1666668e-2f), -0.5f), 1.0f);
+    const float sn = fma_(s, ce, mul_(c, se));
+    c = fma_(c, ce, -mul_(s, se));
+    s = sn;
+}
+template <int DYN = 0>
+MPPI_HD void arm_step_serial(ArmState& st, const ArmF& A, float v1, float v2) {
+    arm_rates<DYN>(st, A, v1, v2);
+    const float e1 = mul_(st.d1, A.dt), e12 = mul_(add_(st.d1, st.d2), A.dt);
+    kahan_(st.q1, st.kq1, fma_(st.d1, A.dt, -st.kq1));
+    kahan_(st.q2, st.kq2, fma_(st.d2, A.dt, -st.kq2));
+    const int32_t i1 = f2i_rn_(mul_(st.d1, A.dtfix)), i2 = f2i_rn_(mul_(st.d2, A.dtfix));
+    st.a1 += (uint32_t)i1;
+    st.a12 += (uint32_t)i1 + (uint32_t)i2;
+    if (fmaxf(fabsf(e1), fabsf(e12)) <= 0.25f) {
+        rotate_small_(st.s1, st.c1, e1);
+        rotate_small_(st.s12, st.c12, e12);
+    } else {                                   // (also NaN)
+        sincos_fix(st.a1, st.s1, st.c1);
+        sincos_fix(st.a12, st.s12, st.c12);
+    }
 }
 
 // End-effector in window-local coordinates: (x - ox, y - oy), origin = first row of the window.

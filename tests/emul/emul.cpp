@@ -124,6 +124,29 @@ void emul_cert_probe_given(const double* ref, int n_rows, int p, const float* ce
     }
 }
 
+// The optimal-trajectory rollout of the final stage (control.py:129-134): x <- F(x, u[t-1]) with the t = 0 wrap,
+// one thread, the latency form of the step (arm_step_serial).  out[T][4] = (q1, q2, dq1, dq2) as the kernel stores
+// them (value - compensation in FP64).
+void emul_optimal_traj(const double* x0, const double* u, int T, double dt, const double* arm, double cl1, double cl2,
+                       int dynamics_f1, double* out) {
+    const double m1 = arm[0], m2 = arm[1], l1 = arm[2], l2 = arm[3], lc1 = arm[4], lc2 = arm[5], g = arm[6];
+    ArmF A;
+    A.A0 = (float)(m1 * lc1 * lc1 + l1 + m2 * (l1 * l1 + lc2 * lc2) + l2);
+    A.A1 = (float)(2 * m2 * l1 * lc2);
+    A.M22 = (float)(m2 * lc2 * lc2 + l2); A.B1 = (float)(m2 * l1 * lc2);
+    A.G1a = (float)((m1 * lc1 + m2 * l1) * g); A.G1b = (float)(m2 * lc2 * g);
+    A.dt = (float)dt; A.dtfix = arm_dtfix(dt); A.L1 = (float)cl1; A.L2 = (float)cl2;
+    ArmState st;
+    arm_init(st, (float)x0[0], (float)x0[1], (float)x0[2], (float)x0[3], angle_fix(x0[0]), angle_fix(x0[0] + x0[1]));
+    for (int t = 0; t < T; ++t) {
+        const int tc = t == 0 ? T - 1 : t - 1;
+        if (dynamics_f1) arm_step_serial<1>(st, A, (float)u[2 * tc], (float)u[2 * tc + 1]);
+        else arm_step_serial<0>(st, A, (float)u[2 * tc], (float)u[2 * tc + 1]);
+        out[4 * t + 0] = (double)st.q1 - (double)st.kq1; out[4 * t + 1] = (double)st.q2 - (double)st.kq2;
+        out[4 * t + 2] = (double)st.d1 - (double)st.kd1; out[4 * t + 3] = (double)st.d2 - (double)st.kd2;
+    }
+}
+
 void emul_sincos(const float* x, int n, float* s, float* c) { for (int i = 0; i < n; ++i) sincos_(x[i], s[i], c[i]); }
 // sin / cos as the rollouts take them: of the fixed-point image of an FP64 angle
 void emul_sincos_fix(const double* x, int n, float* s, float* c) { for (int i = 0; i < n; ++i) sincos_fix(angle_fix(x[i]), s[i], c[i]); }

@@ -335,3 +335,34 @@ def test_cost_sum_compensation_is_not_what_holds_the_tolerance(emul, paths, tmp_
         worst[mask] = w_err
     assert worst[3] <= 5e-5, worst
     assert worst[2] > worst[3], worst
+
+
+@pytest.mark.parametrize("dynamics", ["F", "F1"])
+def test_latency_form_of_the_optimal_trajectory_rollout(emul, paths, dynamics):
+    """The final stage rolls the optimal trajectory out with ONE thread (control.py:129-134) in the latency form of
+    the step (mppi_math.cuh::arm_step_serial: sin / cos advanced by rotating through the step's increment).  Against
+    the FP64 oracle on the reference's own closed-loop states and sequences, and on fast motions (increments
+    beyond 0.25 rad take the exact fallback): within the stated 2e-5 of the trajectory tolerance."""
+    with np.load(cases.HERE + "/closed_loop_c1.npz") as z:
+        cl = {k: z[k] for k in z.files}
+    arm_d = mo.default_arm_params()
+    arm = np.array([arm_d[k] for k in ("m1", "m2", "l1", "l2", "lc1", "lc2", "g")], dtype=np.float64)
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    todo = [(cl["state"][s], cl["u_new"][s], 0.006) for s in (1, 200, 700, 1400)]
+    todo += [(np.array([0.3, -0.5, 1.0, -2.0]), rng.normal(0, 20, (100, 2)), 0.006),
+             (np.array([2.0, 1.0, 25.0, -30.0]), rng.normal(0, 40, (64, 2)), 0.01),      # increments up to ~0.5 rad
+             (np.array([-3.0, 0.2, -45.0, 20.0]), rng.normal(0, 5, (50, 2)), 0.006)]
+    for x0, u, dt in todo:
+        T = u.shape[0]
+        s = tuple(float(a) for a in x0)
+        ref = np.zeros((T, 4))
+        for t in range(T):
+            s = mo.arm_step(*s, u[t - 1, 0], u[t - 1, 1], arm_d, dt, dynamics)
+            ref[t] = s
+        out = np.zeros((T, 4))
+        emul.emul_optimal_traj(dp(np.ascontiguousarray(x0, dtype=np.float64)), dp(np.ascontiguousarray(u, dtype=np.float64)),
+                               T, C.c_double(dt), dp(arm), C.c_double(1.0), C.c_double(1.0), 1 if dynamics == "F1" else 0, dp(out))
+        scale = np.maximum(1.0, np.abs(ref))
+        worst = max(worst, float(np.max(np.abs(out - ref) / scale)))
+    assert worst <= 2e-5, worst

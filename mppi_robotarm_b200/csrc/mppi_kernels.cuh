@@ -932,6 +932,7 @@ struct FinalizeSmem {
     double raw[2 * MPPI_MAX_T_INTERNAL];
     double unew[2 * MPPI_MAX_T_INTERNAL];
     __align__(16) float tr[8 * MPPI_MAX_T_INTERNAL];    // optimal trajectory: (value, compensation) per state and step
+    __align__(8) float vf[2 * MPPI_MAX_T_INTERNAL];     // the updated sequence in FP32, in the order the trajectory applies it
     double scale[64];
     double eta_s;
     int timed_out;
@@ -1070,17 +1071,27 @@ __device__ __forceinline__ void finalize_env(const DevCfg& cfg, const DevIo& io,
     // memory; all threads then convert and store the trajectory (keeps global / PCIe stores off the chain).
     MPPI_FPHASE(4);
     if (cfg.flags & 1) {
+        // controls in the order of use (t = 0 wraps to the last one, Q3), converted once by all threads: the serial
+        // loop then only waits for arithmetic — its loads run one step ahead of their use
+        for (int t = tid; t < T; t += blockDim.x) {
+            const int tc = t == 0 ? T - 1 : t - 1;
+            ((float2*)sm.vf)[t] = make_float2((float)sm.unew[2 * tc], (float)sm.unew[2 * tc + 1]);
+        }
+        __syncthreads();
         if (tid == 0) {
             const double* x0 = io.x0 + 4 * e;
             ArmState st;
             arm_init(st, (float)x0[0], (float)x0[1], (float)x0[2], (float)x0[3], angle_fix(x0[0]), angle_fix(x0[0] + x0[1]));
+            const bool f1 = (cfg.flags & 32) != 0;                       // MPPI_FLAG_DYNAMICS_F1
+            float2 v = ((const float2*)sm.vf)[0];
             for (int t = 0; t < T; ++t) {
-                const int tc = t == 0 ? T - 1 : t - 1;
-                if (cfg.flags & 32) arm_step_serial<1>(st, cfg.arm, (float)sm.unew[2 * tc], (float)sm.unew[2 * tc + 1]);   // MPPI_FLAG_DYNAMICS_F1
-                else arm_step_serial<0>(st, cfg.arm, (float)sm.unew[2 * tc], (float)sm.unew[2 * tc + 1]);
+                const float2 vn = ((const float2*)sm.vf)[t + 1 < T ? t + 1 : t];
+                if (f1) arm_step_serial<1>(st, cfg.arm, v.x, v.y);
+                else arm_step_serial<0>(st, cfg.arm, v.x, v.y);
                 float4* o = (float4*)(sm.tr + 8 * t);
                 o[0] = make_float4(st.q1, st.q2, st.d1, st.d2);
                 o[1] = make_float4(st.kq1, st.kq2, st.kd1, st.kd2);
+                v = vn;
             }
         }
         __syncthreads();

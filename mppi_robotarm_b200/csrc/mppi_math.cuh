@@ -347,10 +347,9 @@ MPPI_HD void arm_step_serial(ArmState& st, const ArmF& A, float v1, float v2) {
     const int32_t i1 = f2i_rn_(mul_(st.d1, A.dtfix)), i2 = f2i_rn_(mul_(st.d2, A.dtfix));
     st.a1 += (uint32_t)i1;
     st.a12 += (uint32_t)i1 + (uint32_t)i2;
-    if (fmaxf(fabsf(e1), fabsf(e12)) <= 0.25f) {
-        rotate_small_(st.s1, st.c1, e1);
-        rotate_small_(st.s12, st.c12, e12);
-    } else {                                   // (also NaN)
+    rotate_small_(st.s1, st.c1, e1);
+    rotate_small_(st.s12, st.c12, e12);
+    if (!(fmaxf(fabsf(e1), fabsf(e12)) <= 0.25f)) {        // rare (also NaN): the exact values
         sincos_fix(st.a1, st.s1, st.c1);
         sincos_fix(st.a12, st.s12, st.c12);
     }

@@ -746,6 +746,37 @@ def test_certified_search_is_bit_identical_to_the_full_search(paths, K, T, s, no
         assert a[5]["fraction"] > 0.6, a[5]      # most of a long horizon lies beyond the 30-row window
 
 
+@pytest.mark.parametrize("K,T,n_env,noise", [
+    (200003, 12, 1, "philox"),      # 1563 units of 128 samples: one full wave of two-sample CTAs + 379 one-sample CTAs, partial last unit
+    (113000, 20, 1, "injected"),    # 883 units: a single mixed wave (291 two-sample + 301 one-sample CTAs)
+    (32768, 10, 6, "philox"),       # batched, 1536 units over 6 environments: the flat layout crosses environments
+])
+def test_rollout_launch_layouts_give_the_same_costs(paths, monkeypatch, K, T, n_env, noise):
+    """The launch layout of the rollout kernel (mppi_cabi.cu::pick_layout: one sample per thread / two samples per
+    thread / the mixed last wave) only decides which thread computes which sample: costs, weights and the update are
+    the same floats in all three."""
+    with np.load(cases.HERE + "/closed_loop_c1.npz") as z:
+        cl = {k: z[k] for k in z.files}
+    x0, u, p = _tracking_state(cl, 500, T)
+    out = {}
+    for name, env in (("default", {}), ("one", {"MPPI_NS": "1"}), ("two", {"MPPI_NO_MIXED": "1"})):
+        for k in ("MPPI_NS", "MPPI_NO_MIXED"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng = _engine(paths, K, T, n_env=n_env)
+        eps = eng.philox_noise(step=0) if noise == "injected" else None
+        eng.step(np.tile(x0, (n_env, 1)) if n_env > 1 else x0, np.tile(u, (n_env, 1, 1)) if n_env > 1 else u,
+                 np.full(n_env, p) if n_env > 1 else p, eps)
+        S, w = (t.cpu().numpy().copy() for t in eng.last_costs())
+        out[name] = (S, w, eng.out_u_new.copy(), eng.out_rho.copy(), eng.out_eta.copy())
+        eng.close()
+    assert np.all(np.isfinite(out["default"][0])) and out["default"][0].shape[-1] == K
+    for name in ("one", "two"):
+        for i in range(5):
+            assert np.array_equal(out["default"][i], out[name][i]), (name, i)
+
+
 def test_certified_search_batched_environments(paths):
     """n_env > 1: every environment has its own window and certificate (step block in shared memory)."""
     from mppi_robotarm_b200.batched import BatchedMPPIController

@@ -569,13 +569,31 @@ __global__ void __launch_bounds__(32) mppi_prepare_sm100a(DevCfg cfg, DevIo io, 
 // ================================================================================================
 constexpr int kRollThreads = 128;
 
+// MPPI_NOISE_AHEAD: the draw for horizon steps t+2, t+3 is issued at step t, next to the dynamics of step t instead
+// of at the head of the dependent chain of step t+2 (Philox rounds -> Box-Muller -> input -> rates): the same calls
+// on the same counters, so the same floats.  One call past the end of the horizon is drawn and dropped.
+#ifndef MPPI_NOISE_AHEAD
+#define MPPI_NOISE_AHEAD 1
+#endif
 struct PhiloxNoise {            // eps drawn in-kernel: one Philox call serves two horizon steps
     NoiseCfg nc; uint32_t env, k;
     float e1a, e1b;
+#if MPPI_NOISE_AHEAD
+    float n0a, n0b, n1a, n1b;   // the pair after the current one
+    __device__ __forceinline__ void prime() { noise_pair(nc, env, k, 0u, n0a, n0b, n1a, n1b); }
+    __device__ __forceinline__ void operator()(int t, float& a, float& b) {
+        if ((t & 1) == 0) {
+            a = n0a; b = n0b; e1a = n1a; e1b = n1b;
+            noise_pair(nc, env, k, ((uint32_t)t >> 1) + 1u, n0a, n0b, n1a, n1b);
+        } else { a = e1a; b = e1b; }
+    }
+#else
+    __device__ __forceinline__ void prime() {}
     __device__ __forceinline__ void operator()(int t, float& a, float& b) {
         if ((t & 1) == 0) noise_pair(nc, env, k, (uint32_t)t >> 1, a, b, e1a, e1b);
         else { a = e1a; b = e1b; }
     }
+#endif
 };
 struct InjectedNoise {          // eps read from the caller's [K,T,2] tensor
     const float2* row;
@@ -686,6 +704,7 @@ __device__ __forceinline__ float roll_samples(const DevCfg& cfg, const StepHeade
         for (int s = 0; s < NS; ++s) {
             nz[s].nc = cfg.noise; nz[s].nc.step = (uint32_t)(*step_ctr); nz[s].env = (uint32_t)e;
             nz[s].k = (uint32_t)(cfg.k_offset + kl[s]);
+            nz[s].prime();
         }
         rollout_cost_n<NS, DYN, JL>(hd, cfg.arm, cfg.cost, win, cert, sb.rows, sb.srows, sb.ctl, T, um, nz, S, hits);
     } else {

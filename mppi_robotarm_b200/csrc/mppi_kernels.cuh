@@ -1102,11 +1102,19 @@ __device__ __forceinline__ void finalize_env(const DevCfg& cfg, const DevIo& io,
             ArmState st;
             arm_init(st, (float)x0[0], (float)x0[1], (float)x0[2], (float)x0[3], angle_fix(x0[0]), angle_fix(x0[0] + x0[1]));
             const bool f1 = (cfg.flags & 32) != 0;                       // MPPI_FLAG_DYNAMICS_F1
+            // the arm constants in registers: left to itself the compiler re-loads four of them from the constant bank
+            // (LDC, a memory-path load) at the head of every iteration of this latency-bound loop
+            // (a one-lane shuffle: the only form ptxas does not see through and turn back into LDC)
+            ArmF A = cfg.arm;
+#ifndef MPPI_TRAJ_LDC
+            A.A0 = __shfl_sync(1u, A.A0, 0); A.A1 = __shfl_sync(1u, A.A1, 0);
+            A.M22 = __shfl_sync(1u, A.M22, 0); A.B1 = __shfl_sync(1u, A.B1, 0);
+#endif
             float2 v = ((const float2*)sm.vf)[0];
             for (int t = 0; t < T; ++t) {
                 const float2 vn = ((const float2*)sm.vf)[t + 1 < T ? t + 1 : t];
-                if (f1) arm_step_serial<1>(st, cfg.arm, v.x, v.y);
-                else arm_step_serial<0>(st, cfg.arm, v.x, v.y);
+                if (f1) arm_step_serial<1>(st, A, v.x, v.y);
+                else arm_step_serial<0>(st, A, v.x, v.y);
                 float4* o = (float4*)(sm.tr + 8 * t);
                 o[0] = make_float4(st.q1, st.q2, st.d1, st.d2);
                 o[1] = make_float4(st.kq1, st.kq2, st.kd1, st.kd2);

@@ -942,6 +942,10 @@ mppi_wsum_injected_sm100a(DevCfg cfg, const float* __restrict__ w, const float* 
 //    median-filter, update the sequence, roll the optimal trajectory out (control.py:122-134).
 // ================================================================================================
 __device__ __forceinline__ int reflect_idx(int i, int n) {          // scipy 'reflect': d c b a | a b c d | d c b a
+    if (n >= kFilter) {                     // |overhang| < n: one mirror about either end, no division
+        i = i < 0 ? -1 - i : i;
+        return i >= n ? 2 * n - 1 - i : i;
+    }
     const int period = 2 * n;
     i %= period; if (i < 0) i += period;
     return i >= n ? period - 1 - i : i;
@@ -969,6 +973,8 @@ __device__ __forceinline__ unsigned long long global_ns() {
 __device__ __forceinline__ void finalize_env(const DevCfg& cfg, const DevIo& io, int e, const double* gathered, int world,
                                              const PeerExchange& px, FinalizeSmem& sm) {
     const int tid = threadIdx.x, T = cfg.T;
+    // the nominal control this thread updates below: loaded now, so that the L2 round trip is over by then
+    const double u_first = tid < 2 * T ? io.u_prev[(size_t)e * 2 * T + tid] : 0.0;
 #ifdef MPPI_PHASE_PRINT
     unsigned long long fp[8]; fp[0] = global_ns();
 #define MPPI_FPHASE(i) fp[i] = global_ns()
@@ -1000,6 +1006,21 @@ __device__ __forceinline__ void finalize_env(const DevCfg& cfg, const DevIo& io,
     const bool skip = sm.timed_out != 0;
     const size_t stride_rank = (size_t)cfg.n_env * (2 + 2 * T);
     const double* g0 = gathered + (size_t)e * (2 + 2 * T);
+#ifndef MPPI_COMBINE_GENERAL
+    if (world == 1) {
+        // one GPU: rho = rho_0, the rescaling factor is exp(-0) = 1 and eta = 1 * eta_0 — the same values as the
+        // general form below without its FP64 exp and minimum on the latency path
+        if (tid == 0) {
+            const double rho = g0[0], d = rho - rho;          // 0, or NaN for a shard without a finite cost
+            const double sc = d == 0.0 ? 1.0 : d, eta = sc * g0[1];
+            sm.scale[0] = sc;
+            sm.eta_s = eta;
+            const double nan = __longlong_as_double(0x7ff8000000000000ll);
+            out_store(io, io.rho + e, skip ? nan : rho); out_store(io, io.eta + e, skip ? nan : eta);
+            out_store(io, io.status + e, skip ? 1 : 0);
+        }
+    } else
+#endif
     if (tid < 32) {
         // one lane per rank: its minimum, and its rescaling factor (an FP64 exp each — side by side, not one after the
         // other); lane 0 then adds the weight sums in rank order
@@ -1054,6 +1075,7 @@ __device__ __forceinline__ void finalize_env(const DevCfg& cfg, const DevIo& io,
             double win[kFilter];
 #pragma unroll
             for (int o = 0; o < kFilter; ++o) win[o] = sm.raw[2 * reflect_idx(t + o - kFilter / 2, T) + m];
+#ifdef MPPI_MEDIAN_BY_RANK
             med = win[0];
 #pragma unroll
             for (int a = 0; a < kFilter; ++a) {
@@ -1062,8 +1084,26 @@ __device__ __forceinline__ void finalize_env(const DevCfg& cfg, const DevIo& io,
                 for (int b = 0; b < kFilter; ++b) rank += (win[b] < win[a]) || (win[b] == win[a] && b < a);
                 if (rank == kFilter / 2) med = win[a];
             }
+#else
+            // element of rank 5 by a 29-exchange sorting network for ten inputs (verified by the 0-1 principle,
+            // tests/test_host_cpu.py); the VALUE of that rank does not depend on how ties are ordered.  The
+            // exchanges that cannot reach output 5 are removed by the compiler.  (58 FP64 min / max for ~250
+            // compares of the rank count.)
+            static_assert(kFilter == 10, "the network below sorts ten inputs");
+#define MPPI_CE(a, b) { const double lo_ = fmin(win[a], win[b]), hi_ = fmax(win[a], win[b]); win[a] = lo_; win[b] = hi_; }
+            MPPI_CE(0, 8) MPPI_CE(1, 9) MPPI_CE(2, 7) MPPI_CE(3, 5) MPPI_CE(4, 6)
+            MPPI_CE(0, 2) MPPI_CE(1, 4) MPPI_CE(5, 8) MPPI_CE(7, 9)
+            MPPI_CE(0, 3) MPPI_CE(2, 4) MPPI_CE(5, 7) MPPI_CE(6, 9)
+            MPPI_CE(0, 1) MPPI_CE(3, 6) MPPI_CE(8, 9)
+            MPPI_CE(1, 5) MPPI_CE(2, 3) MPPI_CE(4, 8) MPPI_CE(6, 7)
+            MPPI_CE(1, 2) MPPI_CE(3, 5) MPPI_CE(4, 6) MPPI_CE(7, 8)
+            MPPI_CE(2, 3) MPPI_CE(4, 5) MPPI_CE(6, 7)
+            MPPI_CE(3, 4) MPPI_CE(5, 6)
+#undef MPPI_CE
+            med = win[kFilter / 2];
+#endif
         }
-        const double u = io.u_prev[(size_t)e * 2 * T + c] + med;        // control.py:126
+        const double u = (c == tid ? u_first : io.u_prev[(size_t)e * 2 * T + c]) + med;        // control.py:126
         sm.unew[c] = u;
         out_store(io, io.w_eps_filt + (size_t)e * 2 * T + c, med);
         out_store(io, io.u_new + (size_t)e * 2 * T + c, u);

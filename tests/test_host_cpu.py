@@ -133,3 +133,23 @@ def test_noise_factor_handles_definite_semidefinite_and_rejects_asymmetric():
         noise_factor(np.array([[10.0, 10.0], [100.0, 100.0]]))       # the reference's (unusable) default Sigma: asymmetric
     with pytest.raises(np.linalg.LinAlgError):
         noise_factor(np.array([[1.0, 2.0], [2.0, 1.0]]))             # indefinite
+
+
+def test_median_network_of_the_final_stage_sorts_ten_inputs():
+    """The final stage takes the rank-5 element of each 10-sample window (scipy.ndimage.median_filter(size=10),
+    control.py:319-327) from a sorting network written out in the kernel source: parse the exchanges from that source
+    and check them by the 0-1 principle (a network that sorts every 0/1 input sorts every input)."""
+    import itertools
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(__file__), "..", "mppi_robotarm_b200", "csrc", "mppi_kernels.cuh")).read()
+    body = src[src.index("#define MPPI_CE(a, b)"):src.index("#undef MPPI_CE")]
+    ces = [(int(a), int(b)) for a, b in re.findall(r"MPPI_CE\((\d+), (\d+)\)", body)]
+    assert len(ces) == 29 and all(0 <= a < b < 10 for a, b in ces)
+    for bits in itertools.product((0, 1), repeat=10):
+        v = list(bits)
+        for a, b in ces:
+            if v[a] > v[b]:
+                v[a], v[b] = v[b], v[a]
+        assert v == sorted(v)
+    assert "med = win[kFilter / 2];" in src

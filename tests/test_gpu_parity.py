@@ -211,9 +211,10 @@ def test_full_size_config4_properties(paths):
     eng2.close()
 
 
-@pytest.mark.parametrize("K,T", [(200, 1), (200, 2), (64, 255), (64, 256), (1, 30), (33, 9)])
+@pytest.mark.parametrize("K,T", [(200, 1), (200, 2), (64, 255), (64, 256), (1, 30), (33, 9), (40, 10), (40, 11), (40, 5)])
 def test_extreme_horizons_and_tiny_sample_counts(paths, K, T):
-    """Edges of the supported shape range (T = 1 .. MPPI_MAX_T, K = 1) against the oracle."""
+    """Edges of the supported shape range (T = 1 .. MPPI_MAX_T, K = 1; T around the filter width, where the final
+    stage switches between its two forms of the mirror index) against the oracle."""
     case = dict(name="edge", file="xydq_circle.txt", K=K, T=T, ctor=dict(param_lambda=3.0e4))
     ctrl, kw = H.make_controller(case, paths)
     eps = mo.injected_noise(5, K, T, kw["sigma"])

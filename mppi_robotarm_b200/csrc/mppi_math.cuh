@@ -327,7 +327,7 @@ MPPI_HD void arm_step(ArmState& st, const ArmF& A, float v1, float v2) {
 // control.py:129-134), where what counts is the length of the dependent chain, not the instruction count: sin / cos
 // of the new angles follow from the old ones by rotating through the step's increment e = dq dt (|e| <= 0.25 rad:
 // Taylor terms to e^5 / e^6, truncation < 2e-8) instead of F2I -> add -> I2FP -> polynomial.  The angles themselves
-// are still integrated (compensated floats for the output, fixed point for the exact fallback of a larger step).
+// are still integrated (compensated floats: for the output, and for the exact fallback of a larger step).
 // Each rotation adds one rounding (~6e-8) to the unit vector: ~6e-7 after 100 steps, against a stated tolerance
 // of 2e-5 on the trajectory.
 MPPI_HD void rotate_small_(float& s, float& c, float e) {
@@ -344,12 +344,13 @@ MPPI_HD void arm_step_serial(ArmState& st, const ArmF& A, float v1, float v2) {
     const float e1 = mul_(st.d1, A.dt), e12 = mul_(add_(st.d1, st.d2), A.dt);
     kahan_(st.q1, st.kq1, fma_(st.d1, A.dt, -st.kq1));
     kahan_(st.q2, st.kq2, fma_(st.d2, A.dt, -st.kq2));
-    const int32_t i1 = f2i_rn_(mul_(st.d1, A.dtfix)), i2 = f2i_rn_(mul_(st.d2, A.dtfix));
-    st.a1 += (uint32_t)i1;
-    st.a12 += (uint32_t)i1 + (uint32_t)i2;
     rotate_small_(st.s1, st.c1, e1);
     rotate_small_(st.s12, st.c12, e12);
     if (!(fmaxf(fabsf(e1), fabsf(e12)) <= 0.25f)) {        // rare (also NaN): the exact values
+        // of the compensated float angles (value = q - kq, held to ~1e-8 relative), reduced in FP64: the serial loop does
+        // not carry the fixed-point pair (7 instructions per step on a chain that is all latency)
+        const double q1 = (double)st.q1 - (double)st.kq1, q2 = (double)st.q2 - (double)st.kq2;
+        st.a1 = angle_fix(q1); st.a12 = angle_fix(q1 + q2);
         sincos_fix(st.a1, st.s1, st.c1);
         sincos_fix(st.a12, st.s12, st.c12);
     }
